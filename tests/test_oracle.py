@@ -1,0 +1,124 @@
+"""The oracle (oracle/rpc_oracle.py) against the golden fixtures produced by the unmodified
+reference (tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from make_golden import CASES, KERNEL_CASES, golden_inputs, kernel_inputs
+from oracle import rpc_oracle as orc
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name + ".npz"))
+
+
+def relerr(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def run_oracle(spec):
+    inp = golden_inputs(spec)
+    A = orc.OracleDenseMatrix(inp["dense"]) if "dense" in inp else orc.OracleKernelMatrix(
+        inp["X"], kernel=inp["kernel"], bandwidth=inp["bandwidth"], **inp["kw"])
+    rng, legacy = orc.make_streams(spec["seed"])
+    kw = {"stoptol": spec["stoptol"]} if "stoptol" in spec else {}
+    if spec["alg"] == "simple":
+        res = orc.simple_rpcholesky(A, spec["k"], rng, **kw)
+    elif spec["alg"] == "block":
+        res = orc.block_rpcholesky(A, spec["k"], spec["b"], rng, **kw)
+    else:
+        res = orc.accelerated_rpcholesky(A, spec["k"], spec["b"], rng, legacy, **kw)
+    return A, res
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_factorisation_matches_reference(name):
+    spec = CASES[name]
+    gold = load(name)
+    A, res = run_oracle(spec)
+    assert np.array_equal(np.asarray(res.idx, dtype=np.int64), gold["idx"])          # pivots bit-exact
+    assert res.G.shape == gold["G"].shape and res.rows.shape == gold["rows"].shape
+    assert relerr(res.G, gold["G"]) <= 1e-12
+    assert relerr(res.rows, gold["rows"]) <= 1e-13
+    assert abs(res.trace() - float(gold["trace"])) <= 1e-12 * abs(float(gold["trace"]))
+    if "queries" in gold:
+        assert A.num_queries() == int(gold["queries"])
+
+
+@pytest.mark.parametrize("name", sorted(KERNEL_CASES))
+def test_kernel_values_match_reference(name):
+    spec = KERNEL_CASES[name]
+    gold = load(name)
+    X, idx, kw = kernel_inputs(spec)
+    A = orc.OracleKernelMatrix(X, kernel=spec["kernel"], bandwidth=spec["bw"], **kw)
+    # same BLAS/numpy calls in the same order -> expect (near) bit equality
+    np.testing.assert_allclose(A.rows(idx), gold["rows"], rtol=1e-14, atol=1e-16)
+    np.testing.assert_allclose(A.block(idx), gold["block"], rtol=1e-14, atol=1e-16)
+    np.testing.assert_array_equal(A.diag(), gold["diag"])
+    np.testing.assert_allclose(A.rows(int(idx[3]))[0], gold["one_row"], rtol=1e-14, atol=1e-16)
+
+
+def test_manhattan_is_sequential_cdist():
+    from scipy.spatial.distance import cdist
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((9, 50)); Y = rng.standard_normal((200, 50))
+    assert np.array_equal(orc.manhattan_distances(X, Y), cdist(X, Y, "cityblock"))
+
+
+def test_euclidean_matches_sklearn():
+    from sklearn.metrics.pairwise import euclidean_distances
+    rng = np.random.default_rng(4)
+    X = rng.standard_normal((11, 20)); Y = rng.standard_normal((300, 20))
+    assert np.array_equal(orc.euclidean_distances(X, Y), euclidean_distances(X, Y))
+
+
+@pytest.mark.parametrize("tag", ["uniform", "random", "sparse"])
+def test_sampler_is_generator_choice(tag):
+    gold = load("sampler")
+    idx = orc.sample_pivots(gold[tag + "_diag"], gold[tag + "_u"])
+    assert np.array_equal(idx, gold[tag + "_idx"])
+
+
+def test_sampler_live_against_numpy():
+    rng = np.random.default_rng(8)
+    for n in (1, 2, 100, 5000):
+        diag = rng.random(n)
+        a = np.random.Generator(np.random.PCG64(1)).choice(range(n), size=64, p=diag / sum(diag), replace=True)
+        b = orc.sample_pivots(diag, np.random.Generator(np.random.PCG64(1)).random(64))
+        assert np.array_equal(a, b)
+        # scalar draw = one double of the stream
+        g1 = np.random.Generator(np.random.PCG64(2)); g2 = np.random.Generator(np.random.PCG64(2))
+        assert g1.choice(range(n), p=diag / sum(diag)) == orc.sample_pivots(diag, [g2.random()])[0]
+        assert g1.random() == g2.random()
+
+
+def test_seq_sum_is_builtin_sum():
+    rng = np.random.default_rng(9)
+    for n in (1, 17, 1000, 100003):
+        v = rng.random(n) ** 3
+        assert orc.seq_sum(v) == sum(v)
+
+
+def test_sampler_raises_like_choice():
+    with pytest.raises(ValueError):
+        orc.sample_pivots(np.zeros(10), [0.5])
+    with pytest.raises(ValueError):
+        orc.sample_pivots(np.array([1.0, np.nan]), [0.5])
+
+
+def test_rejection_cholesky_properties():
+    rng = np.random.default_rng(10)
+    B = rng.standard_normal((30, 12)); H = B @ B.T      # rank 12 < 30
+    H0 = H.copy()
+    L, acc = orc.rejection_cholesky(H, np.zeros(30))    # u = 0 -> accept while the residual is positive
+    assert len(acc) >= 12
+    L2, acc2 = orc.rejection_cholesky(H0.copy(), rng.random(30))
+    np.testing.assert_allclose(L2 @ L2.T, H0[np.ix_(acc2, acc2)], atol=1e-10)
+    assert np.allclose(L2, np.tril(L2))
+    with pytest.raises(RuntimeError):
+        orc.rejection_cholesky(-np.eye(3), np.zeros(3))
+    with pytest.raises(RuntimeError):
+        orc.rejection_cholesky(np.ones((2, 3)), np.zeros(2))
