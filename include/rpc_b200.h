@@ -1,0 +1,154 @@
+/*
+ * rpc_b200.h -- C ABI of the B200 (sm_100a) RPCholesky hot path.
+ *
+ * The reference (eepperly/Randomly-Pivoted-Cholesky) is pure Python and has no FFI layer; its
+ * boundary is the Python operator protocol (matrix.py) plus the three factorisation loops
+ * (rpcholesky.py).  Every entry point below replaces ONE numpy/scipy/sklearn call site of that
+ * path; the site is cited next to the prototype as `file:line` relative to the reference root.
+ * The Python host in randomly_pivoted_cholesky_b200/ binds these with ctypes.
+ *
+ * Conventions
+ *   - all matrices are float64, row-major, with an explicit leading dimension in ELEMENTS;
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *     unless the prototype says so;
+ *   - return value: 0 = ok, <0 = bad argument, >0 = CUDA error code; rpc_last_error() returns a
+ *     thread-local description.  Nothing throws across the boundary;
+ *   - the caller owns every buffer; the library only owns the scratch inside rpc_ctx;
+ *   - one rpc_ctx per device, not thread-safe.
+ *   - "padded" operands: X, G, rows and diag are allocated by the host with n_pad = a multiple of
+ *     RPC_COL_ALIGN columns/points; pad points are all-zero, pad diagonal entries are 0 so they are
+ *     never sampled.  Kernels run over n_pad columns without edge checks.
+ */
+#ifndef RPC_B200_H
+#define RPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RPC_ABI_VERSION 1
+#define RPC_COL_ALIGN 128   /* n_pad granularity (widest column tile of the DMMA kernels) */
+#define RPC_FEAT_ALIGN 4    /* d_pad granularity (one DMMA k-step) */
+#define RPC_KT 16           /* k-depth of one shared-memory stage; panel K is padded to this */
+
+/* kernel functions, reference kernels.py */
+#define RPC_KERN_GAUSSIAN 0 /* kernels.py:32-39 */
+#define RPC_KERN_LAPLACE 1  /* kernels.py:16-21 */
+#define RPC_KERN_MATERN 2   /* kernels.py:71-85, nu2 in {1,3,5} = 2*nu */
+
+typedef struct rpc_ctx rpc_ctx;
+
+typedef struct rpc_kernel_spec {
+    int32_t kind;            /* RPC_KERN_* */
+    int32_t nu2;             /* Matern: 2*nu in {1,3,5}; ignored otherwise */
+    int32_t extra_stability; /* kernels.py:35-36,74-75: direct-difference distance */
+    int32_t reserved;
+    double bandwidth;
+} rpc_kernel_spec;
+
+int rpc_abi_version(void);
+const char *rpc_last_error(void);
+
+int rpc_ctx_create(int device, rpc_ctx **out);
+int rpc_ctx_destroy(rpc_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t rpc_ctx_launch_count(const rpc_ctx *ctx);
+
+/* ---- kernel evaluator: KernelMatrix.__getitem__ / diag (matrix.py:122-138,185-189) ---------- */
+
+/* xnorm[i] = sum_f X[i,f]^2 : sklearn row_norms(X, squared=True) inside euclidean_distances
+ * (called from kernels.py:38,77). */
+int rpc_row_norms(rpc_ctx *ctx, void *stream, const double *X, int64_t n, int d, int64_t ldx, double *xnorm);
+
+/* A.diag() for the built-in kernels: distance exactly 0 -> exactly 1.0 (kernels.py:11-14,27-30,56-66).
+ * Entries [n, n_pad) are set to 0. */
+int rpc_kernel_diag(rpc_ctx *ctx, void *stream, double *diag, int64_t n, int64_t n_pad);
+
+/* out[j, i] = k(Xpiv[j,:], X[i,:]) for j<s, i<n_pad : A[idx,:] -> kernel_mtx(X[idx], X)
+ * (matrix.py:188-189 -> kernels.py:16-21 / 32-39 / 71-85).  Gaussian/Matern without
+ * extra_stability use D2 = ((-2 x.y) + |x|^2) + |y|^2 clamped at 0 (sklearn euclidean_distances)
+ * with the x.y contraction on FP64 tensor cores (DMMA); Laplace sums |x_f - y_f| in feature order
+ * (scipy cdist 'cityblock').  d must be a multiple of RPC_FEAT_ALIGN (zero-padded features). */
+int rpc_kernel_rows(rpc_ctx *ctx, void *stream, const rpc_kernel_spec *spec, const double *X, const double *xnorm,
+                    int64_t n_pad, int d, int64_t ldx, const double *Xpiv, const double *pnorm, int s, int64_t ldp,
+                    double *out, int64_t ldo);
+
+/* H[i, j] = k(Xpiv[i,:], Xpiv[j,:]) : A[idx,idx] outer block (matrix.py:99,135; rpcholesky.py:189). */
+int rpc_kernel_block(rpc_ctx *ctx, void *stream, const rpc_kernel_spec *spec, const double *Xpiv, const double *pnorm,
+                     int b, int d, int64_t ldp, double *H, int64_t ldh);
+
+/* Dense PSDMatrix operator (matrix.py:86-102): diag gather, row gather A[idx,:], block A[idx,idx]. */
+int rpc_psd_diag(rpc_ctx *ctx, void *stream, const double *A, int64_t n, int64_t lda, double *diag, int64_t n_pad);
+int rpc_psd_rows(rpc_ctx *ctx, void *stream, const double *A, int64_t n, int64_t lda, const int64_t *idx, int s,
+                 double *out, int64_t ldo, int64_t n_pad);
+int rpc_psd_block(rpc_ctx *ctx, void *stream, const double *A, int64_t lda, const int64_t *idx, int b, double *H,
+                  int64_t ldh);
+
+/* ---- pivot sampler: rng.choice(range(n), size=m, p=diags/sum(diags)) (rpcholesky.py:31,91,184) -- */
+
+/* idx[j] = #{ i : cdf[i] <= u[j] } with cdf the normalised prefix sums of diag[0:n_pad].
+ * A blocked parallel scan picks the index; any draw whose decision lies inside the rounding band
+ * of numpy's sequential cumsum is re-resolved ON THE DEVICE by a kernel that replays numpy's
+ * sequential arithmetic exactly (python sum -> p = d/S -> cumsum -> /cdf[-1] -> searchsorted right),
+ * so the pivots are bit-identical to the reference's for the same uniforms.
+ * stats[0] = sum(diag) (blocked order), stats[1] = 1.0 if the probabilities are invalid
+ * (sum <= 0 or NaN: numpy raises ValueError), stats[2] = number of draws re-resolved exactly. */
+int rpc_sample_pivots(rpc_ctx *ctx, void *stream, const double *diag, int64_t n_pad, const double *u, int m,
+                      int64_t *idx, double *stats);
+
+/* ---- per-round small dense work (rpcholesky.py:102-107, 140-157, 189-190, 206-207) -------------- */
+
+/* Xpiv[j,:] = X[idx[j],:], pnorm[j] = xnorm[idx[j]] (matrix.py:189 `self.data[vec_i,:]`) and
+ * P[r, j] = G[r, idx[j]] for r<c (rpcholesky.py:102,189,206 `G[0:counter, idx]`).
+ * X/xnorm may be NULL (dense operator), G may be NULL when c == 0. */
+int rpc_gather_pivots(rpc_ctx *ctx, void *stream, const int64_t *idx, int m, const double *X, const double *xnorm,
+                      int d, int64_t ldx, double *Xpiv, double *pnorm, int64_t ldp, const double *G, int64_t ldg,
+                      int c, double *P, int64_t ldP);
+
+/* H -= P^T P (H is m x m, P is c x m): residual Gram of the proposals (rpcholesky.py:189). */
+int rpc_gram_residual(rpc_ctx *ctx, void *stream, const double *P, int c, int m, int64_t ldP, double *H, int64_t ldh);
+
+/* rejection_cholesky(H) (rpcholesky.py:140-157) with u[j] replacing the j-th np.random.rand().
+ * mode 0: rejection sampling; accepted positions -> acc[0:s] (ascending), stops after max_accept
+ *         (the truncation of rpcholesky.py:193-196).
+ * mode 1: plain Cholesky of H + shift*I (block RPCholesky, rpcholesky.py:106); info[1] = index+1 of
+ *         the first non-positive pivot (numpy would raise LinAlgError), else 0.
+ * L (ldl >= m) receives the s x s lower-triangular factor L[acc,acc] (zeros above the diagonal).
+ * info[0] = s, info[2] = 1 if trace(H) <= 0 (RuntimeError at rpcholesky.py:145). */
+int rpc_rejection_cholesky(rpc_ctx *ctx, void *stream, double *H, int m, int64_t ldh, const double *u, int max_accept,
+                           int mode, double shift, double *L, int64_t ldl, int32_t *acc, int32_t *info);
+
+/* Panel for the fused Schur update.  With Minv = L^{-1} (mode 0) or Minv = T given (mode 1, the
+ * eigh fallback of rpcholesky.py:109-114):
+ *    At[r, j]     = -sum_i P[r, acc[i]] * Minv[j, i]   r < c       (= -(P_acc Minv^T))
+ *    At[c + i, j] = Minv[j, i]                          i < s
+ *    zero elsewhere (rows up to k_pad, columns up to m_pad).
+ * so that G_new = At^T [G[:c]; rows_new] = L^{-1} (rows_new - P_acc^T G[:c])
+ * (rpcholesky.py:102+107, 206+207; np.linalg.solve replaced by the explicit small inverse).
+ * acc may be NULL (= identity selection). */
+int rpc_build_panel(rpc_ctx *ctx, void *stream, const double *P, int64_t ldP, int c, const int32_t *acc, int s,
+                    const double *L, int64_t ldl, int mode, double *At, int64_t ldat, int k_pad);
+
+/* ---- the N-proportional update (rpcholesky.py:41-43, 102-107+128-129, 206-209) ---------------- */
+
+/* G[c:c+s, :] = At^T [G[0:c, :]; rows_new] ; diag = max(diag - colsum(G[c:c+s,:]^2), 0).
+ * FP64 DMMA GEMM (M = s, K = c + s, N = n_pad) with the diagonal update fused in the epilogue.
+ * G rows [c, c+s) are written; rows_new is s x n_pad (normally rows + c*ldr). */
+int rpc_schur_update(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At, int64_t ldat,
+                     int k_pad, const double *rows_new, int64_t ldr, double *diag, int64_t n_pad);
+
+/* One step of simple RPCholesky (rpcholesky.py:40-43), fused: row = A[idx,:]; g = (row - G[:i,idx]^T
+ * G[:i,:]) / sqrt(diag[idx]); rows[i,:] = row; G[i,:] = g; diag = max(diag - g^2, 0).
+ * idx_dev points at the pivot index on the device (no host round trip).  For the dense operator pass
+ * spec = NULL and A/lda. */
+int rpc_simple_step(rpc_ctx *ctx, void *stream, const rpc_kernel_spec *spec, const double *X, const double *xnorm, int d,
+                    int64_t ldx, const double *A, int64_t lda, int64_t n, const int64_t *idx_dev, int i, double *G,
+                    int64_t ldg, double *rows, int64_t ldr, double *diag, int64_t n_pad);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RPC_B200_H */

@@ -1,0 +1,274 @@
+// N-proportional kernels: kernel-row evaluation (K1/K2), fused Schur update (K5), fused simple step (K4).
+#include "dmma_gemm.cuh"
+
+using namespace dg;
+
+// ------------------------------------------------------------------------------------------------
+// DMMA GEMM dispatch: pick the narrowest M tile that holds the rows of the update
+// ------------------------------------------------------------------------------------------------
+template <class C, int MODE>
+static int launch_gemm(rpc_ctx *ctx, cudaStream_t st, const Params &p, int64_t n_pad) {
+    static bool configured = false;
+    if (!configured) {
+        RPC_CUDA(cudaFuncSetAttribute(gemm_kernel<C, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)C::SMEM_BYTES));
+        configured = true;
+    }
+    dim3 grid((unsigned)(n_pad / C::N_TILE));
+    gemm_kernel<C, MODE><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(p);
+    RPC_LAUNCHED(ctx);
+    return 0;
+}
+
+typedef Cfg<4, 2, 8, 4> C256;   // 256 x 64
+typedef Cfg<4, 2, 6, 4> C192;   // 192 x 64
+typedef Cfg<2, 4, 8, 4> C128;   // 128 x 128
+typedef Cfg<2, 4, 4, 4> C64;    //  64 x 128
+typedef Cfg<1, 8, 4, 2> C32;    //  32 x 128
+typedef Cfg<1, 8, 2, 2> C16;    //  16 x 128
+
+int rpc_gemm_max_m(void) { return C256::M_TILE; }
+
+template <int MODE>
+static int dispatch_gemm(rpc_ctx *ctx, cudaStream_t st, const Params &p, int m, int64_t n_pad) {
+    if (m <= 16) return launch_gemm<C16, MODE>(ctx, st, p, n_pad);
+    if (m <= 32) return launch_gemm<C32, MODE>(ctx, st, p, n_pad);
+    if (m <= 64) return launch_gemm<C64, MODE>(ctx, st, p, n_pad);
+    if (m <= 128) return launch_gemm<C128, MODE>(ctx, st, p, n_pad);
+    if (m <= 192) return launch_gemm<C192, MODE>(ctx, st, p, n_pad);
+    return launch_gemm<C256, MODE>(ctx, st, p, n_pad);
+}
+
+static int tile_rows_for(int m) {
+    if (m <= 16) return 16;
+    if (m <= 32) return 32;
+    if (m <= 64) return 64;
+    if (m <= 128) return 128;
+    if (m <= 192) return 192;
+    return 256;
+}
+
+extern "C" int rpc_schur_update(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At,
+                                int64_t ldat, int k_pad, const double *rows_new, int64_t ldr, double *diag,
+                                int64_t n_pad) {
+    RPC_CHECK_ARG(ctx && G && At && rows_new && diag, "null pointer");
+    RPC_CHECK_ARG(s >= 1 && c >= 0, "s >= 1, c >= 0");
+    RPC_CHECK_ARG(n_pad > 0 && n_pad % RPC_COL_ALIGN == 0, "n_pad must be a positive multiple of RPC_COL_ALIGN");
+    RPC_CHECK_ARG(k_pad % RPC_KT == 0 && k_pad >= c + s, "k_pad must be a multiple of RPC_KT and >= c+s");
+    RPC_CHECK_ARG(ldg % 2 == 0 && ldr % 2 == 0 && ldat % 2 == 0, "leading dimensions must be even (16-byte rows)");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int m0 = 0; m0 < s; m0 += 256) {
+        int m = s - m0 < 256 ? s - m0 : 256;
+        RPC_CHECK_ARG(ldat >= m0 + tile_rows_for(m), "ldat too small for the zero-padded row tile");
+        Params p{};
+        p.At = At + m0; p.ldat = ldat; p.k_pad = k_pad; p.m_valid = m;
+        p.G = G; p.ldg = ldg; p.c = c; p.R = rows_new; p.ldr = ldr; p.K = c + s;
+        p.Cout = G + (int64_t)(c + m0) * ldg; p.ldc = ldg; p.diag = diag;
+        int rc = dispatch_gemm<MODE_SCHUR>(ctx, st, p, m, n_pad);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-core evaluator: Laplace (L1, strictly sequential over features like scipy cdist 'cityblock')
+// and the direct-difference Euclidean form (extra_stability).  4 pivots x 4 points per thread.
+// ------------------------------------------------------------------------------------------------
+constexpr int DK_TP = 64;    // pivots per CTA pass (16 thread rows x 4)
+constexpr int DK_TN = 64;    // points per CTA (16 thread cols x 4)
+constexpr int DK_FT = 32;    // features per smem chunk
+
+template <bool L1>
+__global__ void __launch_bounds__(256) direct_rows_kernel(KernParams kp, const double *__restrict__ X, int64_t ldx, int d,
+                                                          const double *__restrict__ Xpiv, int64_t ldp, int s,
+                                                          double *__restrict__ out, int64_t ldo) {
+    __shared__ double Ps[DK_FT][DK_TP + 4];
+    __shared__ double Ys[DK_FT][DK_TN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int64_t col0 = (int64_t)blockIdx.x * DK_TN;
+    for (int p0 = 0; p0 < s; p0 += DK_TP) {
+        double acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+        for (int f0 = 0; f0 < d; f0 += DK_FT) {
+            __syncthreads();
+            for (int q = tid; q < DK_FT * DK_TP; q += 256) {
+                int pi = q / DK_FT, f = q - pi * DK_FT;
+                double v = 0.0;
+                if (p0 + pi < s && f0 + f < d) v = Xpiv[(int64_t)(p0 + pi) * ldp + f0 + f];
+                Ps[f][pi] = v;
+            }
+            for (int q = tid; q < DK_FT * DK_TN; q += 256) {
+                int ni = q / DK_FT, f = q - ni * DK_FT;
+                double v = 0.0;
+                if (f0 + f < d) v = X[(col0 + ni) * ldx + f0 + f];
+                Ys[f][ni] = v;
+            }
+            __syncthreads();
+            const int fmax = d - f0 < DK_FT ? d - f0 : DK_FT;
+            for (int f = 0; f < fmax; ++f) {
+                double xp[4], yv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) xp[i] = Ps[f][ty * 4 + i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) yv[j] = Ys[f][tx * 4 + j];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        double df = xp[i] - yv[j];
+                        if (L1) acc[i][j] += fabs(df);            // sequential in f: bit-equal to cdist
+                        else acc[i][j] = fma(df, df, acc[i][j]);
+                    }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int row = p0 + ty * 4 + i;
+            if (row < s) {
+                double v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = L1 ? kern_from_l1(kp, acc[i][j]) : kern_from_d2(kp, acc[i][j]);
+                double *dst = out + (int64_t)row * ldo + col0 + tx * 4;
+                *reinterpret_cast<double2 *>(dst) = make_double2(v[0], v[1]);
+                *reinterpret_cast<double2 *>(dst + 2) = make_double2(v[2], v[3]);
+            }
+        }
+    }
+}
+
+extern "C" int rpc_kernel_rows(rpc_ctx *ctx, void *stream, const rpc_kernel_spec *spec, const double *X,
+                               const double *xnorm, int64_t n_pad, int d, int64_t ldx, const double *Xpiv,
+                               const double *pnorm, int s, int64_t ldp, double *out, int64_t ldo) {
+    RPC_CHECK_ARG(ctx && spec && X && Xpiv && out, "null pointer");
+    RPC_CHECK_ARG(s >= 1, "s >= 1");
+    RPC_CHECK_ARG(n_pad > 0 && n_pad % RPC_COL_ALIGN == 0, "n_pad must be a positive multiple of RPC_COL_ALIGN");
+    RPC_CHECK_ARG(d >= 1 && d % RPC_FEAT_ALIGN == 0 && ldx % 2 == 0, "d must be a multiple of RPC_FEAT_ALIGN, ldx even");
+    RPC_CHECK_ARG(ldo % 2 == 0, "ldo must be even");
+    RPC_CHECK_ARG(spec->kind >= 0 && spec->kind <= 2, "unknown kernel kind");
+    RPC_CHECK_ARG(spec->kind != RPC_KERN_MATERN || spec->nu2 == 1 || spec->nu2 == 3 || spec->nu2 == 5,
+                  "Matern nu must be 0.5, 1.5 or 2.5");
+    cudaStream_t st = (cudaStream_t)stream;
+    KernParams kp = make_kern_params(spec);
+    if (spec->kind == RPC_KERN_LAPLACE || spec->extra_stability) {
+        dim3 grid((unsigned)(n_pad / DK_TN));
+        if (spec->kind == RPC_KERN_LAPLACE)
+            direct_rows_kernel<true><<<grid, 256, 0, st>>>(kp, X, ldx, d, Xpiv, ldp, s, out, ldo);
+        else
+            direct_rows_kernel<false><<<grid, 256, 0, st>>>(kp, X, ldx, d, Xpiv, ldp, s, out, ldo);
+        RPC_LAUNCHED(ctx);
+        return 0;
+    }
+    RPC_CHECK_ARG(xnorm && pnorm, "row norms required for the expanded Euclidean form");
+    // A operand = Xpiv^T (d x s) zero padded to (k_pad x 256) in the context workspace
+    const int k_pad = (d + RPC_KT - 1) / RPC_KT * RPC_KT;
+    for (int m0 = 0; m0 < s; m0 += 256) {
+        int m = s - m0 < 256 ? s - m0 : 256;
+        int rc = rpc_ws_reserve(ctx, (size_t)k_pad * 256 * sizeof(double));
+        if (rc) return rc;
+        rc = rpc_transpose_pad(ctx, st, Xpiv + (int64_t)m0 * ldp, ldp, m, d, ctx->ws, 256, k_pad);
+        if (rc) return rc;
+        Params p{};
+        p.At = ctx->ws; p.ldat = 256; p.k_pad = k_pad; p.m_valid = m;
+        p.X = X; p.ldx = ldx; p.d = d; p.xnorm = xnorm; p.pnorm = pnorm + m0; p.kp = kp;
+        p.Cout = out + (int64_t)m0 * ldo; p.ldc = ldo;
+        rc = dispatch_gemm<MODE_EVAL>(ctx, st, p, m, n_pad);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// simple RPCholesky step, fully fused (HBM-bound GEMV over the i x n prefix of G)
+// ------------------------------------------------------------------------------------------------
+constexpr int SS_THREADS = 256;
+constexpr int SS_MAXD = 1024;   // features cached in smem
+
+__global__ void __launch_bounds__(SS_THREADS) simple_step_kernel(int has_spec, KernParams kp, const double *__restrict__ X,
+                                                                 const double *__restrict__ xnorm, int d, int64_t ldx,
+                                                                 const double *__restrict__ A, int64_t lda, int64_t n,
+                                                                 const int64_t *__restrict__ idx_dev, int i,
+                                                                 double *__restrict__ G, int64_t ldg,
+                                                                 double *__restrict__ rows, int64_t ldr,
+                                                                 double *__restrict__ diag_in, double *__restrict__ diag_out,
+                                                                 int64_t n_pad) {
+    extern __shared__ double sm[];          // [i] pivot column of G, then [d] pivot point
+    double *pcol = sm;
+    double *xp = sm + i;
+    const int64_t piv = idx_dev[i];
+    for (int r = threadIdx.x; r < i; r += SS_THREADS) pcol[r] = G[(int64_t)r * ldg + piv];
+    if (has_spec)
+        for (int f = threadIdx.x; f < d; f += SS_THREADS) xp[f] = X[piv * ldx + f];
+    __syncthreads();
+    const double dpiv = diag_in[piv];
+    const double scale = sqrt(dpiv);
+    const double pn = has_spec && xnorm ? xnorm[piv] : 0.0;
+    for (int64_t col = (int64_t)blockIdx.x * SS_THREADS + threadIdx.x; col < n_pad; col += (int64_t)gridDim.x * SS_THREADS) {
+        double row;
+        if (!has_spec) {
+            row = col < n ? A[piv * lda + col] : 0.0;
+        } else if (kp.kind == RPC_KERN_LAPLACE) {
+            double l1 = 0.0;
+            for (int f = 0; f < d; ++f) l1 += fabs(xp[f] - X[col * ldx + f]);
+            row = kern_from_l1(kp, l1);
+        } else if (kp.stab) {
+            double d2 = 0.0;
+            for (int f = 0; f < d; ++f) { double df = xp[f] - X[col * ldx + f]; d2 = fma(df, df, d2); }
+            row = kern_from_d2(kp, d2);
+        } else {
+            double dot = 0.0;
+            for (int f = 0; f < d; ++f) dot = fma(xp[f], X[col * ldx + f], dot);
+            double d2 = (-2.0 * dot + pn) + xnorm[col];
+            row = kern_from_d2(kp, d2 > 0.0 ? d2 : 0.0);
+        }
+        // g = (row - G[:i,piv]^T G[:i,col]) / sqrt(diag[piv])   (rpcholesky.py:41)
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int r = 0;
+        for (; r + 4 <= i; r += 4) {
+            a0 = fma(pcol[r], G[(int64_t)r * ldg + col], a0);
+            a1 = fma(pcol[r + 1], G[(int64_t)(r + 1) * ldg + col], a1);
+            a2 = fma(pcol[r + 2], G[(int64_t)(r + 2) * ldg + col], a2);
+            a3 = fma(pcol[r + 3], G[(int64_t)(r + 3) * ldg + col], a3);
+        }
+        for (; r < i; ++r) a0 = fma(pcol[r], G[(int64_t)r * ldg + col], a0);
+        double g = (row - ((a0 + a1) + (a2 + a3))) / scale;
+        rows[(int64_t)i * ldr + col] = row;
+        G[(int64_t)i * ldg + col] = g;
+        double dv = diag_in[col] - g * g;
+        diag_out[col] = dv > 0.0 ? dv : 0.0;
+    }
+}
+
+extern "C" int rpc_simple_step(rpc_ctx *ctx, void *stream, const rpc_kernel_spec *spec, const double *X,
+                               const double *xnorm, int d, int64_t ldx, const double *A, int64_t lda, int64_t n,
+                               const int64_t *idx_dev, int i, double *G, int64_t ldg, double *rows, int64_t ldr,
+                               double *diag, int64_t n_pad) {
+    RPC_CHECK_ARG(ctx && idx_dev && G && rows && diag, "null pointer");
+    RPC_CHECK_ARG((spec && X) || A, "either a kernel spec with X or a dense A is required");
+    RPC_CHECK_ARG(i >= 0 && n_pad > 0, "i >= 0, n_pad > 0");
+    RPC_CHECK_ARG(!spec || d <= SS_MAXD, "d too large for the fused simple step");
+    cudaStream_t st = (cudaStream_t)stream;
+    KernParams kp{};
+    if (spec) kp = make_kern_params(spec);
+    // the step reads diag[piv] while other CTAs overwrite diag: double-buffer through the workspace
+    int rc = rpc_ws_reserve(ctx, (size_t)n_pad * sizeof(double));
+    if (rc) return rc;
+    int grid = (int)((n_pad + SS_THREADS - 1) / SS_THREADS);
+    int cap = ctx->sm_count * 8;
+    if (grid > cap) grid = cap;
+    size_t shm = (size_t)(i + (spec ? d : 0) + 1) * sizeof(double);
+    static size_t configured = 48 * 1024;
+    if (shm > configured) {
+        RPC_CUDA(cudaFuncSetAttribute(simple_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = 200 * 1024;
+    }
+    RPC_CHECK_ARG(shm <= 200 * 1024, "rank too large for the fused simple step");
+    simple_step_kernel<<<grid, SS_THREADS, shm, st>>>(spec ? 1 : 0, kp, X, xnorm, d, ldx, A, lda, n, idx_dev, i, G, ldg,
+                                                      rows, ldr, diag, ctx->ws, n_pad);
+    RPC_LAUNCHED(ctx);
+    RPC_CUDA(cudaMemcpyAsync(diag, ctx->ws, (size_t)n_pad * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}

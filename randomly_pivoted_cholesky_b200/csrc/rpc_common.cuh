@@ -1,0 +1,86 @@
+// Shared declarations of the sm_100a RPCholesky kernels (internal; the public ABI is include/rpc_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/rpc_b200.h"
+
+struct rpc_ctx {
+    int device;
+    int sm_count;
+    int64_t launches;
+    // scratch owned by the context (grown on demand, never shrunk)
+    double *ws;        // general double workspace
+    size_t ws_bytes;
+    int32_t *flags;    // small int workspace (sampler flags etc.)
+    size_t flags_bytes;
+};
+
+void rpc_set_error(const char *fmt, ...);
+int rpc_ws_reserve(rpc_ctx *ctx, size_t bytes);
+int rpc_flags_reserve(rpc_ctx *ctx, size_t bytes);
+// out (k_pad x ldo) = zero-padded transpose of in (m x d)
+int rpc_transpose_pad(rpc_ctx *ctx, cudaStream_t st, const double *in, int64_t ldi, int m, int d, double *out, int64_t ldo,
+                      int k_pad);
+
+#define RPC_CHECK_ARG(cond, msg)                                   \
+    do {                                                           \
+        if (!(cond)) {                                             \
+            rpc_set_error("%s: bad argument: %s", __func__, msg);  \
+            return -1;                                             \
+        }                                                          \
+    } while (0)
+
+#define RPC_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            rpc_set_error("%s: %s failed: %s", __func__, #call, cudaGetErrorString(e_));        \
+            return (int)e_;                                                                     \
+        }                                                                                       \
+    } while (0)
+
+// every kernel launch goes through this so the context can count them
+#define RPC_LAUNCHED(ctx)                                                                       \
+    do {                                                                                        \
+        (ctx)->launches++;                                                                      \
+        cudaError_t e_ = cudaPeekAtLastError();                                                 \
+        if (e_ != cudaSuccess) {                                                                \
+            rpc_set_error("%s: kernel launch failed: %s", __func__, cudaGetErrorString(e_));    \
+            return (int)e_;                                                                     \
+        }                                                                                       \
+    } while (0)
+
+// ---- kernel function on a squared Euclidean distance / L1 distance ---------------------------------
+struct KernParams {
+    int kind;      // RPC_KERN_*
+    int nu2;       // Matern 2*nu
+    int stab;      // extra_stability
+    double bw;     // bandwidth
+};
+
+__host__ inline KernParams make_kern_params(const rpc_kernel_spec *s) {
+    KernParams p;
+    p.kind = s->kind; p.nu2 = s->nu2; p.stab = s->extra_stability; p.bw = s->bandwidth;
+    return p;
+}
+
+// Value of the kernel from the clamped squared distance d2 (expanded or direct form).
+// Mirrors the reference op order: dsts = sqrt(d2); Gaussian exp(-0.5*dsts**2/bw**2) (kernels.py:39);
+// Matern r = dsts/bw, or r = dsts when extra_stability (the reference omits /bw there, kernels.py:74-75).
+__device__ __forceinline__ double kern_from_d2(const KernParams &kp, double d2) {
+    double dst = sqrt(d2);
+    if (kp.kind == RPC_KERN_GAUSSIAN) {
+        return exp(-0.5 * (dst * dst) / (kp.bw * kp.bw));
+    }
+    double r = kp.stab ? dst : dst / kp.bw;
+    if (kp.nu2 == 1) return exp(-r);
+    if (kp.nu2 == 3) {
+        const double s3 = 1.7320508075688772;  // np.sqrt(3)
+        return (1.0 + s3 * r) * exp(-s3 * r);
+    }
+    const double s5 = 2.23606797749979;        // np.sqrt(5)
+    return (1.0 + s5 * r + 5.0 / 3.0 * r * r) * exp(-s5 * r);
+}
+
+__device__ __forceinline__ double kern_from_l1(const KernParams &kp, double l1) { return exp(-l1 / kp.bw); }

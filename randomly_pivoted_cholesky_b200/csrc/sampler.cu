@@ -1,0 +1,285 @@
+// Residual-proportional pivot sampler, bit-identical to numpy's
+//     rng.choice(range(n), size=m, p=diags/sum(diags), replace=True)          (rpcholesky.py:31,91,184)
+// i.e.  S = sum(diags) [python builtin: left-to-right fp64];  p = diags / S;  cdf = cumsum(p) [left-to-right];
+//       cdf /= cdf[-1];  idx = searchsorted(cdf, u, side='right').
+//
+// A parallel scan rounds differently from numpy's sequential one, so the device computes the
+// SEQUENTIALLY ROUNDED prefix sums exactly, in parallel, with this observation: while the running
+// sum c stays inside one binade [2^e, 2^(e+1)) with ulp q = 2^(e-52), fl(c + x) = c + q*rne(x/q)
+// (ties aside), and all quantities are integer multiples of q below 2^53 q, so they add EXACTLY in
+// any order.  Per chunk of SC_CH elements:
+//   1. plain parallel sums give an approximate prefix P with a rigorous bound |c - P| <= delta*P;
+//   2. a chunk whose running sums provably stay in one binade and that holds no rounding tie is
+//      "regular": its exact contribution D = q * sum_j rne(x_j/q) is computed in parallel;
+//   3. one thread walks the chunks: carry += D (an exact fp64 add) for regular chunks and replays the
+//      few others (binade crossings, ties: ~20 per scan) element by element with real fp64 adds;
+//   4. each draw binary-searches the exact chunk carries with numpy's own predicate
+//      fl(c/c_last) <= u and replays one chunk sequentially to land on the element.
+// The same machinery run on diag itself yields python's sum(diags) bit-exactly (stoptol tests,
+// rpcholesky.py:45,133,224, therefore agree with the reference too).
+#include "rpc_common.cuh"
+
+constexpr int SC_CH = 256;            // elements per chunk (one warp, 8 per lane)
+constexpr int SC_WARPS = 8;           // chunks per CTA in the parallel passes
+
+struct ScanBufs {
+    double *csum;     // [nch+1] approximate chunk sums -> exclusive prefix P
+    double *D;        // [nch]   exact chunk contribution (regular chunks)
+    int32_t *cls;     // [nch]   binade exponent e of a regular chunk, or INT_MIN if it must be replayed
+    double *cstart;   // [nch+1] exact sequential running sum before each chunk; [nch] = total
+};
+
+__device__ __forceinline__ double pow2d(int e) {   // 2^e for e in [-1022, 1023]
+    return __longlong_as_double((long long)(e + 1023) << 52);
+}
+
+template <bool DIV>
+__device__ __forceinline__ double elem(const double *__restrict__ d, int64_t j, double S) {
+    return DIV ? d[j] / S : d[j];
+}
+
+// 1. approximate chunk sums (+ validity: NaN or negative entries make numpy raise ValueError)
+template <bool DIV>
+__global__ void __launch_bounds__(SC_WARPS * 32) sc_chunk_sums(const double *__restrict__ d, int64_t n, const double *Sptr,
+                                                                double *__restrict__ csum, int32_t *__restrict__ bad) {
+    const int lane = threadIdx.x & 31;
+    const int64_t k = (int64_t)blockIdx.x * SC_WARPS + (threadIdx.x >> 5);
+    const int64_t base = k * SC_CH;
+    if (base >= n) return;
+    const double S = DIV ? *Sptr : 1.0;
+    double s = 0.0;
+    bool isbad = false;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        int64_t j = base + lane * 8 + t;
+        double x = j < n ? elem<DIV>(d, j, S) : 0.0;
+        isbad |= !(x >= 0.0);
+        s += x;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (__any_sync(0xffffffffu, isbad) && lane == 0) atomicExch(bad, 1);
+    if (lane == 0) csum[k] = s;
+}
+
+// 2. exclusive scan of the chunk sums, one CTA
+__global__ void __launch_bounds__(1024) sc_scan_chunks(double *__restrict__ csum, int nch) {
+    __shared__ double part[1024];
+    const int tid = threadIdx.x;
+    const int per = (nch + 1023) / 1024;
+    const int b0 = tid * per;
+    double s = 0.0;
+    for (int i = 0; i < per; ++i) if (b0 + i < nch) s += csum[b0 + i];
+    part[tid] = s;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over 1024 partials
+    for (int o = 1; o < 1024; o <<= 1) {
+        double v = tid >= o ? part[tid - o] : 0.0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    double run = tid > 0 ? part[tid - 1] : 0.0;
+    for (int i = 0; i < per; ++i) {
+        if (b0 + i < nch) { double v = csum[b0 + i]; csum[b0 + i] = run; run += v; }
+    }
+    if (tid == 1023) csum[nch] = part[1023];
+}
+
+// 3. classify each chunk and compute the exact contribution of the regular ones
+template <bool DIV>
+__global__ void __launch_bounds__(SC_WARPS * 32) sc_classify(const double *__restrict__ d, int64_t n, const double *Sptr,
+                                                             const double *__restrict__ P, double delta,
+                                                             double *__restrict__ D, int32_t *__restrict__ cls) {
+    const int lane = threadIdx.x & 31;
+    const int64_t k = (int64_t)blockIdx.x * SC_WARPS + (threadIdx.x >> 5);
+    const int64_t base = k * SC_CH;
+    if (base >= n) return;
+    const double S = DIV ? *Sptr : 1.0;
+    const double lo = P[k] * (1.0 - delta), hi = P[k + 1] * (1.0 + delta);
+    bool regular = lo > 0.0 && isfinite(hi);
+    int e = 0;
+    if (regular) {
+        e = ilogb(lo);                               // lo in [2^e, 2^(e+1))
+        regular = e >= -960 && e <= 1000 && hi < pow2d(e + 1);
+    }
+    double A = 0.0;
+    bool tie = false;
+    if (regular) {                                   // warp-uniform
+        const double scale = pow2d(52 - e);          // exact power of two
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            int64_t j = base + lane * 8 + t;
+            double x = j < n ? elem<DIV>(d, j, S) : 0.0;
+            double v = x * scale;                    // exact (or a harmless underflow towards 0)
+            double kf = floor(v);
+            double f = v - kf;                       // exact
+            tie |= (f == 0.5);
+            A += kf + (f > 0.5 ? 1.0 : 0.0);         // integers < 2^53: exact
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) A += __shfl_xor_sync(0xffffffffu, A, o);
+        if (__any_sync(0xffffffffu, tie)) regular = false;
+    }
+    if (lane == 0) {
+        cls[k] = regular ? e : INT_MIN;
+        D[k] = regular ? A * pow2d(e - 52) : 0.0;    // exact: integer times a power of two
+    }
+}
+
+// 4. the walk: exact running sum before every chunk.  One warp: lanes stage data, lane 0 adds.
+template <bool DIV>
+__global__ void __launch_bounds__(32) sc_walk(const double *__restrict__ d, int64_t n, const double *Sptr,
+                                              const double *__restrict__ D, const int32_t *__restrict__ cls, int nch,
+                                              double *__restrict__ cstart, int32_t *__restrict__ bad) {
+    __shared__ double xs[SC_CH];
+    __shared__ double ds[32 * 8];
+    __shared__ int32_t es[32 * 8];
+    const int lane = threadIdx.x;
+    const double S = DIV ? *Sptr : 1.0;
+    double carry = 0.0;                              // meaningful in lane 0 only
+    int violated = 0;
+    for (int k0 = 0; k0 < nch; k0 += 256) {
+        // stage 256 chunk descriptors
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            int k = k0 + t * 32 + lane;
+            ds[t * 32 + lane] = k < nch ? D[k] : 0.0;
+            es[t * 32 + lane] = k < nch ? cls[k] : 0;
+        }
+        __syncwarp();
+        const int kend = min(256, nch - k0);
+        int kk = 0;
+        while (kk < kend) {
+            // lane 0 runs through regular chunks until it meets one that needs a replay
+            int stop = kend;
+            if (lane == 0) {
+                int q = kk;
+                for (; q < kend; ++q) {
+                    int e = es[q];
+                    if (e == INT_MIN) break;
+                    cstart[k0 + q] = carry;
+                    if (ilogb(carry) != e) violated = 1;   // the a-priori bound guarantees this never fires
+                    carry += ds[q];                        // exact
+                }
+                stop = q;
+            }
+            stop = __shfl_sync(0xffffffffu, stop, 0);
+            kk = stop;
+            if (kk < kend) {
+                // replay chunk k0+kk with real sequential fp64 adds
+                const int64_t base = (int64_t)(k0 + kk) * SC_CH;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    int64_t j = base + t * 32 + lane;
+                    xs[t * 32 + lane] = j < n ? elem<DIV>(d, j, S) : 0.0;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    cstart[k0 + kk] = carry;
+#pragma unroll 16
+                    for (int j = 0; j < SC_CH; ++j) carry += xs[j];
+                }
+                __syncwarp();
+                ++kk;
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        cstart[nch] = carry;
+        if (violated) atomicExch(bad, 2);
+    }
+}
+
+// 5. locate the draws: idx = #{ j : fl(c_j / c_last) <= u }
+__global__ void __launch_bounds__(32) sc_locate(const double *__restrict__ d, int64_t n, const double *Sptr,
+                                                const double *__restrict__ cstart, int nch, const double *__restrict__ u,
+                                                int64_t *__restrict__ idx) {
+    __shared__ double xs[SC_CH];
+    const int lane = threadIdx.x;
+    const double S = *Sptr;
+    const double clast = cstart[nch];
+    const double uu = u[blockIdx.x];
+    // first chunk whose END value exceeds u: cdf is non-decreasing, cstart[k+1] is the value at chunk k's end
+    int lo = 0, hi = nch - 1;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (cstart[mid + 1] / clast > uu) hi = mid; else lo = mid + 1;
+    }
+    const int64_t base = (int64_t)lo * SC_CH;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        int64_t j = base + t * 32 + lane;
+        xs[t * 32 + lane] = j < n ? d[j] / S : 0.0;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        double c = cstart[lo];
+        int cnt = 0;
+        for (int j = 0; j < SC_CH; ++j) {
+            c += xs[j];
+            if (c / clast <= uu) ++cnt; else break;
+        }
+        int64_t r = base + cnt;
+        idx[blockIdx.x] = r < n ? r : n - 1;
+    }
+}
+
+__global__ void sc_finish(const double *__restrict__ Sptr, const double *__restrict__ ctot, const int32_t *__restrict__ bad,
+                          double *__restrict__ stats) {
+    double S = *Sptr;
+    int b = *bad;
+    stats[0] = S;
+    // numpy raises ValueError when p holds NaN / negatives or does not sum to 1 (S == 0, inf, NaN)
+    double tot = *ctot;
+    bool invalid = (b == 1) || !(S > 0.0) || !isfinite(S) || !(fabs(tot - 1.0) <= 1.4901161193847656e-08);
+    stats[1] = invalid ? 1.0 : 0.0;
+    stats[2] = (b == 2) ? 1.0 : 0.0;
+}
+
+extern "C" int rpc_sample_pivots(rpc_ctx *ctx, void *stream, const double *diag, int64_t n_pad, const double *u, int m,
+                                 int64_t *idx, double *stats) {
+    RPC_CHECK_ARG(ctx && diag && stats, "null pointer");
+    RPC_CHECK_ARG(n_pad > 0 && m >= 0, "bad sizes");
+    RPC_CHECK_ARG(m == 0 || (u && idx), "uniforms and idx required when m > 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nch = (int)((n_pad + SC_CH - 1) / SC_CH);
+    // workspace layout (doubles): csum[nch+1] | D[nch] | cstartA[nch+1] | cstartB[nch+1] ; ints: cls[nch] | bad[2]
+    size_t nd = (size_t)4 * (nch + 2);
+    int rc = rpc_ws_reserve(ctx, nd * sizeof(double));
+    if (rc) return rc;
+    rc = rpc_flags_reserve(ctx, (size_t)(nch + 8) * sizeof(int32_t));
+    if (rc) return rc;
+    double *csum = ctx->ws, *D = csum + (nch + 2), *cA = D + (nch + 2), *cB = cA + (nch + 2);
+    int32_t *cls = ctx->flags, *bad = ctx->flags + nch;
+    RPC_CUDA(cudaMemsetAsync(bad, 0, 2 * sizeof(int32_t), st));
+    const double delta = ((double)n_pad + 256.0) * 1.1102230246251565e-16 * 1.01;
+    const unsigned grid = (unsigned)((nch + SC_WARPS - 1) / SC_WARPS);
+    const double *Sptr = cA + nch;     // exact python sum(diags)
+
+    sc_chunk_sums<false><<<grid, SC_WARPS * 32, 0, st>>>(diag, n_pad, nullptr, csum, bad);
+    RPC_LAUNCHED(ctx);
+    sc_scan_chunks<<<1, 1024, 0, st>>>(csum, nch);
+    RPC_LAUNCHED(ctx);
+    sc_classify<false><<<grid, SC_WARPS * 32, 0, st>>>(diag, n_pad, nullptr, csum, delta, D, cls);
+    RPC_LAUNCHED(ctx);
+    sc_walk<false><<<1, 32, 0, st>>>(diag, n_pad, nullptr, D, cls, nch, cA, bad);
+    RPC_LAUNCHED(ctx);
+
+    sc_chunk_sums<true><<<grid, SC_WARPS * 32, 0, st>>>(diag, n_pad, Sptr, csum, bad);
+    RPC_LAUNCHED(ctx);
+    sc_scan_chunks<<<1, 1024, 0, st>>>(csum, nch);
+    RPC_LAUNCHED(ctx);
+    sc_classify<true><<<grid, SC_WARPS * 32, 0, st>>>(diag, n_pad, Sptr, csum, delta, D, cls);
+    RPC_LAUNCHED(ctx);
+    sc_walk<true><<<1, 32, 0, st>>>(diag, n_pad, Sptr, D, cls, nch, cB, bad);
+    RPC_LAUNCHED(ctx);
+    if (m > 0) {
+        sc_locate<<<m, 32, 0, st>>>(diag, n_pad, Sptr, cB, nch, u, idx);
+        RPC_LAUNCHED(ctx);
+    }
+    sc_finish<<<1, 1, 0, st>>>(Sptr, cB + nch, bad, stats);
+    RPC_LAUNCHED(ctx);
+    return 0;
+}

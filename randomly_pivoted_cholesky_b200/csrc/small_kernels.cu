@@ -1,0 +1,454 @@
+// Per-round small dense work and operator helpers: row norms, diagonal, dense-operator gathers,
+// pivot gather, b x b kernel block, residual Gram, rejection / shifted Cholesky, panel assembly.
+#include "rpc_common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// row norms (warp per point), diagonal fill
+// ------------------------------------------------------------------------------------------------
+__global__ void row_norms_kernel(const double *__restrict__ X, int64_t n, int d, int64_t ldx, double *__restrict__ out) {
+    int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    double acc = 0.0;
+    for (int f = lane; f < d; f += 32) { double v = X[row * ldx + f]; acc = fma(v, v, acc); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[row] = acc;
+}
+
+extern "C" int rpc_row_norms(rpc_ctx *ctx, void *stream, const double *X, int64_t n, int d, int64_t ldx, double *xnorm) {
+    RPC_CHECK_ARG(ctx && X && xnorm && n > 0 && d > 0, "null pointer or empty");
+    unsigned grid = (unsigned)((n + 7) / 8);
+    row_norms_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, n, d, ldx, xnorm);
+    RPC_LAUNCHED(ctx);
+    return 0;
+}
+
+__global__ void fill_diag_kernel(double *diag, int64_t n, int64_t n_pad) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_pad) diag[i] = i < n ? 1.0 : 0.0;
+}
+
+extern "C" int rpc_kernel_diag(rpc_ctx *ctx, void *stream, double *diag, int64_t n, int64_t n_pad) {
+    RPC_CHECK_ARG(ctx && diag && n > 0 && n_pad >= n, "null pointer or bad sizes");
+    fill_diag_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, (cudaStream_t)stream>>>(diag, n, n_pad);
+    RPC_LAUNCHED(ctx);
+    return 0;
+}
+
+// out (k_pad x ldo) = zero-padded transpose of in (m x d): out[f][j] = in[j][f]
+__global__ void transpose_pad_kernel(const double *__restrict__ in, int64_t ldi, int m, int d, double *__restrict__ out,
+                                     int64_t ldo, int k_pad) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (int64_t)k_pad * ldo) return;
+    int f = (int)(q / ldo), j = (int)(q - (int64_t)f * ldo);
+    out[q] = (f < d && j < m) ? in[(int64_t)j * ldi + f] : 0.0;
+}
+
+int rpc_transpose_pad(rpc_ctx *ctx, cudaStream_t st, const double *in, int64_t ldi, int m, int d, double *out, int64_t ldo,
+                      int k_pad) {
+    int64_t tot = (int64_t)k_pad * ldo;
+    transpose_pad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(in, ldi, m, d, out, ldo, k_pad);
+    RPC_LAUNCHED(ctx);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense PSDMatrix operator (matrix.py:86-102)
+// ------------------------------------------------------------------------------------------------
+__global__ void psd_diag_kernel(const double *__restrict__ A, int64_t n, int64_t lda, double *__restrict__ diag, int64_t n_pad) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_pad) diag[i] = i < n ? A[i * lda + i] : 0.0;
+}
+extern "C" int rpc_psd_diag(rpc_ctx *ctx, void *stream, const double *A, int64_t n, int64_t lda, double *diag, int64_t n_pad) {
+    RPC_CHECK_ARG(ctx && A && diag && n > 0 && n_pad >= n, "null pointer or bad sizes");
+    psd_diag_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, (cudaStream_t)stream>>>(A, n, lda, diag, n_pad);
+    RPC_LAUNCHED(ctx);
+    return 0;
+}
+
+__global__ void psd_rows_kernel(const double *__restrict__ A, int64_t n, int64_t lda, const int64_t *__restrict__ idx,
+                                double *__restrict__ out, int64_t ldo, int64_t n_pad) {
+    const int64_t src = idx[blockIdx.y];
+    for (int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; col < n_pad; col += (int64_t)gridDim.x * blockDim.x)
+        out[(int64_t)blockIdx.y * ldo + col] = col < n ? A[src * lda + col] : 0.0;
+}
+extern "C" int rpc_psd_rows(rpc_ctx *ctx, void *stream, const double *A, int64_t n, int64_t lda, const int64_t *idx, int s,
+                            double *out, int64_t ldo, int64_t n_pad) {
+    RPC_CHECK_ARG(ctx && A && idx && out && s >= 1 && n_pad >= n, "null pointer or bad sizes");
+    unsigned gx = (unsigned)((n_pad + 255) / 256);
+    if (gx > 1024) gx = 1024;
+    psd_rows_kernel<<<dim3(gx, s), 256, 0, (cudaStream_t)stream>>>(A, n, lda, idx, out, ldo, n_pad);
+    RPC_LAUNCHED(ctx);
+    return 0;
+}
+
+__global__ void psd_block_kernel(const double *__restrict__ A, int64_t lda, const int64_t *__restrict__ idx, int b,
+                                 double *__restrict__ H, int64_t ldh) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= b * b) return;
+    int i = q / b, j = q - i * b;
+    H[(int64_t)i * ldh + j] = A[idx[i] * lda + idx[j]];
+}
+extern "C" int rpc_psd_block(rpc_ctx *ctx, void *stream, const double *A, int64_t lda, const int64_t *idx, int b, double *H,
+                             int64_t ldh) {
+    RPC_CHECK_ARG(ctx && A && idx && H && b >= 1, "null pointer or bad sizes");
+    psd_block_kernel<<<(b * b + 255) / 256, 256, 0, (cudaStream_t)stream>>>(A, lda, idx, b, H, ldh);
+    RPC_LAUNCHED(ctx);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// b x b kernel block A[idx,idx] (same formulas as the row evaluator)
+// ------------------------------------------------------------------------------------------------
+__global__ void kernel_block_kernel(KernParams kp, const double *__restrict__ Xp, const double *__restrict__ pn, int b, int d,
+                                    int64_t ldp, double *__restrict__ H, int64_t ldh) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= b * b) return;
+    int i = q / b, j = q - i * b;
+    const double *x = Xp + (int64_t)i * ldp, *y = Xp + (int64_t)j * ldp;
+    double v;
+    if (kp.kind == RPC_KERN_LAPLACE) {
+        double l1 = 0.0;
+        for (int f = 0; f < d; ++f) l1 += fabs(x[f] - y[f]);
+        v = kern_from_l1(kp, l1);
+    } else if (kp.stab) {
+        double d2 = 0.0;
+        for (int f = 0; f < d; ++f) { double df = x[f] - y[f]; d2 = fma(df, df, d2); }
+        v = kern_from_d2(kp, d2);
+    } else {
+        double dot = 0.0;
+        for (int f = 0; f < d; ++f) dot = fma(x[f], y[f], dot);
+        double d2 = (-2.0 * dot + pn[i]) + pn[j];
+        v = kern_from_d2(kp, d2 > 0.0 ? d2 : 0.0);
+    }
+    H[(int64_t)i * ldh + j] = v;
+}
+
+extern "C" int rpc_kernel_block(rpc_ctx *ctx, void *stream, const rpc_kernel_spec *spec, const double *Xpiv,
+                                const double *pnorm, int b, int d, int64_t ldp, double *H, int64_t ldh) {
+    RPC_CHECK_ARG(ctx && spec && Xpiv && H && b >= 1 && d >= 1, "null pointer or bad sizes");
+    RPC_CHECK_ARG(spec->kind == RPC_KERN_LAPLACE || spec->extra_stability || pnorm, "pivot norms required");
+    kernel_block_kernel<<<(b * b + 127) / 128, 128, 0, (cudaStream_t)stream>>>(make_kern_params(spec), Xpiv, pnorm, b, d, ldp,
+                                                                             H, ldh);
+    RPC_LAUNCHED(ctx);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pivot gather: Xpiv = X[idx], pnorm = xnorm[idx], P = G[:c, idx]
+// ------------------------------------------------------------------------------------------------
+__global__ void gather_pivots_kernel(const int64_t *__restrict__ idx, int m, const double *__restrict__ X,
+                                     const double *__restrict__ xnorm, int d, int64_t ldx, double *__restrict__ Xpiv,
+                                     double *__restrict__ pnorm, int64_t ldp, const double *__restrict__ G, int64_t ldg, int c,
+                                     double *__restrict__ P, int64_t ldP) {
+    int blk = blockIdx.x;
+    if (blk < c) {
+        for (int j = threadIdx.x; j < m; j += blockDim.x) P[(int64_t)blk * ldP + j] = G[(int64_t)blk * ldg + idx[j]];
+    } else {
+        int j = blk - c;
+        int64_t src = idx[j];
+        for (int f = threadIdx.x; f < d; f += blockDim.x) Xpiv[(int64_t)j * ldp + f] = X[src * ldx + f];
+        if (threadIdx.x == 0 && xnorm && pnorm) pnorm[j] = xnorm[src];
+    }
+}
+
+extern "C" int rpc_gather_pivots(rpc_ctx *ctx, void *stream, const int64_t *idx, int m, const double *X,
+                                 const double *xnorm, int d, int64_t ldx, double *Xpiv, double *pnorm, int64_t ldp,
+                                 const double *G, int64_t ldg, int c, double *P, int64_t ldP) {
+    RPC_CHECK_ARG(ctx && idx && m >= 1 && c >= 0, "null pointer or bad sizes");
+    RPC_CHECK_ARG(c == 0 || (G && P), "G and P required when c > 0");
+    RPC_CHECK_ARG(!X || Xpiv, "Xpiv required when X is given");
+    int blocks = c + (X ? m : 0);
+    if (blocks == 0) return 0;
+    gather_pivots_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(idx, m, X, xnorm, d, ldx, Xpiv, pnorm, ldp, G, ldg, c, P,
+                                                                  ldP);
+    RPC_LAUNCHED(ctx);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// residual Gram: H -= P^T P.  32x32 output tile per CTA, split over K in chunks of GR_KC rows with
+// partial sums in the workspace, then a fixed-order reduction (deterministic, no atomics).
+// ------------------------------------------------------------------------------------------------
+constexpr int GR_T = 32;
+constexpr int GR_KC = 128;
+
+__global__ void __launch_bounds__(256) gram_partial_kernel(const double *__restrict__ P, int c, int m, int64_t ldP,
+                                                           double *__restrict__ part) {
+    __shared__ double Pi[GR_T][GR_T + 1];
+    __shared__ double Pj[GR_T][GR_T + 1];
+    const int i0 = blockIdx.y * GR_T, j0 = blockIdx.x * GR_T;
+    const int k0 = blockIdx.z * GR_KC;
+    const int k1 = min(c, k0 + GR_KC);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16 threads, 2 x 2 outputs each
+    double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
+    for (int kb = k0; kb < k1; kb += GR_T) {
+        __syncthreads();
+        for (int q = threadIdx.x; q < GR_T * GR_T; q += 256) {
+            int kk = q / GR_T, col = q - kk * GR_T;
+            int k = kb + kk;
+            Pi[kk][col] = (k < k1 && i0 + col < m) ? P[(int64_t)k * ldP + i0 + col] : 0.0;
+            Pj[kk][col] = (k < k1 && j0 + col < m) ? P[(int64_t)k * ldP + j0 + col] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < GR_T; ++kk) {
+            double x0 = Pi[kk][ty * 2], x1 = Pi[kk][ty * 2 + 1];
+            double y0 = Pj[kk][tx * 2], y1 = Pj[kk][tx * 2 + 1];
+            a00 = fma(x0, y0, a00); a01 = fma(x0, y1, a01);
+            a10 = fma(x1, y0, a10); a11 = fma(x1, y1, a11);
+        }
+    }
+    double *dst = part + (size_t)blockIdx.z * m * m;
+    int i = i0 + ty * 2, j = j0 + tx * 2;
+    if (i < m && j < m) dst[(size_t)i * m + j] = a00;
+    if (i < m && j + 1 < m) dst[(size_t)i * m + j + 1] = a01;
+    if (i + 1 < m && j < m) dst[(size_t)(i + 1) * m + j] = a10;
+    if (i + 1 < m && j + 1 < m) dst[(size_t)(i + 1) * m + j + 1] = a11;
+}
+
+__global__ void gram_finish_kernel(const double *__restrict__ part, int nsplit, int m, double *__restrict__ H, int64_t ldh) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m * m) return;
+    int i = q / m, j = q - i * m;
+    double s = 0.0;
+    for (int z = 0; z < nsplit; ++z) s += part[(size_t)z * m * m + q];
+    H[(int64_t)i * ldh + j] -= s;
+}
+
+extern "C" int rpc_gram_residual(rpc_ctx *ctx, void *stream, const double *P, int c, int m, int64_t ldP, double *H,
+                                 int64_t ldh) {
+    RPC_CHECK_ARG(ctx && H && m >= 1 && c >= 0, "null pointer or bad sizes");
+    if (c == 0) return 0;
+    RPC_CHECK_ARG(P != nullptr, "P required when c > 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    int nsplit = (c + GR_KC - 1) / GR_KC;
+    int rc = rpc_ws_reserve(ctx, (size_t)nsplit * m * m * sizeof(double));
+    if (rc) return rc;
+    int t = (m + GR_T - 1) / GR_T;
+    gram_partial_kernel<<<dim3(t, t, nsplit), 256, 0, st>>>(P, c, m, ldP, ctx->ws);
+    RPC_LAUNCHED(ctx);
+    gram_finish_kernel<<<(m * m + 255) / 256, 256, 0, st>>>(ctx->ws, nsplit, m, H, ldh);
+    RPC_LAUNCHED(ctx);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// rejection_cholesky (rpcholesky.py:140-157) / shifted Cholesky (rpcholesky.py:106): ONE CTA, the
+// lower triangle of H packed in shared memory when it fits (m <= 232), right-looking.
+// ------------------------------------------------------------------------------------------------
+constexpr int RC_THREADS = 1024;
+constexpr int RC_SMEM_MAX_M = 228;
+
+template <bool PACKED>
+__device__ __forceinline__ size_t tri_at(int i, int l, int64_t ld) {
+    return PACKED ? (size_t)i * (i + 1) / 2 + l : (size_t)i * ld + l;
+}
+
+template <bool PACKED>
+__global__ void __launch_bounds__(RC_THREADS, 1) rejection_cholesky_kernel(double *__restrict__ H, int m, int64_t ldh,
+                                                                          const double *__restrict__ u, int max_accept,
+                                                                          int mode, double shift, double *__restrict__ Lfull,
+                                                                          double *__restrict__ L, int64_t ldl,
+                                                                          int32_t *__restrict__ acc, int32_t *__restrict__ info) {
+    extern __shared__ double sh[];
+    double *lcol = sh;                 // [m]
+    double *u0 = sh + m;               // [m] original diagonal
+    int32_t *accpos = (int32_t *)(sh + 2 * m);   // [m]
+    double *T = PACKED ? sh + 3 * m : H;
+    const int64_t ld = ldh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = RC_THREADS / 32;
+
+    if (PACKED) {
+        for (int i = warp; i < m; i += NW)
+            for (int l = lane; l <= i; l += 32) T[tri_at<true>(i, l, ld)] = H[(int64_t)i * ldh + l];
+    }
+    for (int j = tid; j < m; j += RC_THREADS) u0[j] = H[(int64_t)j * ldh + j];
+    __syncthreads();
+    if (mode == 1 && shift != 0.0) {
+        for (int j = tid; j < m; j += RC_THREADS) T[tri_at<PACKED>(j, j, ld)] += shift;
+    }
+    // trace check (np.trace(H) <= 0 -> RuntimeError), sequential like np.trace's add.reduce is not
+    // needed: only the sign matters
+    if (tid == 0) {
+        double tr = 0.0;
+        for (int j = 0; j < m; ++j) tr += u0[j];
+        info[2] = (mode == 0 && !(tr > 0.0)) ? 1 : 0;
+        info[1] = 0;
+    }
+    __syncthreads();
+
+    int nacc = 0;
+    for (int j = 0; j < m; ++j) {
+        const double hjj = T[tri_at<PACKED>(j, j, ld)];
+        bool accept;
+        if (mode == 1) {
+            if (!(hjj > 0.0)) {               // numpy.linalg.cholesky would raise LinAlgError
+                if (tid == 0) info[1] = j + 1;
+                break;
+            }
+            accept = true;
+        } else {
+            accept = u[j] * u0[j] < hjj;      // rpcholesky.py:151
+        }
+        if (!accept) continue;
+        if (nacc == max_accept) break;        // truncation of rpcholesky.py:193-196
+        const double piv = sqrt(hjj);
+        for (int i = j + tid; i < m; i += RC_THREADS) {
+            double v = T[tri_at<PACKED>(i, j, ld)] / piv;
+            lcol[i] = v;
+            Lfull[(size_t)i * m + nacc] = v;
+        }
+        if (tid == 0) accpos[nacc] = j;
+        ++nacc;
+        __syncthreads();
+        // trailing update of the lower triangle: T[i,l] -= l_i l_l, j < l <= i
+        for (int i = j + 1 + warp; i < m; i += NW) {
+            const double li = lcol[i];
+            for (int l = j + 1 + lane; l <= i; l += 32) {
+                size_t a = tri_at<PACKED>(i, l, ld);
+                T[a] = T[a] - li * lcol[l];
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    // L = Lfull[acc, acc] (rpcholesky.py:155-156)
+    for (int q = tid; q < nacc * nacc; q += RC_THREADS) {
+        int r = q / nacc, a = q - r * nacc;
+        L[(int64_t)r * ldl + a] = a <= r ? Lfull[(size_t)accpos[r] * m + a] : 0.0;
+    }
+    for (int q = tid; q < nacc; q += RC_THREADS) acc[q] = accpos[q];
+    if (tid == 0) info[0] = nacc;
+}
+
+extern "C" int rpc_rejection_cholesky(rpc_ctx *ctx, void *stream, double *H, int m, int64_t ldh, const double *u,
+                                      int max_accept, int mode, double shift, double *L, int64_t ldl, int32_t *acc,
+                                      int32_t *info) {
+    RPC_CHECK_ARG(ctx && H && L && acc && info, "null pointer");
+    RPC_CHECK_ARG(m >= 1 && ldh >= m && ldl >= m, "bad sizes");
+    RPC_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 (rejection) or 1 (shifted Cholesky)");
+    RPC_CHECK_ARG(mode == 1 || u != nullptr, "uniforms required for rejection sampling");
+    if (max_accept > m || max_accept < 0) max_accept = m;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = rpc_ws_reserve(ctx, (size_t)m * m * sizeof(double));
+    if (rc) return rc;
+    static bool configured = false;
+    if (!configured) {
+        RPC_CUDA(cudaFuncSetAttribute(rejection_cholesky_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      220 * 1024));
+        configured = true;
+    }
+    if (m <= RC_SMEM_MAX_M) {
+        size_t shm = ((size_t)3 * m + (size_t)m * (m + 1) / 2) * sizeof(double);
+        rejection_cholesky_kernel<true><<<1, RC_THREADS, shm, st>>>(H, m, ldh, u, max_accept, mode, shift, ctx->ws, L, ldl,
+                                                                  acc, info);
+    } else {
+        size_t shm = (size_t)3 * m * sizeof(double);
+        rejection_cholesky_kernel<false><<<1, RC_THREADS, shm, st>>>(H, m, ldh, u, max_accept, mode, shift, ctx->ws, L, ldl,
+                                                                   acc, info);
+    }
+    RPC_LAUNCHED(ctx);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// panel assembly: Minv = L^{-1} (one CTA, thread per column), then At = [-(P_acc Minv^T); Minv^T; 0]
+// ------------------------------------------------------------------------------------------------
+// Mi[i*lds + j] = Minv[i][j];  MiT[i*lds + j] = Minv[j][i]
+__global__ void __launch_bounds__(1024) tri_inverse_kernel(const double *__restrict__ L, int64_t ldl, int s,
+                                                           double *__restrict__ Mi, double *__restrict__ MiT, int lds) {
+    // thread j solves L x = e_j by forward substitution; x_i lives in column j of Mi
+    for (int q = threadIdx.x; q < s * lds; q += blockDim.x) { Mi[q] = 0.0; MiT[q] = 0.0; }
+    __syncthreads();
+    const int j = threadIdx.x;
+    if (j >= s) return;
+    for (int i = j; i < s; ++i) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int l = j;
+        for (; l + 4 <= i; l += 4) {
+            a0 = fma(L[(int64_t)i * ldl + l], Mi[(size_t)l * lds + j], a0);
+            a1 = fma(L[(int64_t)i * ldl + l + 1], Mi[(size_t)(l + 1) * lds + j], a1);
+            a2 = fma(L[(int64_t)i * ldl + l + 2], Mi[(size_t)(l + 2) * lds + j], a2);
+            a3 = fma(L[(int64_t)i * ldl + l + 3], Mi[(size_t)(l + 3) * lds + j], a3);
+        }
+        for (; l < i; ++l) a0 = fma(L[(int64_t)i * ldl + l], Mi[(size_t)l * lds + j], a0);
+        double rhs = (i == j) ? 1.0 : 0.0;
+        double x = (rhs - ((a0 + a1) + (a2 + a3))) / L[(int64_t)i * ldl + i];
+        Mi[(size_t)i * lds + j] = x;
+        MiT[(size_t)j * lds + i] = x;
+    }
+}
+
+// MiT given (lds), At rows: blockIdx.x covers PB rows
+constexpr int PB = 8;
+__global__ void __launch_bounds__(256) panel_kernel(const double *__restrict__ P, int64_t ldP, int c, const int32_t *__restrict__ acc,
+                                                    int s, const double *__restrict__ MiT, int lds, int tri,
+                                                    double *__restrict__ At, int64_t ldat, int k_pad) {
+    extern __shared__ double Ps[];   // [PB][s]
+    const int r0 = blockIdx.x * PB;
+    if (r0 < c) {
+        for (int q = threadIdx.x; q < PB * s; q += blockDim.x) {
+            int rr = q / s, i = q - rr * s;
+            int r = r0 + rr;
+            Ps[q] = (r < c) ? P[(int64_t)r * ldP + (acc ? acc[i] : i)] : 0.0;
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < ldat; j += blockDim.x) {
+        double out[PB];
+#pragma unroll
+        for (int rr = 0; rr < PB; ++rr) out[rr] = 0.0;
+        if (j < s) {
+            // rows of P: -(sum_i P[r][acc_i] * Minv[j][i]), Minv[j][i] = MiT[i][j]; i <= j when triangular
+            const int iend = tri ? j + 1 : s;
+            bool anyP = r0 < c;
+            if (anyP) {
+                for (int i = 0; i < iend; ++i) {
+                    const double mv = MiT[(size_t)i * lds + j];
+#pragma unroll
+                    for (int rr = 0; rr < PB; ++rr) out[rr] = fma(Ps[rr * s + i], mv, out[rr]);
+                }
+            }
+#pragma unroll
+            for (int rr = 0; rr < PB; ++rr) {
+                int r = r0 + rr;
+                if (r < c) out[rr] = -out[rr];
+                else if (r < c + s) out[rr] = MiT[(size_t)(r - c) * lds + j];
+                else out[rr] = 0.0;
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < PB; ++rr) {
+            int r = r0 + rr;
+            if (r < k_pad) At[(int64_t)r * ldat + j] = out[rr];
+        }
+    }
+}
+
+extern "C" int rpc_build_panel(rpc_ctx *ctx, void *stream, const double *P, int64_t ldP, int c, const int32_t *acc, int s,
+                               const double *L, int64_t ldl, int mode, double *At, int64_t ldat, int k_pad) {
+    RPC_CHECK_ARG(ctx && L && At, "null pointer");
+    RPC_CHECK_ARG(s >= 1 && s <= 1024 && c >= 0 && (c == 0 || P), "bad sizes");
+    RPC_CHECK_ARG(k_pad >= c + s && ldat >= s, "k_pad >= c+s and ldat >= s required");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int lds = (s + 7) & ~7;
+    int rc = rpc_ws_reserve(ctx, (size_t)2 * s * lds * sizeof(double));
+    if (rc) return rc;
+    double *Mi = ctx->ws, *MiT = ctx->ws + (size_t)s * lds;
+    if (mode == 0) {
+        tri_inverse_kernel<<<1, 1024, 0, st>>>(L, ldl, s, Mi, MiT, lds);
+        RPC_LAUNCHED(ctx);
+    } else {
+        // Minv given in L (dense s x s): MiT[i][j] = L[j][i]
+        rc = rpc_transpose_pad(ctx, st, L, ldl, s, s, MiT, lds, s);
+        if (rc) return rc;
+    }
+    size_t shm = (size_t)PB * s * sizeof(double);
+    int blocks = (k_pad + PB - 1) / PB;
+    panel_kernel<<<blocks, 256, shm, st>>>(P, ldP, c, acc, s, MiT, lds, mode == 0 ? 1 : 0, At, ldat, k_pad);
+    RPC_LAUNCHED(ctx);
+    return 0;
+}

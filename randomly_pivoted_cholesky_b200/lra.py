@@ -1,0 +1,160 @@
+"""Result type of the hot path: PSDLowRank (reference lra.py:8-41, 87-116).
+
+`PSDLowRank(G, idx=..., rows=...)` keeps the reference's fields and methods.  G / rows may be numpy
+arrays (host container semantics, exactly the reference's) or CUDA tensors produced by the
+factorisation drivers; device-backed results expose `.G` / `.rows` as numpy arrays materialised on
+first access, and `.G_device` / `.rows_device` as (k, N) views of the padded device buffers so that
+a 16 GB factor never has to leave HBM.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+class AbstractPSDLowRank:
+    """lra.py:8-41."""
+
+    def __init__(self, **kwargs):
+        self.idx = kwargs["idx"] if ("idx" in kwargs) else None
+        self._rows = kwargs["rows"] if ("rows" in kwargs) else None
+        self._rows_host = None
+
+    @property
+    def rows(self):
+        if isinstance(self._rows, torch.Tensor):
+            if self._rows_host is None:
+                self._rows_host = self._rows.cpu().numpy()
+            return self._rows_host
+        return self._rows
+
+    @rows.setter
+    def rows(self, value):
+        self._rows = value
+        self._rows_host = None
+
+    @property
+    def rows_device(self):
+        return self._rows if isinstance(self._rows, torch.Tensor) else None
+
+    def matrix(self):
+        return self @ np.identity(self.shape[0])
+
+    def get_rows(self):
+        if not (self._rows is None):
+            return self.rows
+        raise RuntimeError("Rows are not defined for this low-rank approximation")
+
+    def get_indices(self):
+        if not (self.idx is None):
+            return self.idx
+        raise RuntimeError("Indices are not defined for this low-rank approximation")
+
+
+class CompactEigenvalueDecomposition(AbstractPSDLowRank):
+    """lra.py:43-85 (host numpy; off the hot path, kept so PSDLowRank.eigenvalue_decomposition works)."""
+
+    def __init__(self, V, Lambda, **kwargs):
+        super().__init__(**kwargs)
+        self.V = V
+        self.Lambda = Lambda
+        self.shape = (self.V.shape[0], self.V.shape[0])   # the reference stores (V[0], V[0]) (lra.py:49, a bug)
+
+    @staticmethod
+    def from_G(G, **kwargs):
+        Q, R = np.linalg.qr(np.asarray(G).T, "reduced")
+        U, S, _ = np.linalg.svd(R)
+        return CompactEigenvalueDecomposition(Q @ U, S ** 2, **kwargs)
+
+    def evals(self):
+        return self.Lambda
+
+    def evecs(self):
+        return self.V
+
+    def trace(self):
+        return sum(self.Lambda)
+
+    def __matmul__(self, other):
+        if other.ndim == 1:
+            return self.V @ (self.Lambda * (self.V.T @ other))
+        return self.V @ (self.Lambda[:, np.newaxis] * (self.V.T @ other))
+
+    def rank(self):
+        return len(self.Lambda)
+
+    def eigenvalue_decomposition(self):
+        return self
+
+    def krr(self, b, lam):
+        VTb = self.V.T @ b
+        diag = self.Lambda + lam
+        if b.ndim == 1:
+            return b / lam + self.V @ (np.divide(VTb, diag) - VTb / lam)
+        return b / lam + self.V @ (np.divide(VTb, diag[:, np.newaxis]) - VTb / lam)
+
+
+class PSDLowRank(AbstractPSDLowRank):
+    """A ~= G^T G with G of shape (k, N): lra.py:87-116."""
+
+    def __init__(self, G, n=None, **kwargs):
+        super().__init__(**kwargs)
+        self._G = G
+        self._G_host = None
+        ncols = G.shape[1] if n is None else n
+        self.shape = (ncols, ncols)
+
+    # numpy view of the factor (materialised from the device on first use)
+    @property
+    def G(self):
+        if isinstance(self._G, torch.Tensor):
+            if self._G_host is None:
+                self._G_host = self._G.cpu().numpy()
+            return self._G_host
+        return self._G
+
+    @G.setter
+    def G(self, value):
+        self._G = value
+        self._G_host = None
+
+    @property
+    def G_device(self):
+        return self._G if isinstance(self._G, torch.Tensor) else None
+
+    def _on_device(self):
+        return isinstance(self._G, torch.Tensor) and self._G.is_cuda
+
+    def trace(self):
+        if self._on_device():
+            return float(torch.linalg.norm(self._G) ** 2)      # lra.py:94-95, ||G||_F^2
+        return np.linalg.norm(self.G, "fro") ** 2
+
+    def __matmul__(self, other):
+        if self._on_device():
+            o = torch.as_tensor(np.asarray(other, dtype=np.float64), device=self._G.device)
+            return (self._G.T @ (self._G @ o)).cpu().numpy()
+        return self.G.T @ (self.G @ other)
+
+    def rank(self):
+        return self._G.shape[0]
+
+    def matrix(self):
+        if self._on_device():
+            return (self._G.T @ self._G).cpu().numpy()
+        return self.G.T @ self.G
+
+    def eigenvalue_decomposition(self):
+        return CompactEigenvalueDecomposition.from_G(self.G, idx=self.idx, rows=self.rows)
+
+    def scale(self, scaling):
+        if self._on_device():
+            sc = torch.as_tensor(np.asarray(scaling, dtype=np.float64), device=self._G.device)
+            return PSDLowRank(self._G * sc[None, :], idx=self.idx, rows=self._rows)
+        return PSDLowRank(self.G * scaling[np.newaxis, :], idx=self.idx, rows=self.rows)
+
+    def get_left_factor(self):
+        return self.G.T
+
+    def get_right_factor(self):
+        return self.G

@@ -1,0 +1,108 @@
+"""Tensor-level wrappers of single C-ABI entry points (include/rpc_b200.h), used by the tests, bench.py
+and anyone who wants one kernel of the path without the drivers.  Inputs are numpy arrays or CUDA
+tensors; outputs are CUDA tensors unless stated.  Every function runs the CUDA library — no fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import COL_ALIGN, KT, check
+from .matrix import _cuda_device, _ptr, _round_up, _stream
+
+
+def _dev_f64(x, dev):
+    if isinstance(x, torch.Tensor):
+        return x.to(dev, torch.float64).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev)
+
+
+def _ctx(dev):
+    return _lib.Context.get(dev.index)
+
+
+def sample_pivots(diag, u, device=None):
+    """numpy `Generator.choice(len(diag), size=len(u), p=diag/sum(diag))` given its uniforms, bit-exact.
+    Returns (idx int64 tensor, python_sum_of_diag float).  Raises ValueError like numpy on bad p."""
+    dev = _cuda_device(device)
+    ctx = _ctx(dev)
+    d = _dev_f64(diag, dev)
+    n = d.numel()
+    n_pad = _round_up(n, COL_ALIGN)
+    dp = torch.zeros((n_pad,), dtype=torch.float64, device=dev)
+    dp[:n] = d
+    uu = _dev_f64(np.atleast_1d(u), dev)
+    m = uu.numel()
+    idx = torch.empty((max(m, 1),), dtype=torch.int64, device=dev)
+    stats = torch.zeros((4,), dtype=torch.float64, device=dev)
+    check(ctx.lib.rpc_sample_pivots(ctx.handle, _stream(), _ptr(dp), n_pad, _ptr(uu) if m else None, m,
+                                    _ptr(idx) if m else None, _ptr(stats)), "rpc_sample_pivots")
+    sh = stats.cpu().numpy()
+    if sh[2] != 0:
+        raise RuntimeError("internal error: exact-scan binade bound violated")
+    if sh[1] != 0:
+        raise ValueError("probabilities are not a distribution (sum <= 0, NaN or negative entries)")
+    return idx[:m], float(sh[0])
+
+
+def rejection_cholesky(H, u, max_accept=-1, device=None):
+    """rejection_cholesky(H) of rpcholesky.py:140-157 with `u` replacing the np.random.rand() calls.
+    Returns (L (s x s) tensor, accepted positions int64 numpy)."""
+    dev = _cuda_device(device)
+    ctx = _ctx(dev)
+    Hd = _dev_f64(H, dev).clone()
+    if Hd.ndim != 2 or Hd.shape[0] != Hd.shape[1]:
+        raise RuntimeError("rejection_cholesky requires a square matrix")
+    m = Hd.shape[0]
+    ud = _dev_f64(u, dev)
+    L = torch.zeros((m, m), dtype=torch.float64, device=dev)
+    acc = torch.zeros((m,), dtype=torch.int32, device=dev)
+    info = torch.zeros((4,), dtype=torch.int32, device=dev)
+    check(ctx.lib.rpc_rejection_cholesky(ctx.handle, _stream(), _ptr(Hd), m, m, _ptr(ud), int(max_accept), 0, 0.0, _ptr(L), m,
+                                         _ptr(acc), _ptr(info)), "rpc_rejection_cholesky")
+    ih = info.cpu().numpy()
+    if ih[2] != 0:
+        raise RuntimeError("rejection_cholesky requires a strictly positive trace")
+    s = int(ih[0])
+    return L[:s, :s], acc[:s].cpu().numpy().astype(np.int64)
+
+
+def shifted_cholesky(Cm, shift, device=None):
+    """np.linalg.cholesky(C + shift*I) on the device; returns (L, info) with info = failing pivot + 1 or 0."""
+    dev = _cuda_device(device)
+    ctx = _ctx(dev)
+    Hd = _dev_f64(Cm, dev).clone()
+    m = Hd.shape[0]
+    L = torch.zeros((m, m), dtype=torch.float64, device=dev)
+    acc = torch.zeros((m,), dtype=torch.int32, device=dev)
+    info = torch.zeros((4,), dtype=torch.int32, device=dev)
+    check(ctx.lib.rpc_rejection_cholesky(ctx.handle, _stream(), _ptr(Hd), m, m, None, m, 1, float(shift), _ptr(L), m, _ptr(acc),
+                                         _ptr(info)), "rpc_rejection_cholesky")
+    ih = info.cpu().numpy()
+    return L[:int(ih[0]), :int(ih[0])], int(ih[1])
+
+
+def schur_update(G, c, rows_new, P, L, diag, device=None):
+    """One block update on explicit operands (test / bench helper).
+
+    G: (k, n_pad) tensor updated in place at rows [c, c+s); rows_new: (s, n_pad); P: (c, s) = G[:c, S];
+    L: (s, s) lower triangular; diag: (n_pad,) updated in place.  Computes
+    G[c:c+s] = L^{-1}(rows_new - P^T G[:c]); diag = max(diag - colsum(G[c:c+s]^2), 0).
+    """
+    dev = G.device
+    ctx = _ctx(dev)
+    s = rows_new.shape[0]
+    n_pad = G.shape[1]
+    k_pad = _round_up(c + s, KT)
+    ldat = _round_up(s, 256)
+    At = torch.empty((k_pad, ldat), dtype=torch.float64, device=dev)
+    Pd = P.contiguous() if c > 0 else None
+    Ld = L.contiguous()
+    check(ctx.lib.rpc_build_panel(ctx.handle, _stream(), _ptr(Pd), s, c, None, s, _ptr(Ld), s, 0, _ptr(At), ldat, k_pad),
+          "rpc_build_panel")
+    check(ctx.lib.rpc_schur_update(ctx.handle, _stream(), _ptr(G), G.stride(0), c, s, _ptr(At), ldat, k_pad, _ptr(rows_new),
+                                   rows_new.stride(0), _ptr(diag), n_pad), "rpc_schur_update")
+    return At

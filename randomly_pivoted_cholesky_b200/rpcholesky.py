@@ -1,0 +1,369 @@
+"""The factorisation drivers: rpcholesky / simple_rpcholesky / block_rpcholesky / accelerated_rpcholesky.
+
+Same entry points, keyword arguments, random-stream consumption and error behaviour as the reference's
+rpcholesky.py (:12-50 simple, :65-138 block, :140-157 + :159-232 accelerated, :234-257 dispatch); every
+N-proportional or b x b operation runs in the CUDA library (include/rpc_b200.h).  The host only draws
+the uniforms (numpy, so that a seeded replay reproduces the reference's pivots bit for bit), reads back
+the per-round pivot indices / accepted count, and keeps the pivot list.
+
+Random streams:
+  proposals  <- np.random.default_rng()      one double per step (simple), 2*min(k-c,b) per block, b per round
+  rejections <- np.random.random_sample(b)   global legacy stream, b per round (== b calls of np.random.rand())
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import time
+from warnings import warn
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import KT, check
+from .lra import PSDLowRank
+from .matrix import AbstractPSDMatrix, PSDMatrix, _ptr, _round_up, _stream
+
+EPS = float(np.finfo(float).eps)
+AT_LD_ALIGN = 256          # panel leading dimension granularity (widest row tile of the DMMA kernel)
+
+
+def _as_operator(A):
+    if isinstance(A, AbstractPSDMatrix):
+        return A
+    if isinstance(A, (np.ndarray, torch.Tensor)):
+        return PSDMatrix(A)                                   # rpcholesky.py:13-14, 66-67, 160-161
+    raise RuntimeError("A must be an ndarray or an AbstractPSDMatrix")
+
+
+class _State:
+    """Device buffers of one factorisation (data layout in HBM)."""
+
+    def __init__(self, A, k, m_max):
+        self.A = A
+        self.dev = A.device
+        self.ctx = A._ctx
+        self.lib = self.ctx.lib
+        self.n = A.shape[0]
+        self.n_pad = A.n_pad
+        self.k = k
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        self.G = torch.empty((k, self.n_pad), **f64)
+        self.rows = torch.empty((k, self.n_pad), **f64)
+        self.diag = torch.empty((self.n_pad,), **f64)
+        self.m_max = m_max
+        self.u_dev = torch.empty((2 * m_max,), **f64)
+        self.idx_dev = torch.empty((m_max,), dtype=torch.int64, device=self.dev)
+        self.sel_dev = torch.empty((m_max,), dtype=torch.int64, device=self.dev)
+        self.stats = torch.zeros((4,), **f64)
+        self.piv = A._dev_new_payload(m_max)
+        self.sel = A._dev_new_payload(m_max)
+        self.P = torch.empty((max(k, 1), m_max), **f64)
+        self.H = torch.empty((m_max, m_max), **f64)
+        self.L = torch.empty((m_max, m_max), **f64)
+        self.acc = torch.zeros((m_max,), dtype=torch.int32, device=self.dev)
+        self.info = torch.zeros((4,), dtype=torch.int32, device=self.dev)
+        self.ldat = _round_up(m_max, AT_LD_ALIGN)
+        self.k_pad_max = _round_up(k + m_max, KT)
+        self.At = torch.empty((self.k_pad_max, self.ldat), **f64)
+        # pinned staging
+        self.u_host = torch.empty((2 * m_max,), dtype=torch.float64).pin_memory()
+        self.sel_host = torch.empty((m_max,), dtype=torch.int64).pin_memory()
+        A._dev_diag_into(self.diag)
+        A._count(self.n)                                       # A.diag() counts N queries (matrix.py:33-39)
+
+    # ---- thin wrappers over the C ABI ------------------------------------------------------------
+    def upload_uniforms(self, up, ur=None):
+        m = len(up)
+        self.u_host[:m] = torch.from_numpy(up)
+        tot = m
+        if ur is not None:
+            self.u_host[m:m + len(ur)] = torch.from_numpy(ur)
+            tot = m + len(ur)
+        self.u_dev[:tot].copy_(self.u_host[:tot], non_blocking=True)
+
+    def sample(self, m, u_off=0):
+        u = C.c_void_p(self.u_dev.data_ptr() + 8 * u_off)
+        check(self.lib.rpc_sample_pivots(self.ctx.handle, _stream(), _ptr(self.diag), self.n_pad, u, m, _ptr(self.idx_dev),
+                                         _ptr(self.stats)), "rpc_sample_pivots")
+
+    def gather(self, idx_dev, m, piv, c, with_P=True):
+        A = self.A
+        X = getattr(A, "_Xd", None)
+        xn = getattr(A, "_xnorm", None)
+        d = getattr(A, "d_pad", 0)
+        check(self.lib.rpc_gather_pivots(self.ctx.handle, _stream(), _ptr(idx_dev), m, _ptr(X), _ptr(xn), d, d,
+                                         _ptr(piv.X) if piv is not None else None,
+                                         _ptr(piv.norm) if piv is not None else None, d,
+                                         _ptr(self.G) if (with_P and c > 0) else None, self.n_pad, c if with_P else 0,
+                                         _ptr(self.P) if (with_P and c > 0) else None, self.m_max), "rpc_gather_pivots")
+
+    def residual_block(self, idx_dev, m, piv, c, count=True):
+        """H = A[idx,idx] - G[:c,idx]^T G[:c,idx]  (rpcholesky.py:189; also C of :103, which the reference
+        slices out of G_new and therefore does not count as queries)."""
+        self.A._dev_block_into(idx_dev, m, piv, self.H, self.m_max)
+        if count:
+            self.A._count(m * m)
+        check(self.lib.rpc_gram_residual(self.ctx.handle, _stream(), _ptr(self.P), c, m, self.m_max, _ptr(self.H),
+                                         self.m_max), "rpc_gram_residual")
+
+    def cholesky(self, m, mode, max_accept, shift, u_off):
+        u = C.c_void_p(self.u_dev.data_ptr() + 8 * u_off)
+        check(self.lib.rpc_rejection_cholesky(self.ctx.handle, _stream(), _ptr(self.H), m, self.m_max, u, max_accept, mode,
+                                              float(shift), _ptr(self.L), self.m_max, _ptr(self.acc), _ptr(self.info)),
+              "rpc_rejection_cholesky")
+
+    def update(self, c, s, acc_dev, sel_idx_dev, sel_piv, panel_mode=0, Lmat=None):
+        """rows[c:c+s] = A[S,:]; G[c:c+s] = L^{-1}(rows - P^T G[:c]); diag update (rpcholesky.py:101-107,128-129 / 205-209)."""
+        k_pad = _round_up(c + s, KT)
+        Lm = self.L if Lmat is None else Lmat
+        check(self.lib.rpc_build_panel(self.ctx.handle, _stream(), _ptr(self.P), self.m_max, c, _ptr(acc_dev), s, _ptr(Lm),
+                                       Lm.stride(0), panel_mode, _ptr(self.At), self.ldat, k_pad), "rpc_build_panel")
+        rows_ptr = C.c_void_p(self.rows.data_ptr() + 8 * c * self.n_pad)
+        self.A._dev_rows_into(sel_idx_dev, s, sel_piv, rows_ptr, self.n_pad)
+        self.A._count(s * self.n)
+        check(self.lib.rpc_schur_update(self.ctx.handle, _stream(), _ptr(self.G), self.n_pad, c, s, _ptr(self.At), self.ldat,
+                                        k_pad, rows_ptr, self.n_pad, _ptr(self.diag), self.n_pad), "rpc_schur_update")
+
+    def result(self, count, arr_idx):
+        n = self.n
+        return PSDLowRank(self.G[:count, :n], idx=arr_idx, rows=self.rows[:count, :n])
+
+
+def _raise_if_invalid(stats_host):
+    if stats_host[2] != 0.0:
+        raise RuntimeError("internal error: exact-scan binade bound violated")
+    if stats_host[1] != 0.0:
+        # what Generator.choice raises when diags/sum(diags) is not a distribution (callers rely on it:
+        # experiments/comparison.py:51)
+        raise ValueError("probabilities contain NaN" if not (stats_host[0] == stats_host[0]) or stats_host[0] == 0.0
+                         else "probabilities are not non-negative")
+
+
+# --------------------------------------------------------------------------------------------------
+# simple RPCholesky: cholesky_helper(A, k, 'rp', stoptol) -- rpcholesky.py:12-50
+# --------------------------------------------------------------------------------------------------
+def cholesky_helper(A, k, alg, stoptol=0):
+    if alg != "rp":
+        if alg in ("greedy", "rgreedy"):
+            # they share the loop but are SURVEY.md section 8(f) rows, not built yet
+            raise NotImplementedError("greedy pivoting is outside the round-1 hot path")
+        raise RuntimeError("Algorithm '{}' not recognized".format(alg))
+    A = _as_operator(A)
+    if stoptol is None:
+        stoptol = 0
+    st = _State(A, k, 1)
+    lib, ctx = st.lib, st.ctx
+    rng = np.random.default_rng()
+    spec, X, xn, d, ldx, Ad, lda = A._simple_step_args()
+    spec_ref = C.byref(spec) if spec is not None else None
+
+    idx_all = torch.empty((k + 1,), dtype=torch.int64, device=st.dev)
+    stats_all = torch.zeros((k + 1, 4), dtype=torch.float64, device=st.dev)
+    # one uniform per step (rng.choice(range(n), p=...), rpcholesky.py:31); the stream is state independent,
+    # so all k are drawn and uploaded at once and the loop below never waits for the device
+    u_all = torch.from_numpy(rng.random(k)).to(st.dev)
+    count = k
+    arr_len = k
+    check_every_step = stoptol > 0
+    orig_trace = None
+
+    def sample_into(i, m):
+        check(lib.rpc_sample_pivots(ctx.handle, _stream(), _ptr(st.diag), st.n_pad,
+                                    C.c_void_p(u_all.data_ptr() + 8 * i) if m else None, m,
+                                    C.c_void_p(idx_all.data_ptr() + 8 * i) if m else None,
+                                    C.c_void_p(stats_all.data_ptr() + 32 * i)), "rpc_sample_pivots")
+
+    for i in range(k):
+        sample_into(i, 1)
+        if check_every_step:
+            sh = stats_all[i].cpu().numpy()
+            _raise_if_invalid(sh)
+            if i == 0:
+                orig_trace = float(sh[0])
+            elif float(sh[0]) <= stoptol * orig_trace:         # rpcholesky.py:45-48 (drops row i-1, keeps its index)
+                count = i - 1
+                arr_len = i
+                break
+        check(lib.rpc_simple_step(ctx.handle, _stream(), spec_ref, _ptr(X), _ptr(xn), d, ldx, _ptr(Ad), lda, st.n,
+                                  _ptr(idx_all), i, _ptr(st.G), st.n_pad, _ptr(st.rows), st.n_pad, _ptr(st.diag), st.n_pad),
+              "rpc_simple_step")
+        A._count(st.n)
+    else:
+        if check_every_step:
+            sample_into(k, 0)
+            sh = stats_all[k].cpu().numpy()
+            if float(sh[0]) <= stoptol * orig_trace:
+                count = k - 1
+    stats_host = stats_all[:arr_len].cpu().numpy()
+    for r in range(arr_len):
+        _raise_if_invalid(stats_host[r])
+    arr_idx = [int(v) for v in idx_all[:arr_len].cpu().numpy()]
+    return st.result(count, arr_idx)
+
+
+# --------------------------------------------------------------------------------------------------
+# block RPCholesky: block_cholesky_helper(A, k, b, 'rp', strategy='regularize') -- rpcholesky.py:65-138
+# --------------------------------------------------------------------------------------------------
+def block_cholesky_helper(A, k, b, alg, stoptol=1e-14, strategy="regularize", rbrp_atol=0.0, rbrp_rtol="1/b"):
+    if alg != "rp":
+        if alg == "greedy":
+            raise NotImplementedError("block greedy pivoting is outside the round-1 hot path")
+        raise RuntimeError("Algorithm '{}' not recognized".format(alg))
+    if strategy not in ("regularize", "rbrp"):
+        raise ValueError("Strategy '{}' not recognized".format(strategy))
+    if strategy == "rbrp":
+        raise NotImplementedError("strategy='rbrp' (LAPACK pstrf pivoting) is a SURVEY.md section 8(f) row")
+    A = _as_operator(A)
+    if stoptol is None:
+        stoptol = 1e-14
+    b = int(b)
+    st = _State(A, k, 2 * min(b, k))
+    scale = 2.0 * float(torch.max(st.diag))                   # rpcholesky.py:72
+    rng = np.random.default_rng()
+    arr_idx = []
+    counter = 0
+    orig_trace = None
+    count = k
+    while counter < k:
+        block_size = min(k - counter, b)
+        up = rng.random(2 * block_size)                        # rng.choice(..., size=2*block_size) (:91)
+        st.upload_uniforms(up)
+        st.sample(2 * block_size)
+        host = torch.cat([st.stats, st.idx_dev[:2 * block_size].to(torch.float64)]).cpu().numpy()   # one sync
+        stats_host = host[:4]
+        _raise_if_invalid(stats_host)
+        if orig_trace is None:
+            orig_trace = float(stats_host[0])
+        elif stoptol > 0 and float(stats_host[0]) <= stoptol * orig_trace:     # :133-136, checked after the previous block
+            count = counter
+            break
+        idx = np.unique(host[4:].astype(np.int64))[:block_size]                # :92
+        block_size = len(idx)
+        arr_idx.extend(idx)
+        st.sel_host[:block_size] = torch.from_numpy(idx)
+        st.sel_dev[:block_size].copy_(st.sel_host[:block_size], non_blocking=True)
+        st.gather(st.sel_dev, block_size, st.sel, counter)
+        st.residual_block(st.sel_dev, block_size, st.sel, counter, count=False)   # C of :103
+        Hcopy = st.H[:block_size, :block_size].clone()
+        st.cholesky(block_size, 1, block_size, EPS * b * scale, 0)            # :106
+        info = st.info.cpu().numpy()
+        if info[1] != 0:                                                       # :109-114
+            warn("Cholesky failed in block partial Cholesky. Falling back to eigendecomposition")
+            evals, evecs = torch.linalg.eigh(Hcopy)
+            pos = evals > 0
+            scal = torch.where(pos, evals.clamp_min(1e-300) ** -0.5, torch.zeros_like(evals))
+            scal = torch.where(evals < 0, torch.zeros_like(evals), scal)
+            T = (scal[:, None] * evecs.T).contiguous()
+            st.update(counter, block_size, None, st.sel_dev, st.sel, panel_mode=1, Lmat=T)
+        else:
+            st.update(counter, block_size, None, st.sel_dev, st.sel)
+        counter += block_size
+    else:
+        if stoptol > 0:
+            st.sample(0)
+            sh = st.stats.cpu().numpy()
+            if float(sh[0]) <= stoptol * orig_trace:
+                count = counter
+    return st.result(min(count, counter), arr_idx)
+
+
+# --------------------------------------------------------------------------------------------------
+# accelerated RPCholesky -- rpcholesky.py:159-232 (rejection_cholesky :140-157 runs on the device)
+# --------------------------------------------------------------------------------------------------
+def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
+    A = _as_operator(A)
+    if stoptol is None:
+        stoptol = 1e-13
+    auto_b = False
+    if b == "auto":                                            # :169-173
+        b = int(np.ceil(k / 10))
+        auto_b = True
+    b = int(b)
+    b_cap = max(b, int(math.ceil(k / 3)), 10) if auto_b else b
+    st = _State(A, k, b_cap)
+    rng = np.random.default_rng()
+    arr_idx = np.zeros(k, dtype=int)
+    counter = 0
+    orig_trace = None
+    count = k
+    rounds = []
+    while counter < k:
+        t0 = time.perf_counter()
+        up = rng.random(b)                                     # :184
+        legacy_state = np.random.get_state()
+        ur = np.random.random_sample(b)                        # the b np.random.rand() calls of :151
+        st.upload_uniforms(up, ur)
+        st.sample(b)
+        st.gather(st.idx_dev, b, st.piv, counter)
+        st.residual_block(st.idx_dev, b, st.piv, counter)      # :189
+        st.cholesky(b, 0, k - counter, 0.0, b)                 # :190 + truncation :193-196
+        host = torch.cat([st.stats, st.info.to(torch.float64), st.acc[:b].to(torch.float64),
+                          st.idx_dev[:b].to(torch.float64)]).cpu().numpy()          # the round's only sync
+        stats_host, info = host[:4], host[4:8].astype(np.int64)
+        _raise_if_invalid(stats_host)
+        if orig_trace is None:
+            orig_trace = float(stats_host[0])
+        elif stoptol > 0 and float(stats_host[0]) <= stoptol * orig_trace:          # :224-227
+            np.random.set_state(legacy_state)                  # this round never happens in the reference
+            A.queries -= b * b
+            count = counter
+            break
+        if info[2] != 0:
+            raise RuntimeError("rejection_cholesky requires a strictly positive trace")      # :145
+        num_sel = int(info[0])
+        accepted = host[8:8 + num_sel].astype(np.int64)
+        idx = host[8 + b:8 + 2 * b].astype(np.int64)[accepted]
+        arr_idx[counter:counter + num_sel] = idx
+        t1 = time.perf_counter()
+        if num_sel > 0:
+            st.sel_host[:num_sel] = torch.from_numpy(idx)
+            st.sel_dev[:num_sel].copy_(st.sel_host[:num_sel], non_blocking=True)
+            st.gather(st.sel_dev, num_sel, st.sel, 0, with_P=False)
+            st.update(counter, num_sel, st.acc, st.sel_dev, st.sel)
+        counter += num_sel
+        rounds.append(num_sel)
+        if auto_b:                                             # :211-220, on device-synchronised wall time
+            torch.cuda.synchronize(st.dev)
+            t2 = time.perf_counter()
+            rejection_time, process_time = t1 - t0, t2 - t1
+            target = int(np.ceil(b * process_time / (4 * max(rejection_time, 1e-9))))
+            b = max([min([target, int(np.ceil(1.5 * b)), int(np.ceil(k / 3))]), int(np.ceil(b / 3)), 10])
+            b = min(b, b_cap)
+        if verbose:
+            print("Accepted {} / {}".format(num_sel, len(accepted)))
+    else:
+        if stoptol > 0:
+            st.sample(0)
+            sh = st.stats.cpu().numpy()
+            if float(sh[0]) <= stoptol * orig_trace:
+                count = counter
+    res = st.result(min(count, counter), arr_idx)
+    res.rounds = rounds
+    return res
+
+
+# --------------------------------------------------------------------------------------------------
+# dispatch -- rpcholesky.py:234-257
+# --------------------------------------------------------------------------------------------------
+def rpcholesky(A, k, b=None, accelerated=True, **kwargs):
+    if b is None:
+        if accelerated:
+            return accelerated_rpcholesky(A, k, **kwargs)
+        return cholesky_helper(A, k, "rp", **kwargs)
+    if accelerated:
+        return accelerated_rpcholesky(A, k, b, **kwargs)
+    return block_cholesky_helper(A, k, b, "rp", **kwargs)
+
+
+def simple_rpcholesky(A, k, **kwargs):
+    return rpcholesky(A, k, b=None, accelerated=False, **kwargs)
+
+
+def block_rpcholesky(A, k, b=100, **kwargs):
+    return rpcholesky(A, k, b=b, accelerated=False, **kwargs)
+
+
+def greedy(A, k, randomized_tiebreaking=False, b=1, **kwargs):
+    raise NotImplementedError("greedy pivoting (rpcholesky.py:245-251) is a SURVEY.md section 8(f) row, not built yet")

@@ -1,0 +1,322 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden fixtures that
+the unmodified reference produced (tests/golden/make_golden.py).  Run on the B200 box with `-m gpu`.
+
+Tolerances (BASELINE.json north_star): pivots bit-exact; F (= G^T) and A[S,:] within 1e-10 relative
+Frobenius norm; equal trace-norm error.
+"""
+import os
+from unittest import mock
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from make_golden import CASES, KERNEL_CASES, golden_inputs, kernel_inputs  # noqa: E402
+from oracle import rpc_oracle as orc  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+F_TOL = 1e-10
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name + ".npz"))
+
+
+def relerr(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def rpc():
+    import randomly_pivoted_cholesky_b200 as pkg
+    pkg.load()
+    return pkg
+
+
+def replay(seed):
+    """The replay recipe of SURVEY.md 8(c): same patch the golden generator applied to the reference."""
+    np.random.seed(seed)
+    return mock.patch("numpy.random.default_rng", lambda *a, **k: np.random.Generator(np.random.PCG64(seed)))
+
+
+def make_operator(rpc, inp):
+    if "dense" in inp:
+        return inp["dense"]
+    return rpc.KernelMatrix(inp["X"], kernel=inp["kernel"], bandwidth=inp["bandwidth"], **inp["kw"])
+
+
+def run_gpu(rpc, spec):
+    inp = golden_inputs(spec)
+    A = make_operator(rpc, inp)
+    kw = {"stoptol": spec["stoptol"]} if "stoptol" in spec else {}
+    with replay(spec["seed"]):
+        if spec["alg"] == "simple":
+            lra = rpc.simple_rpcholesky(A, spec["k"], **kw)
+        elif spec["alg"] == "block":
+            lra = rpc.block_rpcholesky(A, spec["k"], b=spec["b"], **kw)
+        else:
+            lra = rpc.accelerated_rpcholesky(A, spec["k"], b=spec["b"], **kw)
+    return A, lra
+
+
+# rank-deficient cases: after the residual is exhausted the reference divides round-off by round-off, so
+# only the rows computed while the residual is still resolved are comparable
+ILL_CONDITIONED = {"accel_stoptol", "block_stoptol", "simple_stoptol"}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_factorisation_matches_reference(rpc, name):
+    spec = CASES[name]
+    gold = load(name)
+    A, lra = run_gpu(rpc, spec)
+    idx = np.asarray(lra.idx, dtype=np.int64)
+    assert np.array_equal(idx, gold["idx"]), "pivots must be bit-exact"
+    G, rows = lra.G, lra.rows
+    assert G.shape == gold["G"].shape and rows.shape == gold["rows"].shape
+    assert relerr(rows, gold["rows"]) <= F_TOL
+    if name in ILL_CONDITIONED:
+        r = spec["dense_rank"] - 2
+        assert relerr(G[:r], gold["G"][:r]) <= 1e-7
+        assert abs(lra.trace() - float(gold["trace"])) <= 1e-8 * abs(float(gold["trace"]))
+    else:
+        assert relerr(G, gold["G"]) <= F_TOL
+        assert abs(lra.trace() - float(gold["trace"])) <= 1e-11 * abs(float(gold["trace"]))
+    if "queries" in gold:
+        assert A.num_queries() == int(gold["queries"])
+
+
+@pytest.mark.parametrize("name", sorted(KERNEL_CASES))
+def test_kernel_values_match_reference(rpc, name):
+    spec = KERNEL_CASES[name]
+    gold = load(name)
+    X, idx, kw = kernel_inputs(spec)
+    A = rpc.KernelMatrix(X, kernel=spec["kernel"], bandwidth=spec["bw"], **kw)
+    # Matern nu=1/2 is first order in the sqrt of the round-off self-distance
+    atol = 5e-7 if name == "kern_matern05" else 1e-13
+    np.testing.assert_allclose(A[idx, :], gold["rows"], rtol=1e-12, atol=atol)
+    np.testing.assert_allclose(A[idx, idx], gold["block"], rtol=1e-12, atol=atol)
+    np.testing.assert_array_equal(A.diag(), gold["diag"])
+    np.testing.assert_allclose(A[int(idx[3]), :], gold["one_row"], rtol=1e-12, atol=atol)
+    assert A.num_queries() == 7 * 300 + 49 + 300 + 300
+
+
+def test_laplace_l1_distance_is_bit_exact(rpc):
+    """Sequential feature order == scipy cdist 'cityblock'; only exp() ulps may differ."""
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((700, 50))
+    A = rpc.KernelMatrix(X, kernel="laplace", bandwidth=50.0)
+    idx = np.arange(0, 700, 53)
+    got = A[idx, :]
+    want = orc.laplace_mtx(X[idx], X, bandwidth=50.0)
+    np.testing.assert_allclose(got, want, rtol=4e-16, atol=0)
+
+
+@pytest.mark.parametrize("d", [3, 20, 50, 130])
+@pytest.mark.parametrize("s", [1, 7, 33, 120, 200, 300])
+def test_dmma_evaluator_shapes(rpc, d, s):
+    rng = np.random.default_rng(d * 1000 + s)
+    n = 1000 + 37 * s
+    X = rng.standard_normal((n, d))
+    A = rpc.KernelMatrix(X, kernel="gaussian", bandwidth=float(np.sqrt(d)))
+    idx = rng.integers(0, n, s)
+    want = orc.gaussian_mtx(X[idx], X, bandwidth=float(np.sqrt(d)))
+    got = A[idx, :]
+    got = got.reshape(want.shape)
+    np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-14)
+
+
+@pytest.mark.parametrize("tag", ["uniform", "random", "sparse"])
+def test_sampler_golden(rpc, tag):
+    from randomly_pivoted_cholesky_b200 import ops
+    gold = load("sampler")
+    idx, S = ops.sample_pivots(gold[tag + "_diag"], gold[tag + "_u"])
+    assert np.array_equal(idx.cpu().numpy(), gold[tag + "_idx"])
+    assert S == sum(gold[tag + "_diag"])
+
+
+@pytest.mark.parametrize("n", [1, 2, 255, 256, 257, 5000, 100003, 1000000])
+@pytest.mark.parametrize("kind", ["ones", "random", "heavy", "sparse", "dyadic", "tiny"])
+def test_sampler_bit_exact_vs_numpy(rpc, n, kind):
+    """Exact sequential-cumsum reproduction: idx and python sum(diag) equal numpy's, bit for bit."""
+    from randomly_pivoted_cholesky_b200 import ops
+    rng = np.random.default_rng(n + len(kind))
+    if kind == "ones":
+        d = np.ones(n)
+    elif kind == "random":
+        d = rng.random(n)
+    elif kind == "heavy":
+        d = rng.random(n) ** 12
+    elif kind == "sparse":
+        d = rng.random(n) * (rng.random(n) < 0.05)
+        d[rng.integers(0, n)] = 1.0
+    elif kind == "dyadic":
+        d = np.ldexp(rng.integers(1, 8, n).astype(float), rng.integers(-20, 3, n))   # many rounding ties
+    else:
+        d = rng.random(n) * 1e-200
+    m = 300
+    u = rng.random(m)
+    u[0] = 0.0
+    u[1] = 1.0 - 2.0 ** -53
+    idx, S = ops.sample_pivots(d, u)
+    assert S == orc.seq_sum(d)
+    want = orc.sample_pivots(d, u)
+    assert np.array_equal(idx.cpu().numpy(), want)
+
+
+def test_sampler_raises_like_choice(rpc):
+    from randomly_pivoted_cholesky_b200 import ops
+    with pytest.raises(ValueError):
+        ops.sample_pivots(np.zeros(10), [0.5])
+    with pytest.raises(ValueError):
+        ops.sample_pivots(np.array([1.0, np.nan, 2.0]), [0.5])
+    with pytest.raises(ValueError):
+        ops.sample_pivots(np.array([1.0, -0.5, 2.0]), [0.5])
+
+
+@pytest.mark.parametrize("b", [1, 5, 64, 200, 228, 260])
+def test_rejection_cholesky_matches_oracle(rpc, b):
+    from randomly_pivoted_cholesky_b200 import ops
+    rng = np.random.default_rng(b)
+    r = max(1, b // 2)
+    B = rng.standard_normal((b, r + 3))
+    H = B @ B.T + 1e-3 * np.diag(rng.random(b))
+    u = rng.random(b)
+    Lw, accw = orc.rejection_cholesky(H.copy(), u)
+    L, acc = ops.rejection_cholesky(H, u)
+    assert np.array_equal(acc, accw)
+    np.testing.assert_allclose(L.cpu().numpy(), Lw, rtol=1e-9, atol=1e-11)
+    # truncation (rpcholesky.py:193-196)
+    if len(accw) > 2:
+        L2, acc2 = ops.rejection_cholesky(H, u, max_accept=len(accw) - 2)
+        assert np.array_equal(acc2, accw[:-2])
+        np.testing.assert_allclose(L2.cpu().numpy(), Lw[:-2, :-2], rtol=1e-9, atol=1e-11)
+    with pytest.raises(RuntimeError):
+        ops.rejection_cholesky(-np.eye(3), np.zeros(3))
+
+
+def test_shifted_cholesky_and_failure_flag(rpc):
+    from randomly_pivoted_cholesky_b200 import ops
+    rng = np.random.default_rng(3)
+    B = rng.standard_normal((40, 60))
+    Cm = B @ B.T
+    L, info = ops.shifted_cholesky(Cm, 1e-9)
+    assert info == 0
+    np.testing.assert_allclose(L.cpu().numpy(), np.linalg.cholesky(Cm + 1e-9 * np.eye(40)), rtol=1e-10, atol=1e-10)
+    bad = Cm.copy()
+    bad[7, 7] = -1.0
+    _, info = ops.shifted_cholesky(bad, 0.0)
+    assert info == 8
+
+
+@pytest.mark.parametrize("c,s", [(0, 1), (0, 40), (5, 3), (37, 16), (100, 64), (130, 130), (64, 200), (300, 256), (50, 300)])
+def test_schur_update_matches_numpy(rpc, c, s):
+    """G_new = L^{-1}(rows - P^T G[:c]) and the fused diagonal update, against numpy (fp64)."""
+    from randomly_pivoted_cholesky_b200 import ops
+    rng = np.random.default_rng(c * 1000 + s)
+    n_pad = 128 * 9
+    k = c + s
+    Gh = np.zeros((k, n_pad))
+    Gh[:c] = rng.standard_normal((c, n_pad))
+    rows = rng.standard_normal((s, n_pad))
+    P = rng.standard_normal((c, s))
+    Lh = np.tril(rng.standard_normal((s, s))) + 4 * np.sqrt(s) * np.eye(s)
+    diag = rng.random(n_pad) * 50
+    want = np.linalg.solve(Lh, rows - P.T @ Gh[:c])
+    wdiag = np.clip(diag - np.sum(want ** 2, axis=0), 0, None)
+    dev = torch.device("cuda")
+    G = torch.from_numpy(Gh).to(dev)
+    dg = torch.from_numpy(diag).to(dev)
+    ops.schur_update(G, c, torch.from_numpy(rows).to(dev), torch.from_numpy(P).to(dev), torch.from_numpy(Lh).to(dev), dg)
+    got = G[c:].cpu().numpy()
+    assert relerr(got, want) <= 1e-12
+    np.testing.assert_allclose(dg.cpu().numpy(), wdiag, rtol=1e-11, atol=1e-10)
+    assert np.array_equal(G[:c].cpu().numpy(), Gh[:c])
+
+
+def test_configs_c1_c2_against_oracle(rpc):
+    """BASELINE.json configs[0] in full and configs[1] at reduced N: GPU vs oracle on replayed draws."""
+    # C1: simple_rpcholesky, Gaussian, N=10,000 d=10 k=100
+    X = np.random.default_rng(0).standard_normal((10000, 10))
+    bw = float(np.sqrt(10))
+    with replay(1234):
+        lra = rpc.simple_rpcholesky(rpc.KernelMatrix(X, kernel="gaussian", bandwidth=bw), 100)
+    rng, legacy = orc.make_streams(1234)
+    A0 = orc.OracleKernelMatrix(X, kernel="gaussian", bandwidth=bw)
+    ref = orc.simple_rpcholesky(A0, 100, rng)
+    assert list(lra.idx) == list(ref.idx)
+    assert relerr(lra.G, ref.G) <= F_TOL and relerr(lra.rows, ref.rows) <= F_TOL
+    tr = 10000.0
+    assert abs((tr - lra.trace()) / tr - (tr - ref.trace()) / tr) <= 1e-12
+    # C2 shape at N=20,000: accelerated b=120, Gaussian d=20, k=1000
+    X = np.random.default_rng(1).standard_normal((20000, 20))
+    bw = float(np.sqrt(20))
+    with replay(4321):
+        lra = rpc.accelerated_rpcholesky(rpc.KernelMatrix(X, kernel="gaussian", bandwidth=bw), 1000, b=120)
+    rng, legacy = orc.make_streams(4321)
+    ref = orc.accelerated_rpcholesky(orc.OracleKernelMatrix(X, kernel="gaussian", bandwidth=bw), 1000, 120, rng, legacy)
+    assert np.array_equal(np.asarray(lra.idx), ref.idx)
+    assert lra.rounds == ref.rounds
+    assert relerr(lra.G, ref.G) <= F_TOL and relerr(lra.rows, ref.rows) <= F_TOL
+
+
+def test_block_laplace_against_oracle(rpc):
+    """configs[2] shape (block b=200, Laplace, d=50) at N=20,000, k=600."""
+    X = np.random.default_rng(2).standard_normal((20000, 50))
+    with replay(99):
+        lra = rpc.block_rpcholesky(rpc.KernelMatrix(X, kernel="laplace", bandwidth=50.0), 600, b=200)
+    rng, _ = orc.make_streams(99)
+    ref = orc.block_rpcholesky(orc.OracleKernelMatrix(X, kernel="laplace", bandwidth=50.0), 600, 200, rng)
+    assert [int(i) for i in lra.idx] == [int(i) for i in ref.idx]
+    assert relerr(lra.G, ref.G) <= F_TOL and relerr(lra.rows, ref.rows) <= F_TOL
+
+
+def test_dispatch_and_errors(rpc):
+    X = np.random.default_rng(3).standard_normal((600, 4))
+    A = rpc.KernelMatrix(X, kernel="matern", bandwidth=2.0, nu=2.5)
+    with replay(5):
+        a = rpc.rpcholesky(A, 30, b=10)                 # accelerated with b
+    with replay(5):
+        b_ = rpc.accelerated_rpcholesky(A, 30, b=10)
+    assert np.array_equal(a.idx, b_.idx)
+    with replay(6):
+        c = rpc.rpcholesky(A, 30, b=10, accelerated=False)
+    with replay(6):
+        d = rpc.block_rpcholesky(A, 30, b=10)
+    assert list(c.idx) == list(d.idx)
+    lra = rpc.rpcholesky(A, 40)                        # b="auto"
+    assert lra.G.shape == (40, 600) and lra.rank() == 40
+    with pytest.raises(RuntimeError):
+        rpc.KernelMatrix(X, kernel="cauchy")
+    with pytest.raises(ValueError):
+        rpc.block_rpcholesky(A, 10, b=5, strategy="nope")
+    with pytest.raises(RuntimeError):
+        rpc.cholesky_helper(A, 10, "bogus")
+    # exhausted matrix: Generator.choice raises ValueError in the reference (comparison.py:51 relies on it)
+    Z = np.zeros((50, 50))
+    Z[:3, :3] = np.eye(3)
+    with pytest.raises(ValueError):
+        rpc.simple_rpcholesky(Z, 10)
+
+
+def test_reconstruction_property_large(rpc):
+    """Size-independent properties at N = 200,000: A[S,:] rows reproduce, F F^T interpolates A on S,
+    diag(A - F F^T) >= 0 and the trace identity holds."""
+    n, d, k, b = 200000, 8, 300, 60
+    X = np.random.default_rng(7).standard_normal((n, d))
+    A = rpc.KernelMatrix(X, kernel="gaussian", bandwidth=float(np.sqrt(d)))
+    with replay(8):
+        lra = rpc.accelerated_rpcholesky(A, k, b=b)
+    S = np.asarray(lra.idx)
+    assert len(set(S.tolist())) == k
+    G = lra.G_device
+    rows = lra.rows_device
+    St = torch.as_tensor(S, device=G.device)
+    # Nystrom interpolation on the pivot rows: (F F^T)[S,:] == A[S,:]
+    rec = G[:, St].T @ G
+    err = float(torch.linalg.norm(rec - rows) / torch.linalg.norm(rows))
+    assert err <= 1e-9
+    resid = 1.0 - (G * G).sum(0)
+    assert float(resid.min()) >= -1e-12
+    assert abs(float(resid.clamp_min(0).sum()) - (n - lra.trace())) <= 1e-6 * n
