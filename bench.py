@@ -1,0 +1,342 @@
+#!/usr/bin/env python3
+"""bench.py -- rank-k RPCholesky wall time and kernel entries/s on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload tstar|c3|c2|c1] [--impl reference]
+
+A "step" is one complete factorisation (one pass of the hot path) of the named workload on synthetic
+points X = default_rng(0).standard_normal((N, d)); every step replays the same seeded uniforms
+(`numpy.random.default_rng` -> PCG64(1234), `np.random.seed(1234)`: the parity harness of SURVEY.md 8c).
+Prints ONE JSON line (rank 0).  `value` = A.num_queries() / wall with X resident in HBM; `e2e` = the same
+through the public API starting from a pinned HOST copy of X (H2D inside the timed region) and reading
+the pivots and the trace-norm error back; `roofline` = the fused Schur-update DMMA kernel against the
+measured FP64 peak; `cpu_baseline` = the numpy oracle on a bounded sample on this box's host cores.
+`--impl reference` times the oracle port alone (the reference itself is Python that cannot travel to
+the GPU box; oracle/rpc_oracle.py restates it call for call and is pinned to it by tests/golden).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from unittest import mock
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: alg, kernel, N, d, k, b, bandwidth rule
+    "tstar": dict(alg="accelerated", kernel="gaussian", N=1_000_000, d=50, k=2000, b=200, bw="sqrtd",
+                  text="T*: accelerated_rpcholesky b=200, Gaussian sigma=sqrt(d), N=1e6 d=50 k=2000, fp64"),
+    "c3": dict(alg="block", kernel="laplace", N=1_000_000, d=50, k=2000, b=200, bw="d",
+               text="configs[2]: block_rpcholesky b=200, Laplace sigma=d, N=1e6 d=50 k=2000, fp64"),
+    "c2": dict(alg="accelerated", kernel="gaussian", N=100_000, d=20, k=1000, b=120, bw="sqrtd",
+               text="configs[1]: accelerated_rpcholesky b=120, Gaussian sigma=sqrt(d), N=1e5 d=20 k=1000, fp64"),
+    "c1": dict(alg="simple", kernel="gaussian", N=10_000, d=10, k=100, b=None, bw="sqrtd",
+               text="configs[0]: simple_rpcholesky, Gaussian sigma=sqrt(d), N=1e4 d=10 k=100, fp64"),
+}
+SEED = 1234
+FP64_PEAK_FALLBACK_TFLOPS = 36.9        # profiles/fp64_peaks_r01.json (measured DMMA stream on this pool)
+
+
+def bandwidth(w):
+    return float(np.sqrt(w["d"])) if w["bw"] == "sqrtd" else float(w["d"])
+
+
+def replay(seed=SEED):
+    np.random.seed(seed)
+    return mock.patch("numpy.random.default_rng", lambda *a, **k: np.random.Generator(np.random.PCG64(seed)))
+
+
+def make_points(n, d):
+    return np.random.default_rng(0).standard_normal((n, d))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference (numpy/OpenBLAS with all host threads)
+# ------------------------------------------------------------------------------------------------
+def run_oracle(w, n_sample):
+    from oracle import rpc_oracle as orc
+    X = make_points(n_sample, w["d"])
+    A = orc.OracleKernelMatrix(X, kernel=w["kernel"], bandwidth=bandwidth(w))
+    rng, legacy = orc.make_streams(SEED)
+    t0 = time.perf_counter()
+    if w["alg"] == "accelerated":
+        orc.accelerated_rpcholesky(A, w["k"], w["b"], rng, legacy)
+    elif w["alg"] == "block":
+        orc.block_rpcholesky(A, w["k"], w["b"], rng)
+    else:
+        orc.simple_rpcholesky(A, w["k"], rng)
+    dt = time.perf_counter() - t0
+    return A.num_queries(), dt
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"]
+        return max(n) if n else 1
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def sample_size(w, target_seconds):
+    # the reference costs ~1.1e-4 s per point at k=2000,d=50 on 8 cores; scale by k^2
+    per_point = 1.1e-4 * (w["k"] / 2000.0) ** 2 * 8.0 / max(os.cpu_count() or 8, 1) + 2e-6
+    n = int(min(w["N"], max(20000, target_seconds / per_point)))
+    return max(2 * w["k"], n // 1000 * 1000)
+
+
+def reference_arm(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_s = sample_size(w, 8.0)
+    for _ in range(args.warmup):
+        run_oracle(w, n_s)
+    t_tot, q_tot = 0.0, 0
+    for _ in range(args.steps):
+        q, dt = run_oracle(w, n_s)
+        t_tot += dt
+        q_tot += q
+    value = q_tot / t_tot
+    sample = "same workload at N=%d (k, b, d, kernel unchanged; cost is linear in N)" % n_s
+    out = {
+        "impl": "reference", "metric": "kernel entries/s (rank-k RPCholesky, A.num_queries()/wall)", "value": value,
+        "unit": "entries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": {"workload": w["text"], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "entries/s", "cores": cpu_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw"
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[6]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "power_w_max": max(power), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def factorise(rpc, A, w):
+    with replay():
+        if w["alg"] == "accelerated":
+            return rpc.accelerated_rpcholesky(A, w["k"], b=w["b"])
+        if w["alg"] == "block":
+            return rpc.block_rpcholesky(A, w["k"], b=w["b"])
+        return rpc.simple_rpcholesky(A, w["k"])
+
+
+def gpu_arm(args, w):
+    import torch
+    import torch.distributed as dist
+    import randomly_pivoted_cholesky_b200 as rpc
+    import importlib
+    drv = importlib.import_module("randomly_pivoted_cholesky_b200.rpcholesky")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    rpc.load()
+
+    # weak scaling over replicas of the single-GPU workload until the row-sharded path lands (DESIGN.md section e)
+    n, d = w["N"], w["d"]
+    X = make_points(n, d)
+    Xpin = torch.from_numpy(X).pin_memory()
+    A = rpc.KernelMatrix(Xpin.to(dev), kernel=w["kernel"], bandwidth=bandwidth(w))
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        A.reset()
+        lra = factorise(rpc, A, w)
+        del lra
+    sync_all()
+
+    # ---- timed region: K steps, inputs resident -------------------------------------------------
+    from randomly_pivoted_cholesky_b200 import _lib
+    clocks = ClockSampler(local)
+    clocks.start()
+    drv.KERNEL_TIMERS = []
+    l0 = _lib.total_launches()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    queries = 0
+    for _ in range(args.steps):
+        A.reset()
+        lra = factorise(rpc, A, w)
+        queries += A.num_queries()
+        rank_k = lra.rank()
+        del lra
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.total_launches() - l0
+    timers = drv.KERNEL_TIMERS
+    drv.KERNEL_TIMERS = None
+    clk = clocks.stop()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * queries / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (fused Schur update), from the CUDA events of the timed region
+    phases = {}
+    for ev0, ev1, phase, flops, nbytes in timers:
+        p = phases.setdefault(phase, [0.0, 0.0, 0.0, 0])
+        p[0] += ev0.elapsed_time(ev1) * 1e-3
+        p[1] += flops
+        p[2] += nbytes
+        p[3] += 1
+    peak_tf = FP64_PEAK_FALLBACK_TFLOPS
+    try:
+        peak_tf = json.load(open(os.path.join(ROOT, "profiles", "fp64_peaks_r01.json")))["fp64_peak_tflops"]
+    except Exception:
+        pass
+    hbm = None
+    try:
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    roofline = None
+    if "schur" in phases:
+        sec, flops, nbytes, cnt = phases["schur"]
+        ach = flops / sec / 1e12
+        roofline = {"bound": "tensor", "kernel": "dg::gemm_kernel<MODE_SCHUR> (FP64 DMMA, fused diag update)",
+                    "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                    "peak_source": "measured FP64 DMMA peak, profiles/fp64_peaks_r01.json (MEASURED_PEAKS.json holds bf16/HBM only)",
+                    "launches": cnt, "avg_launch_ms": 1e3 * sec / cnt, "share_of_step": sec / (ms * 1e-3),
+                    "algorithmic_flops_per_launch": flops / cnt, "algorithmic_bytes_per_launch": nbytes / cnt,
+                    "hbm_gbs_achieved": nbytes / sec / 1e9, "hbm_peak_gbs": hbm}
+    phase_ms = {k: 1e3 * v[0] / args.steps for k, v in phases.items()}
+
+    # ---- e2e: host X -> H2D -> factorise -> D2H pivots + trace-norm error, through the public API ----
+    sync_all()
+    e2 = torch.cuda.Event(enable_timing=True)
+    e3 = torch.cuda.Event(enable_timing=True)
+    e2.record()
+    q2 = 0
+    d2h = 0
+    for _ in range(args.steps):
+        A2 = rpc.KernelMatrix(Xpin.to(dev, non_blocking=True), kernel=w["kernel"], bandwidth=bandwidth(w))
+        lra = factorise(rpc, A2, w)
+        idx = np.asarray(lra.idx)
+        err = (n - lra.trace()) / n                      # utils.approximation_error with trace(A) = N
+        q2 += A2.num_queries()
+        d2h = idx.nbytes + 8
+        del lra, A2
+    e3.record()
+    sync_all()
+    ms2 = e2.elapsed_time(e3)
+    if world > 1:
+        t = torch.tensor([ms2], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms2 = float(t.item())
+    e2e = {"value": world * q2 / (ms2 * 1e-3), "unit": "entries/s", "h2d_bytes_per_step": int(X.nbytes),
+           "d2h_bytes_per_step": int(d2h), "ms_per_step": ms2 / args.steps, "trace_norm_error": float(err),
+           "note": "factors G, rows stay in HBM (PSDLowRank is device backed); result read back = pivots + trace error"}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            n_s = sample_size(w, 12.0)
+            q, dt = run_oracle(w, n_s)
+            cpu = {"value": q / dt, "unit": "entries/s", "cores": cpu_threads(), "kind": "port",
+                   "sample": "same workload at N=%d, one run (%.1f s); cost is linear in N" % (n_s, dt)}
+        out = {
+            "metric": "kernel entries/s (rank-k RPCholesky, A.num_queries()/wall)", "value": value, "unit": "entries/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["text"], "rank": rank_k, "l2": "inputs (G: %.1f GB) larger than L2" % (8e-9 * w["k"] * n),
+                       "parallelism": "replicas x%d" % world if world > 1 else "single GPU"},
+            "wall_time_s": ms * 1e-3 / args.steps, "phase_ms_per_step": phase_ms,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="tstar", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        reference_arm(args, w)
+    else:
+        gpu_arm(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -57,22 +57,27 @@ struct KernParams {
     int nu2;       // Matern 2*nu
     int stab;      // extra_stability
     double bw;     // bandwidth
+    double gscale; // Gaussian: -0.5 / bw^2
 };
 
 __host__ inline KernParams make_kern_params(const rpc_kernel_spec *s) {
     KernParams p;
     p.kind = s->kind; p.nu2 = s->nu2; p.stab = s->extra_stability; p.bw = s->bandwidth;
+    p.gscale = -0.5 / (s->bandwidth * s->bandwidth);
     return p;
 }
 
 // Value of the kernel from the clamped squared distance d2 (expanded or direct form).
-// Mirrors the reference op order: dsts = sqrt(d2); Gaussian exp(-0.5*dsts**2/bw**2) (kernels.py:39);
-// Matern r = dsts/bw, or r = dsts when extra_stability (the reference omits /bw there, kernels.py:74-75).
+// Reference: dsts = sqrt(d2); Gaussian exp(-0.5*dsts**2/bw**2) (kernels.py:39); Matern r = dsts/bw, or
+// r = dsts when extra_stability (the reference omits /bw there, kernels.py:74-75).
+// The Gaussian skips the sqrt/re-square round trip and the division (exp(d2 * (-0.5/bw^2))): the argument
+// differs from the reference's by <= 3 ulp, i.e. the value by <= 3e-16*|arg| relative -- five orders below
+// the 1e-10 parity tolerance -- and it removes ~40 FP64-pipe instructions per entry from the epilogue.
 __device__ __forceinline__ double kern_from_d2(const KernParams &kp, double d2) {
-    double dst = sqrt(d2);
     if (kp.kind == RPC_KERN_GAUSSIAN) {
-        return exp(-0.5 * (dst * dst) / (kp.bw * kp.bw));
+        return exp(d2 * kp.gscale);
     }
+    double dst = sqrt(d2);
     double r = kp.stab ? dst : dst / kp.bw;
     if (kp.nu2 == 1) return exp(-r);
     if (kp.nu2 == 3) {

@@ -127,64 +127,67 @@ __global__ void __launch_bounds__(SC_WARPS * 32) sc_classify(const double *__res
     }
 }
 
-// 4. the walk: exact running sum before every chunk.  One warp: lanes stage data, lane 0 adds.
+// 4. the walk: exact running sum before every chunk.  One warp; 32 chunk descriptors per step.
+// A run of regular chunks of ONE binade is folded with a warp prefix sum: all its D are multiples of
+// the same ulp q and their total is below 2^52 q, so the shuffled additions are exact in any order and
+// carry + prefix reproduces the sequential running sum bit for bit.  Chunks that need a replay
+// (cls == INT_MIN) are added element by element by lane 0.
 template <bool DIV>
 __global__ void __launch_bounds__(32) sc_walk(const double *__restrict__ d, int64_t n, const double *Sptr,
                                               const double *__restrict__ D, const int32_t *__restrict__ cls, int nch,
                                               double *__restrict__ cstart, int32_t *__restrict__ bad) {
     __shared__ double xs[SC_CH];
-    __shared__ double ds[32 * 8];
-    __shared__ int32_t es[32 * 8];
     const int lane = threadIdx.x;
+    const unsigned full = 0xffffffffu;
     const double S = DIV ? *Sptr : 1.0;
-    double carry = 0.0;                              // meaningful in lane 0 only
+    double carry = 0.0;                              // identical in all lanes
     int violated = 0;
-    for (int k0 = 0; k0 < nch; k0 += 256) {
-        // stage 256 chunk descriptors
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            int k = k0 + t * 32 + lane;
-            ds[t * 32 + lane] = k < nch ? D[k] : 0.0;
-            es[t * 32 + lane] = k < nch ? cls[k] : 0;
-        }
-        __syncwarp();
-        const int kend = min(256, nch - k0);
-        int kk = 0;
-        while (kk < kend) {
-            // lane 0 runs through regular chunks until it meets one that needs a replay
-            int stop = kend;
-            if (lane == 0) {
-                int q = kk;
-                for (; q < kend; ++q) {
-                    int e = es[q];
-                    if (e == INT_MIN) break;
-                    cstart[k0 + q] = carry;
-                    if (ilogb(carry) != e) violated = 1;   // the a-priori bound guarantees this never fires
-                    carry += ds[q];                        // exact
-                }
-                stop = q;
-            }
-            stop = __shfl_sync(0xffffffffu, stop, 0);
-            kk = stop;
-            if (kk < kend) {
-                // replay chunk k0+kk with real sequential fp64 adds
-                const int64_t base = (int64_t)(k0 + kk) * SC_CH;
+    for (int k0 = 0; k0 < nch; k0 += 32) {
+        const int k = k0 + lane;
+        const bool live = k < nch;
+        const int e = live ? cls[k] : INT_MIN + 1;   // INT_MIN + 1: past the end, never matches a binade
+        const double Dk = live ? D[k] : 0.0;
+        int pos = 0;
+        const int kend = min(32, nch - k0);
+        while (pos < kend) {
+            const int e0 = __shfl_sync(full, e, pos);
+            if (e0 == INT_MIN) {
+                // replay chunk k0+pos with real sequential fp64 adds
+                const int64_t base = (int64_t)(k0 + pos) * SC_CH;
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
                     int64_t j = base + t * 32 + lane;
                     xs[t * 32 + lane] = j < n ? elem<DIV>(d, j, S) : 0.0;
                 }
                 __syncwarp();
-                if (lane == 0) {
-                    cstart[k0 + kk] = carry;
+                if (lane == 0) cstart[k0 + pos] = carry;
+                double cc = carry;
 #pragma unroll 16
-                    for (int j = 0; j < SC_CH; ++j) carry += xs[j];
-                }
+                for (int j = 0; j < SC_CH; ++j) cc += xs[j];   // every lane computes the same chain
+                carry = cc;
                 __syncwarp();
-                ++kk;
+                ++pos;
+                continue;
             }
+            // maximal run [pos, end) of chunks with binade e0
+            const unsigned same = __ballot_sync(full, e == e0);
+            const unsigned from = same >> pos;                        // bit i <-> lane pos+i
+            const int len = (~from == 0u) ? 32 - pos : __ffs(~from) - 1;
+            const int end = pos + len;
+            const bool in_run = lane >= pos && lane < end;
+            double v = in_run ? Dk : 0.0;
+            // inclusive warp prefix sum (exact: see above)
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                double t = __shfl_up_sync(full, v, o);
+                if (lane >= o) v += t;
+            }
+            const double total = __shfl_sync(full, v, 31);
+            if (in_run) cstart[k] = carry + (v - Dk);                  // exclusive prefix, exact
+            if (ilogb(carry) != e0 || !(carry + total <= pow2d(e0 + 1))) violated = 1;
+            carry += total;                                            // exact
+            pos = end;
         }
-        __syncwarp();
     }
     if (lane == 0) {
         cstart[nch] = carry;

@@ -355,30 +355,67 @@ extern "C" int rpc_rejection_cholesky(rpc_ctx *ctx, void *stream, double *H, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// panel assembly: Minv = L^{-1} (one CTA, thread per column), then At = [-(P_acc Minv^T); Minv^T; 0]
+// panel assembly.  mode 0: At = [-P_acc; I; 0] L^{-T}, one triangular solve per panel row (warp per
+// TS_RW rows, the running solution in shared memory, L streamed from L2 with coalesced row reads).
+// mode 1 (eigh fallback): At = [-P_acc; I; 0] T^T with a dense T.
 // ------------------------------------------------------------------------------------------------
-// Mi[i*lds + j] = Minv[i][j];  MiT[i*lds + j] = Minv[j][i]
-__global__ void __launch_bounds__(1024) tri_inverse_kernel(const double *__restrict__ L, int64_t ldl, int s,
-                                                           double *__restrict__ Mi, double *__restrict__ MiT, int lds) {
-    // thread j solves L x = e_j by forward substitution; x_i lives in column j of Mi
-    for (int q = threadIdx.x; q < s * lds; q += blockDim.x) { Mi[q] = 0.0; MiT[q] = 0.0; }
-    __syncthreads();
-    const int j = threadIdx.x;
-    if (j >= s) return;
-    for (int i = j; i < s; ++i) {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int l = j;
-        for (; l + 4 <= i; l += 4) {
-            a0 = fma(L[(int64_t)i * ldl + l], Mi[(size_t)l * lds + j], a0);
-            a1 = fma(L[(int64_t)i * ldl + l + 1], Mi[(size_t)(l + 1) * lds + j], a1);
-            a2 = fma(L[(int64_t)i * ldl + l + 2], Mi[(size_t)(l + 2) * lds + j], a2);
-            a3 = fma(L[(int64_t)i * ldl + l + 3], Mi[(size_t)(l + 3) * lds + j], a3);
+constexpr int TS_RW = 4;        // panel rows solved together by one warp (re-uses every L load 4 times)
+constexpr int TS_WARPS = 4;
+
+__global__ void __launch_bounds__(TS_WARPS * 32) panel_trsm_kernel(const double *__restrict__ P, int64_t ldP, int c,
+                                                                   const int32_t *__restrict__ acc, int s,
+                                                                   const double *__restrict__ L, int64_t ldl,
+                                                                   double *__restrict__ At, int64_t ldat, int k_pad) {
+    extern __shared__ double zs[];                  // [TS_WARPS][TS_RW][s]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = (blockIdx.x * TS_WARPS + warp) * TS_RW;
+    if (r0 >= k_pad) return;
+    double *z = zs + (size_t)warp * TS_RW * s;
+    if (r0 < c + s) {
+        // rows r < c start from -P[r, acc]; row c+i is e_i, whose solution is zero before column i
+        int jstart = r0 >= c ? r0 - c : 0;
+        for (int j = lane; j < s; j += 32) {
+#pragma unroll
+            for (int w = 0; w < TS_RW; ++w) {
+                int r = r0 + w;
+                double v = 0.0;
+                if (r < c) v = -P[(int64_t)r * ldP + (acc ? acc[j] : j)];
+                else if (r - c == j) v = 1.0;
+                z[w * s + j] = v;                  // holds the right-hand side until column j is solved
+            }
         }
-        for (; l < i; ++l) a0 = fma(L[(int64_t)i * ldl + l], Mi[(size_t)l * lds + j], a0);
-        double rhs = (i == j) ? 1.0 : 0.0;
-        double x = (rhs - ((a0 + a1) + (a2 + a3))) / L[(int64_t)i * ldl + i];
-        Mi[(size_t)i * lds + j] = x;
-        MiT[(size_t)j * lds + i] = x;
+        __syncwarp();
+        for (int j = jstart; j < s; ++j) {
+            double part[TS_RW];
+#pragma unroll
+            for (int w = 0; w < TS_RW; ++w) part[w] = 0.0;
+            const double *Lj = L + (int64_t)j * ldl;
+            for (int l = jstart + lane; l < j; l += 32) {
+                const double lv = Lj[l];
+#pragma unroll
+                for (int w = 0; w < TS_RW; ++w) part[w] = fma(lv, z[w * s + l], part[w]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int w = 0; w < TS_RW; ++w) part[w] += __shfl_xor_sync(0xffffffffu, part[w], o);
+            const double ljj = Lj[j];
+            if (lane < TS_RW) {
+                // lane w finishes row w (all lanes hold the reduced sums)
+                double sum = part[0];
+#pragma unroll
+                for (int w = 1; w < TS_RW; ++w) if (lane == w) sum = part[w];
+                z[lane * s + j] = (z[lane * s + j] - sum) / ljj;
+            }
+            __syncwarp();
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < TS_RW; ++w) {
+        int r = r0 + w;
+        if (r >= k_pad) break;
+        const bool live = r < c + s;
+        for (int j = lane; j < ldat; j += 32) At[(int64_t)r * ldat + j] = (live && j < s) ? z[w * s + j] : 0.0;
     }
 }
 
@@ -431,24 +468,32 @@ __global__ void __launch_bounds__(256) panel_kernel(const double *__restrict__ P
 extern "C" int rpc_build_panel(rpc_ctx *ctx, void *stream, const double *P, int64_t ldP, int c, const int32_t *acc, int s,
                                const double *L, int64_t ldl, int mode, double *At, int64_t ldat, int k_pad) {
     RPC_CHECK_ARG(ctx && L && At, "null pointer");
-    RPC_CHECK_ARG(s >= 1 && s <= 1024 && c >= 0 && (c == 0 || P), "bad sizes");
+    RPC_CHECK_ARG(s >= 1 && s <= 768 && c >= 0 && (c == 0 || P), "bad sizes");
     RPC_CHECK_ARG(k_pad >= c + s && ldat >= s, "k_pad >= c+s and ldat >= s required");
     cudaStream_t st = (cudaStream_t)stream;
-    const int lds = (s + 7) & ~7;
-    int rc = rpc_ws_reserve(ctx, (size_t)2 * s * lds * sizeof(double));
-    if (rc) return rc;
-    double *Mi = ctx->ws, *MiT = ctx->ws + (size_t)s * lds;
     if (mode == 0) {
-        tri_inverse_kernel<<<1, 1024, 0, st>>>(L, ldl, s, Mi, MiT, lds);
+        size_t shm = (size_t)TS_WARPS * TS_RW * s * sizeof(double);
+        static bool configured = false;
+        if (!configured) {
+            RPC_CUDA(cudaFuncSetAttribute(panel_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+            configured = true;
+        }
+        int rows_per_cta = TS_WARPS * TS_RW;
+        int blocks = (k_pad + rows_per_cta - 1) / rows_per_cta;
+        panel_trsm_kernel<<<blocks, TS_WARPS * 32, shm, st>>>(P, ldP, c, acc, s, L, ldl, At, ldat, k_pad);
         RPC_LAUNCHED(ctx);
-    } else {
-        // Minv given in L (dense s x s): MiT[i][j] = L[j][i]
-        rc = rpc_transpose_pad(ctx, st, L, ldl, s, s, MiT, lds, s);
-        if (rc) return rc;
+        return 0;
     }
+    // Minv given in L (dense s x s): MiT[i][j] = L[j][i]
+    const int lds = (s + 7) & ~7;
+    int rc = rpc_ws_reserve(ctx, (size_t)s * lds * sizeof(double));
+    if (rc) return rc;
+    double *MiT = ctx->ws;
+    rc = rpc_transpose_pad(ctx, st, L, ldl, s, s, MiT, lds, s);
+    if (rc) return rc;
     size_t shm = (size_t)PB * s * sizeof(double);
     int blocks = (k_pad + PB - 1) / PB;
-    panel_kernel<<<blocks, 256, shm, st>>>(P, ldP, c, acc, s, MiT, lds, mode == 0 ? 1 : 0, At, ldat, k_pad);
+    panel_kernel<<<blocks, 256, shm, st>>>(P, ldP, c, acc, s, MiT, lds, 0, At, ldat, k_pad);
     RPC_LAUNCHED(ctx);
     return 0;
 }

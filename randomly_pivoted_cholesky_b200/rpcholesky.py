@@ -28,6 +28,28 @@ from .matrix import AbstractPSDMatrix, PSDMatrix, _ptr, _round_up, _stream
 EPS = float(np.finfo(float).eps)
 AT_LD_ALIGN = 256          # panel leading dimension granularity (widest row tile of the DMMA kernel)
 
+# bench.py sets this to a list to collect (start_event, end_event, flops, bytes, phase) per timed launch
+KERNEL_TIMERS = None
+
+
+class _timed:
+    """CUDA-event bracket around one launch on the current stream (only active under bench.py)."""
+
+    def __init__(self, phase, flops, nbytes):
+        self.on = KERNEL_TIMERS is not None
+        self.meta = (phase, flops, nbytes)
+
+    def __enter__(self):
+        if self.on:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.e1.record()
+            KERNEL_TIMERS.append((self.e0, self.e1) + self.meta)
+
 
 def _as_operator(A):
     if isinstance(A, AbstractPSDMatrix):
@@ -118,13 +140,20 @@ class _State:
         """rows[c:c+s] = A[S,:]; G[c:c+s] = L^{-1}(rows - P^T G[:c]); diag update (rpcholesky.py:101-107,128-129 / 205-209)."""
         k_pad = _round_up(c + s, KT)
         Lm = self.L if Lmat is None else Lmat
-        check(self.lib.rpc_build_panel(self.ctx.handle, _stream(), _ptr(self.P), self.m_max, c, _ptr(acc_dev), s, _ptr(Lm),
-                                       Lm.stride(0), panel_mode, _ptr(self.At), self.ldat, k_pad), "rpc_build_panel")
+        with _timed("panel", 1.0 * s * s * c + s ** 3 / 3.0, 8.0 * c * s):
+            check(self.lib.rpc_build_panel(self.ctx.handle, _stream(), _ptr(self.P), self.m_max, c, _ptr(acc_dev), s,
+                                           _ptr(Lm), Lm.stride(0), panel_mode, _ptr(self.At), self.ldat, k_pad),
+                  "rpc_build_panel")
         rows_ptr = C.c_void_p(self.rows.data_ptr() + 8 * c * self.n_pad)
-        self.A._dev_rows_into(sel_idx_dev, s, sel_piv, rows_ptr, self.n_pad)
+        n, d = self.n, getattr(self.A, "d", 0)
+        with _timed("eval", 2.0 * s * n * d, 8.0 * n * (s + d)):
+            self.A._dev_rows_into(sel_idx_dev, s, sel_piv, rows_ptr, self.n_pad)
         self.A._count(s * self.n)
-        check(self.lib.rpc_schur_update(self.ctx.handle, _stream(), _ptr(self.G), self.n_pad, c, s, _ptr(self.At), self.ldat,
-                                        k_pad, rows_ptr, self.n_pad, _ptr(self.diag), self.n_pad), "rpc_schur_update")
+        # algorithmic work of the fused update (DESIGN.md): 2 s (c+s) N flops; reads G[:c] and rows_new, writes G_new
+        with _timed("schur", 2.0 * s * (c + s) * n, 8.0 * n * (c + 2 * s + 2)):
+            check(self.lib.rpc_schur_update(self.ctx.handle, _stream(), _ptr(self.G), self.n_pad, c, s, _ptr(self.At),
+                                            self.ldat, k_pad, rows_ptr, self.n_pad, _ptr(self.diag), self.n_pad),
+                  "rpc_schur_update")
 
     def result(self, count, arr_idx):
         n = self.n
@@ -295,10 +324,13 @@ def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
         legacy_state = np.random.get_state()
         ur = np.random.random_sample(b)                        # the b np.random.rand() calls of :151
         st.upload_uniforms(up, ur)
-        st.sample(b)
-        st.gather(st.idx_dev, b, st.piv, counter)
-        st.residual_block(st.idx_dev, b, st.piv, counter)      # :189
-        st.cholesky(b, 0, k - counter, 0.0, b)                 # :190 + truncation :193-196
+        with _timed("sample", 0.0, 16.0 * st.n):
+            st.sample(b)
+        with _timed("gram", 2.0 * b * b * counter, 8.0 * counter * b):
+            st.gather(st.idx_dev, b, st.piv, counter)
+            st.residual_block(st.idx_dev, b, st.piv, counter)      # :189
+        with _timed("reject", b ** 3 / 3.0, 8.0 * b * b):
+            st.cholesky(b, 0, k - counter, 0.0, b)                 # :190 + truncation :193-196
         host = torch.cat([st.stats, st.info.to(torch.float64), st.acc[:b].to(torch.float64),
                           st.idx_dev[:b].to(torch.float64)]).cpu().numpy()          # the round's only sync
         stats_host, info = host[:4], host[4:8].astype(np.int64)
