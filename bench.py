@@ -274,6 +274,10 @@ def gpu_arm(args, w):
                     "algorithmic_flops_per_launch": flops / cnt, "algorithmic_bytes_per_launch": nbytes / cnt,
                     "hbm_gbs_achieved": nbytes / sec / 1e9, "hbm_peak_gbs": hbm}
     phase_ms = {k: 1e3 * v[0] / args.steps for k, v in phases.items()}
+    # per-launch detail of the dominant kernel over the LAST timed step: (ms, TFLOP/s)
+    per_step = max(1, len([1 for t in timers if t[2] == "schur"]) // args.steps)
+    detail = [[round(t[0].elapsed_time(t[1]), 3), round(t[3] / t[0].elapsed_time(t[1]) / 1e9, 2)]
+              for t in timers if t[2] == "schur"][-per_step:]
 
     # ---- e2e: host X -> H2D -> factorise -> D2H pivots + trace-norm error, through the public API ----
     sync_all()
@@ -314,7 +318,7 @@ def gpu_arm(args, w):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["text"], "rank": rank_k, "l2": "inputs (G: %.1f GB) larger than L2" % (8e-9 * w["k"] * n),
                        "parallelism": "replicas x%d" % world if world > 1 else "single GPU"},
-            "wall_time_s": ms * 1e-3 / args.steps, "phase_ms_per_step": phase_ms,
+            "wall_time_s": ms * 1e-3 / args.steps, "phase_ms_per_step": phase_ms, "dominant_kernel_launches_ms_tflops": detail,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
         }
         print(json.dumps(out), flush=True)

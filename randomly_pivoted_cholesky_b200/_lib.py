@@ -92,7 +92,11 @@ _SIGNATURES = {
     "rpc_gram_residual": (_INT, [_P, _P, _P, _INT, _INT, _I64, _P, _I64]),
     "rpc_rejection_cholesky": (_INT, [_P, _P, _P, _INT, _I64, _P, _INT, _INT, _DBL, _P, _I64, _P, _P]),
     "rpc_build_panel": (_INT, [_P, _P, _P, _I64, _INT, _P, _INT, _P, _I64, _INT, _P, _I64, _INT]),
+    "rpc_panel_ld": (_INT, [_INT]),
     "rpc_schur_update": (_INT, [_P, _P, _P, _I64, _INT, _INT, _P, _I64, _INT, _P, _I64, _P, _I64]),
+    "rpc_fused_update_supported": (_INT, [C.POINTER(KernelSpec), _INT, _I64]),
+    "rpc_fused_update": (_INT, [_P, _P, C.POINTER(KernelSpec), _P, _P, _I64, _INT, _I64, _P, _P, _I64, _P, _I64, _INT, _INT, _P,
+                                _I64, _INT, _P, _I64, _P]),
     "rpc_simple_step": (_INT, [_P, _P, C.POINTER(KernelSpec), _P, _P, _INT, _I64, _P, _I64, _I64, _P, _INT, _P, _I64, _P,
                                _I64, _P, _I64]),
 }

@@ -6,46 +6,94 @@ using namespace dg;
 // ------------------------------------------------------------------------------------------------
 // DMMA GEMM dispatch: pick the narrowest M tile that holds the rows of the update
 // ------------------------------------------------------------------------------------------------
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+
 template <class C, int MODE>
 static int launch_gemm(rpc_ctx *ctx, cudaStream_t st, const Params &p, int64_t n_pad) {
     static bool configured = false;
+    size_t shm = (MODE == MODE_FUSED || MODE == MODE_EVALX) ? C::fused_smem_bytes((int)p.ldx) : C::SMEM_BYTES;
+    if (shm > SMEM_LIMIT) {
+        rpc_set_error("launch_gemm: %zu bytes of shared memory needed, %zu available", shm, SMEM_LIMIT);
+        return -4;
+    }
     if (!configured) {
         RPC_CUDA(cudaFuncSetAttribute(gemm_kernel<C, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)C::SMEM_BYTES));
+                                      (MODE == MODE_FUSED || MODE == MODE_EVALX) ? (int)SMEM_LIMIT : (int)C::SMEM_BYTES));
         configured = true;
     }
-    dim3 grid((unsigned)(n_pad / C::N_TILE));
-    gemm_kernel<C, MODE><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(p);
+    // persistent: one CTA per SM walks the column tiles; the producer warp prefetches across tile boundaries
+    Params q = p;
+    q.ntiles = (int)(n_pad / C::N_TILE);
+    unsigned grid = (unsigned)(q.ntiles < ctx->sm_count ? q.ntiles : ctx->sm_count);
+    gemm_kernel<C, MODE><<<grid, C::THREADS, shm, st>>>(q);
     RPC_LAUNCHED(ctx);
     return 0;
 }
 
+// row tiles (M_TILE = 8*WM*MI).  Every tile has 8 consumer warps (two per SM sub-partition: 5- and 3-row-warp
+// shapes were measured 15-20% slower because the DMMA work no longer divides evenly over the 4 SMSPs).
 typedef Cfg<4, 2, 8, 4> C256;   // 256 x 64
+typedef Cfg<4, 2, 7, 4> C224;   // 224 x 64
 typedef Cfg<4, 2, 6, 4> C192;   // 192 x 64
+typedef Cfg<4, 2, 5, 4> C160;   // 160 x 64
 typedef Cfg<2, 4, 8, 4> C128;   // 128 x 128
+typedef Cfg<2, 4, 6, 4> C96;    //  96 x 128
 typedef Cfg<2, 4, 4, 4> C64;    //  64 x 128
 typedef Cfg<1, 8, 4, 2> C32;    //  32 x 128
 typedef Cfg<1, 8, 2, 2> C16;    //  16 x 128
 
 int rpc_gemm_max_m(void) { return C256::M_TILE; }
 
-template <int MODE>
-static int dispatch_gemm(rpc_ctx *ctx, cudaStream_t st, const Params &p, int m, int64_t n_pad) {
-    if (m <= 16) return launch_gemm<C16, MODE>(ctx, st, p, n_pad);
-    if (m <= 32) return launch_gemm<C32, MODE>(ctx, st, p, n_pad);
-    if (m <= 64) return launch_gemm<C64, MODE>(ctx, st, p, n_pad);
-    if (m <= 128) return launch_gemm<C128, MODE>(ctx, st, p, n_pad);
-    if (m <= 192) return launch_gemm<C192, MODE>(ctx, st, p, n_pad);
-    return launch_gemm<C256, MODE>(ctx, st, p, n_pad);
+static int tile_rows_for(int m) {
+    const int tiles[] = {16, 32, 64, 96, 128, 160, 192, 224, 256};
+    for (int t : tiles) if (m <= t) return t;
+    return 256;
 }
 
-static int tile_rows_for(int m) {
-    if (m <= 16) return 16;
-    if (m <= 32) return 32;
-    if (m <= 64) return 64;
-    if (m <= 128) return 128;
-    if (m <= 192) return 192;
-    return 256;
+template <int MODE>
+static int dispatch_gemm(rpc_ctx *ctx, cudaStream_t st, const Params &p, int m, int64_t n_pad) {
+    switch (tile_rows_for(m)) {
+        case 16: return launch_gemm<C16, MODE>(ctx, st, p, n_pad);
+        case 32: return launch_gemm<C32, MODE>(ctx, st, p, n_pad);
+        case 64: return launch_gemm<C64, MODE>(ctx, st, p, n_pad);
+        case 96: return launch_gemm<C96, MODE>(ctx, st, p, n_pad);
+        case 128: return launch_gemm<C128, MODE>(ctx, st, p, n_pad);
+        case 160: return launch_gemm<C160, MODE>(ctx, st, p, n_pad);
+        case 192: return launch_gemm<C192, MODE>(ctx, st, p, n_pad);
+        case 224: return launch_gemm<C224, MODE>(ctx, st, p, n_pad);
+        default: return launch_gemm<C256, MODE>(ctx, st, p, n_pad);
+    }
+}
+
+// leading dimension of a panel whose k-stages can be fetched with ONE bulk copy by the tile chosen for m rows
+static int panel_ld_for(int m) {
+    switch (tile_rows_for(m)) {
+        case 16: return C16::LDA;
+        case 32: return C32::LDA;
+        case 64: return C64::LDA;
+        case 96: return C96::LDA;
+        case 128: return C128::LDA;
+        case 160: return C160::LDA;
+        case 192: return C192::LDA;
+        case 224: return C224::LDA;
+        default: return C256::LDA;
+    }
+}
+extern "C" int rpc_panel_ld(int s) { return s <= 256 ? panel_ld_for(s) : (s + 255) / 256 * 256; }
+
+// shared-memory need of the fused kernel for a given row count / point stride (0 if no tile fits)
+static bool fused_fits(int m, int64_t ldx) {
+    int t = tile_rows_for(m);
+    size_t need;
+    if (t <= 32) need = (t == 16 ? C16::fused_smem_bytes((int)ldx) : C32::fused_smem_bytes((int)ldx));
+    else if (t == 64) need = C64::fused_smem_bytes((int)ldx);
+    else if (t == 96) need = C96::fused_smem_bytes((int)ldx);
+    else if (t == 128) need = C128::fused_smem_bytes((int)ldx);
+    else if (t == 160) need = C160::fused_smem_bytes((int)ldx);
+    else if (t == 192) need = C192::fused_smem_bytes((int)ldx);
+    else if (t == 224) need = C224::fused_smem_bytes((int)ldx);
+    else need = C256::fused_smem_bytes((int)ldx);
+    return need <= SMEM_LIMIT;
 }
 
 extern "C" int rpc_schur_update(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At,
@@ -68,6 +116,38 @@ extern "C" int rpc_schur_update(rpc_ctx *ctx, void *stream, double *G, int64_t l
         if (rc) return rc;
     }
     return 0;
+}
+
+extern "C" int rpc_fused_update_supported(const rpc_kernel_spec *spec, int s, int64_t ldx) {
+    if (!spec || spec->kind == RPC_KERN_LAPLACE || spec->extra_stability) return 0;
+    if (s < 1 || s > 256) return 0;
+    return fused_fits(s, ldx) ? 1 : 0;
+}
+
+extern "C" int rpc_fused_update(rpc_ctx *ctx, void *stream, const rpc_kernel_spec *spec, const double *X, const double *xnorm,
+                                int64_t n_pad, int d, int64_t ldx, const double *Xsel, const double *pnorm, int64_t ldp,
+                                double *G, int64_t ldg, int c, int s, const double *At, int64_t ldat, int k_pad,
+                                double *rows_new, int64_t ldr, double *diag) {
+    RPC_CHECK_ARG(ctx && spec && X && xnorm && Xsel && pnorm && G && At && rows_new && diag, "null pointer");
+    RPC_CHECK_ARG(rpc_fused_update_supported(spec, s, ldx), "kernel/shape not supported by the fused update");
+    RPC_CHECK_ARG(c >= 0 && n_pad > 0 && n_pad % RPC_COL_ALIGN == 0, "bad sizes");
+    RPC_CHECK_ARG(k_pad % RPC_KT == 0 && k_pad >= c + s, "k_pad must be a multiple of RPC_KT and >= c+s");
+    RPC_CHECK_ARG(d >= 1 && d % RPC_FEAT_ALIGN == 0 && ldx % RPC_FEAT_ALIGN == 0 && ldx >= d, "d, ldx must be multiples of 4");
+    RPC_CHECK_ARG(ldg % 2 == 0 && ldr % 2 == 0 && ldat % 2 == 0 && ldat >= tile_rows_for(s), "bad leading dimensions");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ke_pad = (d + RPC_KT - 1) / RPC_KT * RPC_KT;
+    const int ld_e = panel_ld_for(s);
+    int rc = rpc_ws_reserve(ctx, (size_t)ke_pad * ld_e * sizeof(double));
+    if (rc) return rc;
+    rc = rpc_transpose_pad(ctx, st, Xsel, ldp, s, d, ctx->ws, ld_e, ke_pad);
+    if (rc) return rc;
+    Params p{};
+    p.At = At; p.ldat = ldat; p.k_pad = k_pad; p.m_valid = s;
+    p.G = G; p.ldg = ldg; p.c = c; p.R = rows_new; p.ldr = ldr; p.K = c + s;
+    p.Cout = G + (int64_t)c * ldg; p.ldc = ldg; p.diag = diag;
+    p.X = X; p.ldx = ldx; p.d = d; p.xnorm = xnorm; p.pnorm = pnorm; p.kp = make_kern_params(spec);
+    p.At_e = ctx->ws; p.ldat_e = ld_e; p.ke_pad = ke_pad;
+    return dispatch_gemm<MODE_FUSED>(ctx, st, p, s, n_pad);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -163,19 +243,29 @@ extern "C" int rpc_kernel_rows(rpc_ctx *ctx, void *stream, const rpc_kernel_spec
         return 0;
     }
     RPC_CHECK_ARG(xnorm && pnorm, "row norms required for the expanded Euclidean form");
-    // A operand = Xpiv^T (d x s) zero padded to (k_pad x 256) in the context workspace
+    // A operand = Xpiv^T (d x s) zero padded to (k_pad x ld) in the context workspace
     const int k_pad = (d + RPC_KT - 1) / RPC_KT * RPC_KT;
     for (int m0 = 0; m0 < s; m0 += 256) {
         int m = s - m0 < 256 ? s - m0 : 256;
-        int rc = rpc_ws_reserve(ctx, (size_t)k_pad * 256 * sizeof(double));
+        const int ld = panel_ld_for(m);
+        int rc = rpc_ws_reserve(ctx, (size_t)k_pad * ld * sizeof(double));
         if (rc) return rc;
-        rc = rpc_transpose_pad(ctx, st, Xpiv + (int64_t)m0 * ldp, ldp, m, d, ctx->ws, 256, k_pad);
+        rc = rpc_transpose_pad(ctx, st, Xpiv + (int64_t)m0 * ldp, ldp, m, d, ctx->ws, ld, k_pad);
         if (rc) return rc;
         Params p{};
-        p.At = ctx->ws; p.ldat = 256; p.k_pad = k_pad; p.m_valid = m;
+        p.m_valid = m;
         p.X = X; p.ldx = ldx; p.d = d; p.xnorm = xnorm; p.pnorm = pnorm + m0; p.kp = kp;
-        p.Cout = out + (int64_t)m0 * ldo; p.ldc = ldo;
-        rc = dispatch_gemm<MODE_EVAL>(ctx, st, p, m, n_pad);
+        if (fused_fits(m, ldx) && ldx % RPC_FEAT_ALIGN == 0) {
+            // X tile resident in shared memory (one bulk copy per tile), panel staged through the ring
+            p.At_e = ctx->ws; p.ldat_e = ld; p.ke_pad = k_pad;
+            p.At = ctx->ws; p.ldat = ld; p.k_pad = RPC_KT;
+            p.R = out + (int64_t)m0 * ldo; p.ldr = ldo;
+            rc = dispatch_gemm<MODE_EVALX>(ctx, st, p, m, n_pad);
+        } else {
+            p.At = ctx->ws; p.ldat = ld; p.k_pad = k_pad;
+            p.Cout = out + (int64_t)m0 * ldo; p.ldc = ldo;
+            rc = dispatch_gemm<MODE_EVAL>(ctx, st, p, m, n_pad);
+        }
         if (rc) return rc;
     }
     return 0;

@@ -5,12 +5,18 @@
 // One CTA owns ALL M rows of a column tile, so the big operand B (the factor G, or the data X) is read
 // from HBM exactly once per launch and the epilogue (residual-diagonal update / kernel function) is
 // fused.  The small operand At (the pivot panel, K x M, zero padded) is re-read by every CTA from L2.
-// Operands are staged in shared memory by a 4-stage cp.async pipeline; smem leading dimensions are
-// == 4 (mod 16) doubles so that the DMMA fragment loads (lane -> (k = lane&3, row = lane>>2)) hit 16
-// distinct 8-byte bank pairs per half warp.
+//
+// Pipeline (Blackwell/Hopper style, no CTA-wide barrier in the main loop):
+//   * one PRODUCER warp stages the operands with TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx):
+//     per k-stage of KT=16 rows, lane r issues one row of the pivot panel (M_TILE*8 bytes) and one row of
+//     B (N_TILE*8 bytes) into a 4-deep ring of shared-memory stages guarded by full/empty mbarriers;
+//   * WM x WN CONSUMER warps wait on the stage's full barrier, run MI x NI DMMA.8x8x4 per k4-step from
+//     double-buffered register fragments, and release the stage with one arrive per warp.
+// Shared-memory leading dimensions are == 4 (mod 16) doubles so that the DMMA fragment loads
+// (lane -> (k = lane&3, row = lane>>2)) hit 16 distinct 8-byte bank pairs per half warp.
 //
 // tcgen05 has no FP64 kind, so on Blackwell the FP64 tensor path is the warp-level mma.sync DMMA;
-// measured peak on B200: 36.9 TFLOP/s (profiles/fp64_peaks_r01.json), same pipe as DFMA.
+// measured peak on B200: 36.9 TFLOP/s (profiles/fp64_peaks_r01.json), the same pipe as DFMA.
 #pragma once
 #include "rpc_common.cuh"
 
@@ -20,23 +26,30 @@ constexpr int KT = RPC_KT;      // k-depth per stage
 constexpr int STAGES = 4;
 constexpr int LDBK = KT + 4;    // point-major B stage: [n][LDBK]
 
-enum { MODE_SCHUR = 0, MODE_EVAL = 1 };
+enum { MODE_SCHUR = 0, MODE_EVAL = 1, MODE_FUSED = 2, MODE_EVALX = 3 };   // EVALX: EVAL with the X tile resident (phase 1 of FUSED only)
 
 template <int WM_, int WN_, int MI_, int NI_>
 struct Cfg {
     static constexpr int WM = WM_, WN = WN_, MI = MI_, NI = NI_;
-    static constexpr int THREADS = WM * WN * 32;
+    static constexpr int CONSUMERS = WM * WN;                // consumer warps
+    static constexpr int THREADS = (CONSUMERS + 4) * 32;     // + one producer warpgroup (one warp of it works)
+    static_assert(CONSUMERS % 4 == 0, "consumer warps must form whole warpgroups (setmaxnreg, even SMSP load)");
     static constexpr int M_TILE = WM * MI * 8;
     static constexpr int N_TILE = WN * NI * 8;
-    static constexpr int LDA = M_TILE + 4;
+    static constexpr int LDA = (M_TILE % 16 == 0) ? M_TILE + 4 : M_TILE + 12;   // == 4 (mod 16)
     static constexpr int LDB = N_TILE + 4;
     static constexpr int A_STAGE = KT * LDA;                                  // doubles
     static constexpr int B_STAGE_ROW = KT * LDB;                              // k-major B stage
     static constexpr int B_STAGE_PT = N_TILE * LDBK;                          // point-major B stage
     static constexpr int B_STAGE = B_STAGE_ROW > B_STAGE_PT ? B_STAGE_ROW : B_STAGE_PT;
-    static constexpr size_t SMEM_BYTES = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double);
-    static_assert(M_TILE % 16 == 0 || M_TILE == 8, "M_TILE");
-    static_assert(N_TILE % 16 == 0, "N_TILE");
+    static constexpr int STAGE_DOUBLES = STAGES * (A_STAGE + B_STAGE);
+    static constexpr int NBAR = 2 * STAGES + 4;                               // full[], empty[], xfull, xempty, rows_ready, pad
+    static constexpr int RED_DOUBLES = WM * N_TILE;                           // column-sum scratch of the epilogue
+    static constexpr size_t SMEM_BYTES = (size_t)(STAGE_DOUBLES + NBAR + RED_DOUBLES) * sizeof(double);
+    // MODE_FUSED keeps the whole X tile resident: N_TILE x ldx doubles (+16 zero doubles of slack)
+    static constexpr size_t fused_smem_bytes(int ldx) { return SMEM_BYTES + ((size_t)N_TILE * ldx + 16) * sizeof(double); }
+    static_assert(M_TILE % 8 == 0 && N_TILE % 16 == 0, "tile shape");
+    static_assert(LDA % 16 == 4 && LDB % 16 == 4, "bank-conflict-free leading dimensions");
 };
 
 struct Params {
@@ -61,59 +74,175 @@ struct Params {
     const double *xnorm;   // per point
     const double *pnorm;   // per pivot (row of C)
     KernParams kp;
+    // MODE_FUSED: phase 1 evaluates rows_new = k(Xsel, X) (panel At_e = Xsel^T, ke_pad x ldat_e) into R,
+    // phase 2 is MODE_SCHUR reading those rows back through L2
+    const double *At_e;
+    int64_t ldat_e;
+    int ke_pad;
+    int ntiles;            // column tiles (n_pad / N_TILE); the kernel is persistent over them
 };
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c[0]), "+d"(c[1])
-                 : "d"(a), "d"(b));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(c[0]), "+d"(c[1])
+        : "d"(a), "d"(b));
 }
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+// ---- mbarrier / TMA bulk-copy primitives (PTX ISA 8.x, sm_90+) ----------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-// src_bytes = 0 -> 16 zero bytes are written
-__device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gmem_src, int src_bytes) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy (TMA engine, no tensor map), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+__device__ __forceinline__ void consumer_bar_sync(int nthreads) {
+    asm volatile("bar.sync 1, %0;\n" ::"r"(nthreads) : "memory");
+}
+
+// bytes of the panel part of a stage: one contiguous block (padding columns included) when the panel was
+// built with leading dimension LDA, else KT separate rows
+template <class C>
+__device__ __forceinline__ unsigned panel_bytes(int64_t ldat) {
+    return ldat == C::LDA ? KT * C::LDA * 8 : KT * C::M_TILE * 8;
+}
+template <class C>
+__device__ __forceinline__ void produce_panel(double *As, const double *At, int64_t ldat, int k0, uint64_t *full, int lane) {
+    if (ldat == C::LDA) {          // the TMA engine is rate limited per copy (~40 ns): one 33 KB copy, not 16 rows
+        if (lane == 0) bulk_g2s(As, At + (int64_t)k0 * ldat, KT * C::LDA * 8, full);
+    } else if (lane < KT) {
+        bulk_g2s(As + lane * C::LDA, At + (int64_t)(k0 + lane) * ldat, C::M_TILE * 8, full);
+    }
+}
 
 template <class C, int MODE>
-__device__ __forceinline__ void load_stage(const Params &p, double *As, double *Bs, int k0, int64_t col0, int tid) {
-    // A tile: KT rows x M_TILE columns of At
-    constexpr int ACH = C::M_TILE / 2;   // 16-byte chunks per row
-#pragma unroll 2
-    for (int q = tid; q < KT * ACH; q += C::THREADS) {
-        int r = q / ACH, c2 = q - r * ACH;
-        cp_async16(As + r * C::LDA + c2 * 2, p.At + (int64_t)(k0 + r) * p.ldat + c2 * 2);
-    }
+__device__ __forceinline__ unsigned stage_bytes(const Params &p, int k0) {
+    unsigned a = panel_bytes<C>(p.ldat);
+    if (MODE == MODE_SCHUR) return a + KT * C::N_TILE * 8;
+    int kb = p.d - k0;
+    kb = kb > KT ? KT : kb;
+    return a + (unsigned)C::N_TILE * kb * 8;
+}
+
+// the producer warp: the panel stage in one copy, lane r issues row r of the B tile
+template <class C, int MODE>
+__device__ __forceinline__ void produce_stage(const Params &p, double *As, double *Bs, uint64_t *full, int k0, int64_t col0,
+                                              int lane) {
+    if (lane == 0) mbar_expect_tx(full, stage_bytes<C, MODE>(p, k0));
+    __syncwarp();
+    produce_panel<C>(As, p.At, p.ldat, k0, full, lane);
     if (MODE == MODE_SCHUR) {
-        constexpr int BCH = C::N_TILE / 2;
-#pragma unroll 2
-        for (int q = tid; q < KT * BCH; q += C::THREADS) {
-            int r = q / BCH, c2 = q - r * BCH;
-            int kk = k0 + r;
+        if (lane >= 32 - KT) {
+            const int r = lane - (32 - KT);
+            const int kk = k0 + r;
             const double *src;
             if (kk < p.c) src = p.G + (int64_t)kk * p.ldg;
             else if (kk < p.K) src = p.R + (int64_t)(kk - p.c) * p.ldr;
             else src = p.R;                       // padded k: At is zero there, any finite row will do
-            cp_async16(Bs + r * C::LDB + c2 * 2, src + col0 + c2 * 2);
+            bulk_g2s(Bs + r * C::LDB, src + col0, C::N_TILE * 8, full);
         }
     } else {
-        constexpr int KCH = KT / 2;
-#pragma unroll 2
-        for (int q = tid; q < C::N_TILE * KCH; q += C::THREADS) {
-            int n = q / KCH, c2 = q - n * KCH;
-            int kk = k0 + c2 * 2;
-            int ok = kk < p.d;
-            const double *src = p.X + (col0 + n) * p.ldx + (ok ? kk : 0);
-            cp_async16_zfill(Bs + n * LDBK + c2 * 2, src, ok ? 16 : 0);
+        int kb = p.d - k0;
+        kb = kb > KT ? KT : kb;                   // features left (multiple of 4); the rest of the stage row keeps
+        for (int n = lane; n < C::N_TILE; n += 32)  // stale-but-finite data that meets zero rows of At
+            bulk_g2s(Bs + n * LDBK, p.X + (col0 + n) * p.ldx + k0, (unsigned)kb * 8, full);
+    }
+}
+
+// one k-stage of DMMAs with double-buffered fragments; `ksteps` (1..4) k4-steps hold non-zero panel rows.
+// BKIND 0: B stage is k-major [KT][LDB]; BKIND 1: point-major [N_TILE][LDBK]; BKIND 2: resident X tile [N_TILE][ldx]
+template <class C, int BKIND>
+__device__ __forceinline__ void consume_stage(double (&acc)[C::MI][C::NI][2], const double *As, const double *Bs, int ldx,
+                                              int lk, int ksteps) {
+    double a[2][C::MI], b[2][C::NI];
+    auto ldb = [&](int j, int kk) -> double {
+        if (BKIND == 0) return Bs[kk * C::LDB + j * 8];
+        if (BKIND == 1) return Bs[j * 8 * LDBK + kk];
+        return Bs[j * 8 * ldx + kk];
+    };
+#pragma unroll
+    for (int i = 0; i < C::MI; ++i) a[0][i] = As[lk * C::LDA + i * 8];
+#pragma unroll
+    for (int j = 0; j < C::NI; ++j) b[0][j] = ldb(j, lk);
+#pragma unroll
+    for (int ks = 0; ks < KT / 4; ++ks) {
+        const int cur = ks & 1, nxt = cur ^ 1;
+        if (ks + 1 < KT / 4 && ks + 1 < ksteps) {
+            const int kk = (ks + 1) * 4 + lk;
+#pragma unroll
+            for (int i = 0; i < C::MI; ++i) a[nxt][i] = As[kk * C::LDA + i * 8];
+#pragma unroll
+            for (int j = 0; j < C::NI; ++j) b[nxt][j] = ldb(j, kk);
+        }
+        if (ks < ksteps) {
+#pragma unroll
+            for (int i = 0; i < C::MI; ++i)
+#pragma unroll
+                for (int j = 0; j < C::NI; ++j) dmma884(acc[i][j], a[cur][i], b[cur][j]);
         }
     }
+}
+
+// kernel values from the x.y accumulators -> Cout (MODE_EVAL and phase 1 of MODE_FUSED)
+template <class C>
+__device__ __forceinline__ void eval_epilogue(const Params &p, double (&acc)[C::MI][C::NI][2], double *out, int64_t ldo,
+                                              int64_t col0, int m0, int n0, int lr, int lk) {
+    double xn[C::NI][2];
+#pragma unroll
+    for (int j = 0; j < C::NI; ++j) {
+        xn[j][0] = p.xnorm[col0 + n0 + j * 8 + 2 * lk];
+        xn[j][1] = p.xnorm[col0 + n0 + j * 8 + 2 * lk + 1];
+    }
+#pragma unroll
+    for (int i = 0; i < C::MI; ++i) {
+        const int row = m0 + i * 8 + lr;
+        if (row < p.m_valid) {
+            const double pn = p.pnorm[row];
+            double *dst = out + (int64_t)row * ldo + col0 + n0 + 2 * lk;
+#pragma unroll
+            for (int j = 0; j < C::NI; ++j) {
+                // sklearn: D2 = ((-2 * X.Y^T) + XX) + YY, clamped at 0
+                double d0 = (-2.0 * acc[i][j][0] + pn) + xn[j][0];
+                double d1 = (-2.0 * acc[i][j][1] + pn) + xn[j][1];
+                d0 = d0 > 0.0 ? d0 : 0.0;
+                d1 = d1 > 0.0 ? d1 : 0.0;
+                *reinterpret_cast<double2 *>(dst + j * 8) = kern_from_d2_pair(p.kp, d0, d1);
+            }
+        }
+    }
+}
+
+// k4-steps of stage kt that hold real (non-padded) panel rows
+__device__ __forceinline__ int live_ksteps(int kt, int k_real) {
+    int left = k_real - kt * KT;
+    return left >= KT ? KT / 4 : (left + 3) / 4;
 }
 
 template <class C, int MODE>
@@ -121,133 +250,186 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
     extern __shared__ __align__(16) double smem[];
     double *As_base = smem;
     double *Bs_base = smem + STAGES * C::A_STAGE;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + C::STAGE_DOUBLES);
+    uint64_t *empty = full + STAGES;
+    uint64_t *xfull = empty + STAGES;
+    uint64_t *xempty = xfull + 1;
+    uint64_t *rows_ready = xempty + 1;
+    double *red = smem + C::STAGE_DOUBLES + C::NBAR;         // [WM][N_TILE]
+    double *Xs = red + C::RED_DOUBLES;                       // MODE_FUSED only: [N_TILE][ldx] + 16 zeros
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
+    const int nk = p.k_pad / KT;
+    constexpr bool XRES = (MODE == MODE_FUSED || MODE == MODE_EVALX);   // phase 1 with the X tile resident
+    const int nke = XRES ? p.ke_pad / KT : 0;
+    const int nk2 = (MODE == MODE_EVALX) ? 0 : nk;
+    const int ldx = (int)p.ldx;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], C::CONSUMERS);
+        }
+        mbar_init(xfull, 1);
+        mbar_init(xempty, C::CONSUMERS);
+        mbar_init(rows_ready, C::CONSUMERS);
+        fence_barrier_init();
+    }
+    if (MODE == MODE_EVAL) {
+        // partial-row copies of the last k tile leave the tail of a stage row untouched: make it finite
+        for (int q = tid; q < STAGES * C::B_STAGE; q += C::THREADS) Bs_base[q] = 0.0;
+        fence_proxy_async();
+    }
+    if (XRES) {
+        // the k loop of phase 1 runs to ke_pad >= ldx: the last point's reads run into this slack, which
+        // must be finite because it meets zero rows of the panel
+        if (tid < 16) Xs[C::N_TILE * ldx + tid] = 0.0;
+    }
+    __syncthreads();
+
+    if (warp >= C::CONSUMERS) {
+        // the producer warpgroup hands its registers to the consumers (the kernel launches with 168/thread)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+        if (warp != C::CONSUMERS) return;
+        // ------------------------------- producer warp: runs ahead over the tiles -------------------
+        int it = 0;
+        unsigned tpar = 0;                                   // parity of this CTA's tile counter
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, tpar ^= 1) {
+            const int64_t col0 = (int64_t)tile * C::N_TILE;
+            if (XRES) {
+                mbar_wait(xempty, tpar ^ 1);                 // consumers are done with the previous X tile
+                if (lane == 0) {
+                    const unsigned bytes = (unsigned)(C::N_TILE * ldx * 8);
+                    mbar_expect_tx(xfull, bytes);
+                    bulk_g2s(Xs, p.X + col0 * p.ldx, bytes, xfull);   // the whole X tile in one bulk copy
+                }
+                for (int kt = 0; kt < nke; ++kt, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                    if (lane == 0) mbar_expect_tx(&full[s], panel_bytes<C>(p.ldat_e));
+                    __syncwarp();
+                    produce_panel<C>(As_base + s * C::A_STAGE, p.At_e, p.ldat_e, kt * KT, &full[s], lane);
+                }
+            }
+            bool rows_waited = (MODE != MODE_FUSED);
+            for (int kt = 0; kt < nk2; ++kt, ++it) {
+                const int s = it % STAGES;
+                if (!rows_waited && kt * KT + KT > p.c) {    // this stage reads rows_new written by phase 1
+                    mbar_wait(rows_ready, tpar);
+                    rows_waited = true;
+                }
+                mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);   // first lap: returns immediately
+                produce_stage<C, MODE == MODE_FUSED ? MODE_SCHUR : MODE>(p, As_base + s * C::A_STAGE,
+                                                                          Bs_base + s * C::B_STAGE, &full[s], kt * KT, col0, lane);
+            }
+        }
+        return;
+    }
+
+    // ----------------------------------- consumer warps ------------------------------------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
     const int wm = warp % C::WM, wn = warp / C::WM;
     const int m0 = wm * C::MI * 8, n0 = wn * C::NI * 8;
     const int lr = lane >> 2, lk = lane & 3;
-    const int64_t col0 = (int64_t)blockIdx.x * C::N_TILE;
+    const int k_real = (MODE == MODE_EVAL) ? p.d : p.K;
 
-    double acc[C::MI][C::NI][2];
+    int it = 0;
+    unsigned tpar = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, tpar ^= 1) {
+        const int64_t col0 = (int64_t)tile * C::N_TILE;
+        double acc[C::MI][C::NI][2];
 #pragma unroll
-    for (int i = 0; i < C::MI; ++i)
+        for (int i = 0; i < C::MI; ++i)
 #pragma unroll
-        for (int j = 0; j < C::NI; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+            for (int j = 0; j < C::NI; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
-    const int nk = p.k_pad / KT;
-    // prologue: STAGES-1 stages in flight
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < nk) load_stage<C, MODE>(p, As_base + s * C::A_STAGE, Bs_base + s * C::B_STAGE, s * KT, col0, tid);
-        cp_async_commit();
-    }
-    for (int kt = 0; kt < nk; ++kt) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        {   // refill the stage consumed in the previous iteration
-            int nxt = kt + STAGES - 1;
-            if (nxt < nk) {
-                int s = nxt % STAGES;
-                load_stage<C, MODE>(p, As_base + s * C::A_STAGE, Bs_base + s * C::B_STAGE, nxt * KT, col0, tid);
+        if (XRES) {
+            // ---- phase 1: rows_new tile = k(Xsel, X tile), written to R and read back by phase 2 through L2
+            mbar_wait(xfull, tpar);
+            for (int kt = 0; kt < nke; ++kt, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(&full[s], (it / STAGES) & 1);
+                consume_stage<C, 2>(acc, As_base + s * C::A_STAGE + m0 + lr, Xs + (n0 + lr) * ldx + kt * KT, ldx, lk,
+                                    live_ksteps(kt, p.d));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
             }
-            cp_async_commit();
-        }
-        const double *As = As_base + (kt % STAGES) * C::A_STAGE;
-        const double *Bs = Bs_base + (kt % STAGES) * C::B_STAGE;
-#pragma unroll
-        for (int ks = 0; ks < KT / 4; ++ks) {
-            const int kk = ks * 4 + lk;
-            double a[C::MI], b[C::NI];
-#pragma unroll
-            for (int i = 0; i < C::MI; ++i) a[i] = As[kk * C::LDA + m0 + i * 8 + lr];
-#pragma unroll
-            for (int j = 0; j < C::NI; ++j) {
-                if (MODE == MODE_SCHUR) b[j] = Bs[kk * C::LDB + n0 + j * 8 + lr];
-                else b[j] = Bs[(n0 + j * 8 + lr) * LDBK + kk];
-            }
+            if (lane == 0) mbar_arrive(xempty);            // the X tile may be overwritten by the next one
+            eval_epilogue<C>(p, acc, const_cast<double *>(p.R), p.ldr, col0, m0, n0, lr, lk);
+            if (MODE == MODE_EVALX) continue;
+            fence_proxy_async_all();                       // generic-proxy global writes -> visible to the TMA reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(rows_ready);
 #pragma unroll
             for (int i = 0; i < C::MI; ++i)
 #pragma unroll
-                for (int j = 0; j < C::NI; ++j) dmma884(acc[i][j], a[i], b[j]);
+                for (int j = 0; j < C::NI; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
         }
-    }
-    cp_async_wait<0>();
-    __syncthreads();   // all warps done with the stages: smem can be reused by the epilogue
+        for (int kt = 0; kt < nk2; ++kt, ++it) {
+            const int s = it % STAGES;
+            mbar_wait(&full[s], (it / STAGES) & 1);
+            if (MODE == MODE_EVAL)
+                consume_stage<C, 1>(acc, As_base + s * C::A_STAGE + m0 + lr, Bs_base + s * C::B_STAGE + (n0 + lr) * LDBK, 0,
+                                    lk, live_ksteps(kt, k_real));
+            else
+                consume_stage<C, 0>(acc, As_base + s * C::A_STAGE + m0 + lr, Bs_base + s * C::B_STAGE + n0 + lr, 0, lk,
+                                    live_ksteps(kt, k_real));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);         // this warp is done reading the stage
+        }
 
-    // C fragment: row = m0 + i*8 + lr, cols = n0 + j*8 + 2*lk + {0,1}
-    if (MODE == MODE_SCHUR) {
-        double csum[C::NI][2];
+        // C fragment: row = m0 + i*8 + lr, cols = n0 + j*8 + 2*lk + {0,1}
+        if (MODE != MODE_EVAL) {
+            double csum[C::NI][2];
 #pragma unroll
-        for (int j = 0; j < C::NI; ++j) { csum[j][0] = 0.0; csum[j][1] = 0.0; }
+            for (int j = 0; j < C::NI; ++j) { csum[j][0] = 0.0; csum[j][1] = 0.0; }
 #pragma unroll
-        for (int i = 0; i < C::MI; ++i) {
-            const int row = m0 + i * 8 + lr;
-            if (row < p.m_valid) {
-                double *dst = p.Cout + (int64_t)row * p.ldc + col0 + n0 + 2 * lk;
+            for (int i = 0; i < C::MI; ++i) {
+                const int row = m0 + i * 8 + lr;
+                if (row < p.m_valid) {
+                    double *dst = p.Cout + (int64_t)row * p.ldc + col0 + n0 + 2 * lk;
+#pragma unroll
+                    for (int j = 0; j < C::NI; ++j)
+                        *reinterpret_cast<double2 *>(dst + j * 8) = make_double2(acc[i][j][0], acc[i][j][1]);
+                }
+                // rows >= m_valid are exactly zero (At zero padded), so they add nothing below
 #pragma unroll
                 for (int j = 0; j < C::NI; ++j) {
-                    *reinterpret_cast<double2 *>(dst + j * 8) = make_double2(acc[i][j][0], acc[i][j][1]);
+                    csum[j][0] = fma(acc[i][j][0], acc[i][j][0], csum[j][0]);
+                    csum[j][1] = fma(acc[i][j][1], acc[i][j][1], csum[j][1]);
                 }
             }
-            // rows >= m_valid are exactly zero (At zero padded), so they add nothing below
+            // reduce over the 8 row groups of the warp (lanes with equal lk)
 #pragma unroll
-            for (int j = 0; j < C::NI; ++j) {
-                csum[j][0] = fma(acc[i][j][0], acc[i][j][0], csum[j][0]);
-                csum[j][1] = fma(acc[i][j][1], acc[i][j][1], csum[j][1]);
-            }
-        }
-        // reduce over the 8 row groups of the warp (lanes with equal lk)
+            for (int j = 0; j < C::NI; ++j)
 #pragma unroll
-        for (int j = 0; j < C::NI; ++j)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                double v = csum[j][e];
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
-                v += __shfl_xor_sync(0xffffffffu, v, 8);
-                v += __shfl_xor_sync(0xffffffffu, v, 16);
-                csum[j][e] = v;
-            }
-        double *red = smem;   // [WM][N_TILE]
-        if (lr == 0) {
-#pragma unroll
-            for (int j = 0; j < C::NI; ++j) {
-                red[wm * C::N_TILE + n0 + j * 8 + 2 * lk] = csum[j][0];
-                red[wm * C::N_TILE + n0 + j * 8 + 2 * lk + 1] = csum[j][1];
-            }
-        }
-        __syncthreads();
-        for (int n = tid; n < C::N_TILE; n += C::THREADS) {
-            double sres = 0.0;
-#pragma unroll
-            for (int w = 0; w < C::WM; ++w) sres += red[w * C::N_TILE + n];
-            double dv = p.diag[col0 + n] - sres;
-            p.diag[col0 + n] = dv > 0.0 ? dv : 0.0;      // .clip(min=0); NaN -> 0 never arises from finite data
-        }
-    } else {
-        double xn[C::NI][2];
-#pragma unroll
-        for (int j = 0; j < C::NI; ++j) {
-            xn[j][0] = p.xnorm[col0 + n0 + j * 8 + 2 * lk];
-            xn[j][1] = p.xnorm[col0 + n0 + j * 8 + 2 * lk + 1];
-        }
-#pragma unroll
-        for (int i = 0; i < C::MI; ++i) {
-            const int row = m0 + i * 8 + lr;
-            if (row < p.m_valid) {
-                const double pn = p.pnorm[row];
-                double *dst = p.Cout + (int64_t)row * p.ldc + col0 + n0 + 2 * lk;
+                for (int e = 0; e < 2; ++e) {
+                    double v = csum[j][e];
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    csum[j][e] = v;
+                }
+            consumer_bar_sync(C::CONSUMERS * 32);          // previous tile's readers of `red` are done
+            if (lr == 0) {
 #pragma unroll
                 for (int j = 0; j < C::NI; ++j) {
-                    // sklearn: D2 = ((-2 * X.Y^T) + XX) + YY, clamped at 0
-                    double d0 = (-2.0 * acc[i][j][0] + pn) + xn[j][0];
-                    double d1 = (-2.0 * acc[i][j][1] + pn) + xn[j][1];
-                    d0 = d0 > 0.0 ? d0 : 0.0;
-                    d1 = d1 > 0.0 ? d1 : 0.0;
-                    *reinterpret_cast<double2 *>(dst + j * 8) =
-                        make_double2(kern_from_d2(p.kp, d0), kern_from_d2(p.kp, d1));
+                    red[wm * C::N_TILE + n0 + j * 8 + 2 * lk] = csum[j][0];
+                    red[wm * C::N_TILE + n0 + j * 8 + 2 * lk + 1] = csum[j][1];
                 }
             }
+            consumer_bar_sync(C::CONSUMERS * 32);
+            for (int n = tid; n < C::N_TILE; n += C::CONSUMERS * 32) {
+                double sres = 0.0;
+#pragma unroll
+                for (int w = 0; w < C::WM; ++w) sres += red[w * C::N_TILE + n];
+                double dv = p.diag[col0 + n] - sres;
+                p.diag[col0 + n] = dv > 0.0 ? dv : 0.0;    // .clip(min=0)
+            }
+        } else {
+            eval_epilogue<C>(p, acc, p.Cout, p.ldc, col0, m0, n0, lr, lk);
         }
     }
 }

@@ -88,4 +88,10 @@ __device__ __forceinline__ double kern_from_d2(const KernParams &kp, double d2) 
     return (1.0 + s5 * r + 5.0 / 3.0 * r * r) * exp(-s5 * r);
 }
 
+// Out-of-line pair version for the unrolled DMMA epilogues: inlining exp() at all 64 accumulator sites of a
+// thread made the epilogue ~60 KB of SASS, larger than the instruction cache, and 3x slower than the math.
+static __device__ __noinline__ double2 kern_from_d2_pair(const KernParams kp, double d0, double d1) {
+    return make_double2(kern_from_d2(kp, d0), kern_from_d2(kp, d1));
+}
+
 __device__ __forceinline__ double kern_from_l1(const KernParams &kp, double l1) { return exp(-l1 / kp.bw); }

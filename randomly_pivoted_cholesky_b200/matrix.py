@@ -219,6 +219,8 @@ class KernelMatrix(AbstractPSDMatrix):
         self.n_pad = _round_up(n, COL_ALIGN)
         self.d = d
         self.d_pad = _round_up(d, FEAT_ALIGN)
+        # point stride == 4 (mod 8) doubles: the DMMA fragment reads of a resident X tile are then bank-conflict free
+        self.ldx = self.d_pad if self.d_pad % 8 == 4 else self.d_pad + 4
         self._ctx = _lib.Context.get(dev.index)
         self.kernel_kwargs = dict(kwargs)
 
@@ -245,11 +247,11 @@ class KernelMatrix(AbstractPSDMatrix):
         if kind == _lib.KERN_LAPLACE:
             stab = False                                     # LaplaceKernel_mtx ignores it (kernels.py:16)
 
-        Xp = torch.zeros((self.n_pad, self.d_pad), dtype=torch.float64, device=dev)
+        Xp = torch.zeros((self.n_pad, self.ldx), dtype=torch.float64, device=dev)
         Xp[:n, :d] = Xd
         self._Xd = Xp
         self._xnorm = torch.zeros((self.n_pad,), dtype=torch.float64, device=dev)
-        check(self._ctx.lib.rpc_row_norms(self._ctx.handle, _stream(), _ptr(Xp), self.n_pad, self.d_pad, self.d_pad,
+        check(self._ctx.lib.rpc_row_norms(self._ctx.handle, _stream(), _ptr(Xp), self.n_pad, self.d_pad, self.ldx,
                                           _ptr(self._xnorm)), "rpc_row_norms")
 
         if isinstance(bandwidth, str):
@@ -286,7 +288,7 @@ class KernelMatrix(AbstractPSDMatrix):
         n = self.shape[0]
         mi, mj = len(vec_i), len(vec_j)
         ti = torch.as_tensor(np.asarray(vec_i, dtype=np.int64), device=self.device)
-        piv = _PivotPayload(mi, self.d_pad, self.device)
+        piv = _PivotPayload(mi, self.ldx, self.device)
         self._dev_gather(ti, mi, piv)
         full = (mj == n) and (vec_j == list(range(n)) if mj < 4096 else
                               bool(np.array_equal(np.asarray(vec_j, dtype=np.int64), np.arange(n))))
@@ -295,13 +297,13 @@ class KernelMatrix(AbstractPSDMatrix):
         else:
             tj = torch.as_tensor(np.asarray(vec_j, dtype=np.int64), device=self.device)
             npad = _round_up(mj, COL_ALIGN)
-            Y = torch.zeros((npad, self.d_pad), dtype=torch.float64, device=self.device)
+            Y = torch.zeros((npad, self.ldx), dtype=torch.float64, device=self.device)
             Y[:mj] = self._Xd[tj]
             ynorm = torch.zeros((npad,), dtype=torch.float64, device=self.device)
             ynorm[:mj] = self._xnorm[tj]
         out = torch.empty((mi, npad), dtype=torch.float64, device=self.device)
         check(self._ctx.lib.rpc_kernel_rows(self._ctx.handle, _stream(), C.byref(self._spec), _ptr(Y), _ptr(ynorm), npad,
-                                            self.d_pad, self.d_pad, _ptr(piv.X), _ptr(piv.norm), mi, self.d_pad,
+                                            self.d_pad, self.ldx, _ptr(piv.X), _ptr(piv.norm), mi, self.ldx,
                                             _ptr(out), npad), "rpc_kernel_rows")
         return out[:, :mj].cpu().numpy()
 
@@ -327,21 +329,21 @@ class KernelMatrix(AbstractPSDMatrix):
               "rpc_kernel_diag")
 
     def _dev_new_payload(self, m_max):
-        return _PivotPayload(m_max, self.d_pad, self.device)
+        return _PivotPayload(m_max, self.ldx, self.device)
 
     def _dev_gather(self, idx_dev, m, piv):
         check(self._ctx.lib.rpc_gather_pivots(self._ctx.handle, _stream(), _ptr(idx_dev), m, _ptr(self._Xd), _ptr(self._xnorm),
-                                              self.d_pad, self.d_pad, _ptr(piv.X), _ptr(piv.norm), self.d_pad, None, 0, 0,
+                                              self.d_pad, self.ldx, _ptr(piv.X), _ptr(piv.norm), self.ldx, None, 0, 0,
                                               None, 0), "rpc_gather_pivots")
 
     def _dev_block_into(self, idx_dev, m, piv, H, ldh):
         check(self._ctx.lib.rpc_kernel_block(self._ctx.handle, _stream(), C.byref(self._spec), _ptr(piv.X), _ptr(piv.norm), m,
-                                             self.d_pad, self.d_pad, _ptr(H), ldh), "rpc_kernel_block")
+                                             self.d_pad, self.ldx, _ptr(H), ldh), "rpc_kernel_block")
 
     def _dev_rows_into(self, idx_dev, m, piv, out_ptr, ldo):
         check(self._ctx.lib.rpc_kernel_rows(self._ctx.handle, _stream(), C.byref(self._spec), _ptr(self._Xd), _ptr(self._xnorm),
-                                            self.n_pad, self.d_pad, self.d_pad, _ptr(piv.X), _ptr(piv.norm), m, self.d_pad,
+                                            self.n_pad, self.d_pad, self.ldx, _ptr(piv.X), _ptr(piv.norm), m, self.ldx,
                                             out_ptr, ldo), "rpc_kernel_rows")
 
     def _simple_step_args(self):
-        return self._spec, self._Xd, self._xnorm, self.d_pad, self.d_pad, None, 0
+        return self._spec, self._Xd, self._xnorm, self.d_pad, self.ldx, None, 0

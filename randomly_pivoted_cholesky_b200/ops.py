@@ -97,7 +97,7 @@ def schur_update(G, c, rows_new, P, L, diag, device=None):
     s = rows_new.shape[0]
     n_pad = G.shape[1]
     k_pad = _round_up(c + s, KT)
-    ldat = _round_up(s, 256)
+    ldat = int(ctx.lib.rpc_panel_ld(s))
     At = torch.empty((k_pad, ldat), dtype=torch.float64, device=dev)
     Pd = P.contiguous() if c > 0 else None
     Ld = L.contiguous()

@@ -28,6 +28,11 @@ from .matrix import AbstractPSDMatrix, PSDMatrix, _ptr, _round_up, _stream
 EPS = float(np.finfo(float).eps)
 AT_LD_ALIGN = 256          # panel leading dimension granularity (widest row tile of the DMMA kernel)
 
+# rpc_fused_update (kernel rows evaluated inside the Schur kernel) measured ~10% slower per round than
+# rpc_kernel_rows + rpc_schur_update on B200 (profiles/): opt-in only
+import os as _os
+USE_FUSED = _os.environ.get("RPC_B200_FUSED", "0") == "1"
+
 # bench.py sets this to a list to collect (start_event, end_event, flops, bytes, phase) per timed launch
 KERNEL_TIMERS = None
 
@@ -86,9 +91,8 @@ class _State:
         self.L = torch.empty((m_max, m_max), **f64)
         self.acc = torch.zeros((m_max,), dtype=torch.int32, device=self.dev)
         self.info = torch.zeros((4,), dtype=torch.int32, device=self.dev)
-        self.ldat = _round_up(m_max, AT_LD_ALIGN)
         self.k_pad_max = _round_up(k + m_max, KT)
-        self.At = torch.empty((self.k_pad_max, self.ldat), **f64)
+        self.At = torch.empty((self.k_pad_max * (_round_up(m_max, AT_LD_ALIGN) + 16),), **f64)   # panel, per-round ld
         # pinned staging
         self.u_host = torch.empty((2 * m_max,), dtype=torch.float64).pin_memory()
         self.sel_host = torch.empty((m_max,), dtype=torch.int64).pin_memory()
@@ -115,9 +119,10 @@ class _State:
         X = getattr(A, "_Xd", None)
         xn = getattr(A, "_xnorm", None)
         d = getattr(A, "d_pad", 0)
-        check(self.lib.rpc_gather_pivots(self.ctx.handle, _stream(), _ptr(idx_dev), m, _ptr(X), _ptr(xn), d, d,
+        ldx = getattr(A, "ldx", 0)
+        check(self.lib.rpc_gather_pivots(self.ctx.handle, _stream(), _ptr(idx_dev), m, _ptr(X), _ptr(xn), d, ldx,
                                          _ptr(piv.X) if piv is not None else None,
-                                         _ptr(piv.norm) if piv is not None else None, d,
+                                         _ptr(piv.norm) if piv is not None else None, ldx,
                                          _ptr(self.G) if (with_P and c > 0) else None, self.n_pad, c if with_P else 0,
                                          _ptr(self.P) if (with_P and c > 0) else None, self.m_max), "rpc_gather_pivots")
 
@@ -139,20 +144,32 @@ class _State:
     def update(self, c, s, acc_dev, sel_idx_dev, sel_piv, panel_mode=0, Lmat=None):
         """rows[c:c+s] = A[S,:]; G[c:c+s] = L^{-1}(rows - P^T G[:c]); diag update (rpcholesky.py:101-107,128-129 / 205-209)."""
         k_pad = _round_up(c + s, KT)
+        ldat = int(self.lib.rpc_panel_ld(s))          # stride that lets the kernel fetch a panel stage in one bulk copy
         Lm = self.L if Lmat is None else Lmat
         with _timed("panel", 1.0 * s * s * c + s ** 3 / 3.0, 8.0 * c * s):
             check(self.lib.rpc_build_panel(self.ctx.handle, _stream(), _ptr(self.P), self.m_max, c, _ptr(acc_dev), s,
-                                           _ptr(Lm), Lm.stride(0), panel_mode, _ptr(self.At), self.ldat, k_pad),
+                                           _ptr(Lm), Lm.stride(0), panel_mode, _ptr(self.At), ldat, k_pad),
                   "rpc_build_panel")
         rows_ptr = C.c_void_p(self.rows.data_ptr() + 8 * c * self.n_pad)
         n, d = self.n, getattr(self.A, "d", 0)
+        A = self.A
+        spec = getattr(A, "_spec", None)
+        if USE_FUSED and spec is not None and self.lib.rpc_fused_update_supported(C.byref(spec), s, A.ldx):
+            # kernel rows evaluated and consumed in ONE pass over the column tile (DESIGN.md: fused update)
+            with _timed("schur", 2.0 * s * (c + s + d) * n, 8.0 * n * (c + 2 * s + d + 2)):
+                check(self.lib.rpc_fused_update(self.ctx.handle, _stream(), C.byref(spec), _ptr(A._Xd), _ptr(A._xnorm),
+                                                self.n_pad, A.d_pad, A.ldx, _ptr(sel_piv.X), _ptr(sel_piv.norm), A.ldx,
+                                                _ptr(self.G), self.n_pad, c, s, _ptr(self.At), ldat, k_pad, rows_ptr,
+                                                self.n_pad, _ptr(self.diag)), "rpc_fused_update")
+            A._count(s * self.n)
+            return
         with _timed("eval", 2.0 * s * n * d, 8.0 * n * (s + d)):
             self.A._dev_rows_into(sel_idx_dev, s, sel_piv, rows_ptr, self.n_pad)
         self.A._count(s * self.n)
-        # algorithmic work of the fused update (DESIGN.md): 2 s (c+s) N flops; reads G[:c] and rows_new, writes G_new
+        # algorithmic work of the Schur update (DESIGN.md): 2 s (c+s) N flops; reads G[:c] and rows_new, writes G_new
         with _timed("schur", 2.0 * s * (c + s) * n, 8.0 * n * (c + 2 * s + 2)):
             check(self.lib.rpc_schur_update(self.ctx.handle, _stream(), _ptr(self.G), self.n_pad, c, s, _ptr(self.At),
-                                            self.ldat, k_pad, rows_ptr, self.n_pad, _ptr(self.diag), self.n_pad),
+                                            ldat, k_pad, rows_ptr, self.n_pad, _ptr(self.diag), self.n_pad),
                   "rpc_schur_update")
 
     def result(self, count, arr_idx):
