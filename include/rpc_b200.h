@@ -89,13 +89,12 @@ int rpc_psd_block(rpc_ctx *ctx, void *stream, const double *A, int64_t lda, cons
 
 /* ---- pivot sampler: rng.choice(range(n), size=m, p=diags/sum(diags)) (rpcholesky.py:31,91,184) -- */
 
-/* idx[j] = #{ i : cdf[i] <= u[j] } with cdf the normalised prefix sums of diag[0:n_pad].
- * A blocked parallel scan picks the index; any draw whose decision lies inside the rounding band
- * of numpy's sequential cumsum is re-resolved ON THE DEVICE by a kernel that replays numpy's
- * sequential arithmetic exactly (python sum -> p = d/S -> cumsum -> /cdf[-1] -> searchsorted right),
- * so the pivots are bit-identical to the reference's for the same uniforms.
- * stats[0] = sum(diag) (blocked order), stats[1] = 1.0 if the probabilities are invalid
- * (sum <= 0 or NaN: numpy raises ValueError), stats[2] = number of draws re-resolved exactly. */
+/* idx[j] = #{ i : cdf[i] <= u[j] } with cdf = cumsum(diag/sum(diag)) / cdf[-1] over diag[0:n_pad], every sum
+ * rounded exactly as numpy's sequential left-to-right fp64 loop rounds it (the device reproduces the sequentially
+ * rounded prefix sums in parallel, csrc/sampler.cu), so the pivots are bit-identical to the reference's for the
+ * same uniforms and stats[0] equals python's sum(diags) bit for bit.
+ * stats[0] = sum(diag), stats[1] = 1.0 if the probabilities are invalid (sum <= 0, NaN or negative entries:
+ * numpy raises ValueError), stats[2] = 1.0 on an internal consistency failure (never observed).  m may be 0. */
 int rpc_sample_pivots(rpc_ctx *ctx, void *stream, const double *diag, int64_t n_pad, const double *u, int m,
                       int64_t *idx, double *stats);
 
@@ -103,10 +102,13 @@ int rpc_sample_pivots(rpc_ctx *ctx, void *stream, const double *diag, int64_t n_
 
 /* Xpiv[j,:] = X[idx[j],:], pnorm[j] = xnorm[idx[j]] (matrix.py:189 `self.data[vec_i,:]`) and
  * P[r, j] = G[r, idx[j]] for r<c (rpcholesky.py:102,189,206 `G[0:counter, idx]`).
- * X/xnorm may be NULL (dense operator), G may be NULL when c == 0. */
+ * X/xnorm may be NULL (dense operator), G may be NULL when c == 0.
+ * Row-sharded operation: idx holds GLOBAL indices and this shard owns [lo, hi) (local row = idx - lo);
+ * entries of pivots owned by another shard are written as 0, so that a sum all-reduce of the payload over
+ * the shards assembles it exactly (one non-zero contributor per slot).  Single GPU: lo = 0, hi = N. */
 int rpc_gather_pivots(rpc_ctx *ctx, void *stream, const int64_t *idx, int m, const double *X, const double *xnorm,
                       int d, int64_t ldx, double *Xpiv, double *pnorm, int64_t ldp, const double *G, int64_t ldg,
-                      int c, double *P, int64_t ldP);
+                      int c, double *P, int64_t ldP, int64_t lo, int64_t hi);
 
 /* H -= P^T P (H is m x m, P is c x m): residual Gram of the proposals (rpcholesky.py:189). */
 int rpc_gram_residual(rpc_ctx *ctx, void *stream, const double *P, int c, int m, int64_t ldP, double *H, int64_t ldh);

@@ -180,7 +180,7 @@ __device__ __forceinline__ void produce_stage(const Params &p, double *As, doubl
 // BKIND 0: B stage is k-major [KT][LDB]; BKIND 1: point-major [N_TILE][LDBK]; BKIND 2: resident X tile [N_TILE][ldx]
 template <class C, int BKIND>
 __device__ __forceinline__ void consume_stage(double (&acc)[C::MI][C::NI][2], const double *As, const double *Bs, int ldx,
-                                              int lk, int ksteps) {
+                                              int lk, int ksteps, int mi_cnt) {
     double a[2][C::MI], b[2][C::NI];
     auto ldb = [&](int j, int kk) -> double {
         if (BKIND == 0) return Bs[kk * C::LDB + j * 8];
@@ -188,7 +188,7 @@ __device__ __forceinline__ void consume_stage(double (&acc)[C::MI][C::NI][2], co
         return Bs[j * 8 * ldx + kk];
     };
 #pragma unroll
-    for (int i = 0; i < C::MI; ++i) a[0][i] = As[lk * C::LDA + i * 8];
+    for (int i = 0; i < C::MI; ++i) a[0][i] = i < mi_cnt ? As[lk * C::LDA + i * 8] : 0.0;
 #pragma unroll
     for (int j = 0; j < C::NI; ++j) b[0][j] = ldb(j, lk);
 #pragma unroll
@@ -197,15 +197,17 @@ __device__ __forceinline__ void consume_stage(double (&acc)[C::MI][C::NI][2], co
         if (ks + 1 < KT / 4 && ks + 1 < ksteps) {
             const int kk = (ks + 1) * 4 + lk;
 #pragma unroll
-            for (int i = 0; i < C::MI; ++i) a[nxt][i] = As[kk * C::LDA + i * 8];
+            for (int i = 0; i < C::MI; ++i) a[nxt][i] = i < mi_cnt ? As[kk * C::LDA + i * 8] : 0.0;
 #pragma unroll
             for (int j = 0; j < C::NI; ++j) b[nxt][j] = ldb(j, kk);
         }
         if (ks < ksteps) {
 #pragma unroll
             for (int i = 0; i < C::MI; ++i)
+                if (i < mi_cnt) {                      // warp-uniform: this warp owns mi_cnt row fragments
 #pragma unroll
-                for (int j = 0; j < C::NI; ++j) dmma884(acc[i][j], a[cur][i], b[cur][j]);
+                    for (int j = 0; j < C::NI; ++j) dmma884(acc[i][j], a[cur][i], b[cur][j]);
+                }
         }
     }
 }
@@ -213,7 +215,7 @@ __device__ __forceinline__ void consume_stage(double (&acc)[C::MI][C::NI][2], co
 // kernel values from the x.y accumulators -> Cout (MODE_EVAL and phase 1 of MODE_FUSED)
 template <class C>
 __device__ __forceinline__ void eval_epilogue(const Params &p, double (&acc)[C::MI][C::NI][2], double *out, int64_t ldo,
-                                              int64_t col0, int m0, int n0, int lr, int lk) {
+                                              int64_t col0, int m0, int n0, int lr, int lk, int mi_cnt) {
     double xn[C::NI][2];
 #pragma unroll
     for (int j = 0; j < C::NI; ++j) {
@@ -223,7 +225,7 @@ __device__ __forceinline__ void eval_epilogue(const Params &p, double (&acc)[C::
 #pragma unroll
     for (int i = 0; i < C::MI; ++i) {
         const int row = m0 + i * 8 + lr;
-        if (row < p.m_valid) {
+        if (i < mi_cnt && row < p.m_valid) {
             const double pn = p.pnorm[row];
             double *dst = out + (int64_t)row * ldo + col0 + n0 + 2 * lk;
 #pragma unroll
@@ -331,8 +333,13 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
     // ----------------------------------- consumer warps ------------------------------------------
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
     const int wm = warp % C::WM, wn = warp / C::WM;
-    const int m0 = wm * C::MI * 8, n0 = wn * C::NI * 8;
+    const int n0 = wn * C::NI * 8;
     const int lr = lane >> 2, lk = lane & 3;
+    // Every warp row owns MI fragments of 8 rows.  (Dealing ceil(m/8) fragments unevenly over the warp rows, to
+    // get an 8-row instead of a 32-row tile granularity, was measured 2% SLOWER on B200: the predicated DMMAs cost
+    // more than the idle fragments they save -- profiles/schur_micro_r01.jsonl.)
+    constexpr int mi_cnt = C::MI;
+    const int m0 = wm * C::MI * 8;
     const int k_real = (MODE == MODE_EVAL) ? p.d : p.K;
 
     int it = 0;
@@ -352,12 +359,12 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
                 const int s = it % STAGES;
                 mbar_wait(&full[s], (it / STAGES) & 1);
                 consume_stage<C, 2>(acc, As_base + s * C::A_STAGE + m0 + lr, Xs + (n0 + lr) * ldx + kt * KT, ldx, lk,
-                                    live_ksteps(kt, p.d));
+                                    live_ksteps(kt, p.d), mi_cnt);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[s]);
             }
             if (lane == 0) mbar_arrive(xempty);            // the X tile may be overwritten by the next one
-            eval_epilogue<C>(p, acc, const_cast<double *>(p.R), p.ldr, col0, m0, n0, lr, lk);
+            eval_epilogue<C>(p, acc, const_cast<double *>(p.R), p.ldr, col0, m0, n0, lr, lk, mi_cnt);
             if (MODE == MODE_EVALX) continue;
             fence_proxy_async_all();                       // generic-proxy global writes -> visible to the TMA reads
             __syncwarp();
@@ -372,10 +379,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
             mbar_wait(&full[s], (it / STAGES) & 1);
             if (MODE == MODE_EVAL)
                 consume_stage<C, 1>(acc, As_base + s * C::A_STAGE + m0 + lr, Bs_base + s * C::B_STAGE + (n0 + lr) * LDBK, 0,
-                                    lk, live_ksteps(kt, k_real));
+                                    lk, live_ksteps(kt, k_real), mi_cnt);
             else
                 consume_stage<C, 0>(acc, As_base + s * C::A_STAGE + m0 + lr, Bs_base + s * C::B_STAGE + n0 + lr, 0, lk,
-                                    live_ksteps(kt, k_real));
+                                    live_ksteps(kt, k_real), mi_cnt);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);         // this warp is done reading the stage
         }
@@ -388,7 +395,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
 #pragma unroll
             for (int i = 0; i < C::MI; ++i) {
                 const int row = m0 + i * 8 + lr;
-                if (row < p.m_valid) {
+                if (i < mi_cnt && row < p.m_valid) {         // fragments >= mi_cnt belong to the next warp row
                     double *dst = p.Cout + (int64_t)row * p.ldc + col0 + n0 + 2 * lk;
 #pragma unroll
                     for (int j = 0; j < C::NI; ++j)
@@ -429,7 +436,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
                 p.diag[col0 + n] = dv > 0.0 ? dv : 0.0;    // .clip(min=0)
             }
         } else {
-            eval_epilogue<C>(p, acc, p.Cout, p.ldc, col0, m0, n0, lr, lk);
+            eval_epilogue<C>(p, acc, p.Cout, p.ldc, col0, m0, n0, lr, lk, mi_cnt);
         }
     }
 }

@@ -136,7 +136,6 @@ template <bool DIV>
 __global__ void __launch_bounds__(32) sc_walk(const double *__restrict__ d, int64_t n, const double *Sptr,
                                               const double *__restrict__ D, const int32_t *__restrict__ cls, int nch,
                                               double *__restrict__ cstart, int32_t *__restrict__ bad) {
-    __shared__ double xs[SC_CH];
     const int lane = threadIdx.x;
     const unsigned full = 0xffffffffu;
     const double S = DIV ? *Sptr : 1.0;
@@ -152,20 +151,56 @@ __global__ void __launch_bounds__(32) sc_walk(const double *__restrict__ d, int6
         while (pos < kend) {
             const int e0 = __shfl_sync(full, e, pos);
             if (e0 == INT_MIN) {
-                // replay chunk k0+pos with real sequential fp64 adds
-                const int64_t base = (int64_t)(k0 + pos) * SC_CH;
+                // Chunk k0+pos could not be classified a priori (binade crossing, rounding tie, start of the
+                // array).  Now the EXACT carry is known, so the same argument is applied at a finer grain: lane l
+                // owns 8 consecutive elements; all lanes up to the first one that crosses the binade of the
+                // carry (or holds a tie) are folded in bulk, that lane's 8 elements are added one by one, repeat.
+                const int64_t base = (int64_t)(k0 + pos) * SC_CH + lane * 8;
+                double x[8];
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    int64_t j = base + t * 32 + lane;
-                    xs[t * 32 + lane] = j < n ? elem<DIV>(d, j, S) : 0.0;
-                }
-                __syncwarp();
+                for (int t = 0; t < 8; ++t) x[t] = (base + t) < n ? elem<DIV>(d, base + t, S) : 0.0;
                 if (lane == 0) cstart[k0 + pos] = carry;
-                double cc = carry;
-#pragma unroll 16
-                for (int j = 0; j < SC_CH; ++j) cc += xs[j];   // every lane computes the same chain
-                carry = cc;
-                __syncwarp();
+                int lpos = 0;
+                while (lpos < 32) {
+                    const int e = carry > 0.0 ? ilogb(carry) : INT_MIN;
+                    int f = lpos;                                  // first lane that needs the sequential treatment
+                    if (e >= -960 && e <= 1000) {
+                        const double scale = pow2d(52 - e), q = pow2d(e - 52), top = pow2d(e + 1);
+                        double A = 0.0;
+                        bool tie = false;
+                        if (lane >= lpos) {
+#pragma unroll
+                            for (int t = 0; t < 8; ++t) {
+                                double v = x[t] * scale;
+                                double kf = floor(v);
+                                double fr = v - kf;
+                                tie |= (fr == 0.5);
+                                A += kf + (fr > 0.5 ? 1.0 : 0.0);
+                            }
+                        }
+                        double pre = A;                            // inclusive prefix over lanes >= lpos (exact integers)
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            double t2 = __shfl_up_sync(full, pre, o);
+                            if (lane >= o) pre += t2;
+                        }
+                        // lanes below lpos contributed 0, so `pre` is already the prefix over [lpos, lane]
+                        const bool bad = lane >= lpos && (tie || !isfinite(pre) || !(carry + pre * q < top));
+                        const unsigned badmask = __ballot_sync(full, bad);
+                        f = badmask ? __ffs(badmask) - 1 : 32;
+                        if (f > lpos) {
+                            const double upto = __shfl_sync(full, pre, f - 1);
+                            carry += upto * q;                     // exact: all terms are multiples of q below 2^53 q
+                        }
+                    }
+                    if (f < 32) {
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) carry += __shfl_sync(full, x[t], f);   // the real sequential adds
+                        lpos = f + 1;
+                    } else {
+                        lpos = 32;
+                    }
+                }
                 ++pos;
                 continue;
             }

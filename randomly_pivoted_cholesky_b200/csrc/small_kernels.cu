@@ -141,28 +141,34 @@ extern "C" int rpc_kernel_block(rpc_ctx *ctx, void *stream, const rpc_kernel_spe
 __global__ void gather_pivots_kernel(const int64_t *__restrict__ idx, int m, const double *__restrict__ X,
                                      const double *__restrict__ xnorm, int d, int64_t ldx, double *__restrict__ Xpiv,
                                      double *__restrict__ pnorm, int64_t ldp, const double *__restrict__ G, int64_t ldg, int c,
-                                     double *__restrict__ P, int64_t ldP) {
+                                     double *__restrict__ P, int64_t ldP, int64_t lo, int64_t hi) {
     int blk = blockIdx.x;
     if (blk < c) {
-        for (int j = threadIdx.x; j < m; j += blockDim.x) P[(int64_t)blk * ldP + j] = G[(int64_t)blk * ldg + idx[j]];
+        for (int j = threadIdx.x; j < m; j += blockDim.x) {
+            const int64_t g = idx[j];
+            P[(int64_t)blk * ldP + j] = (g >= lo && g < hi) ? G[(int64_t)blk * ldg + (g - lo)] : 0.0;
+        }
     } else {
         int j = blk - c;
-        int64_t src = idx[j];
-        for (int f = threadIdx.x; f < d; f += blockDim.x) Xpiv[(int64_t)j * ldp + f] = X[src * ldx + f];
-        if (threadIdx.x == 0 && xnorm && pnorm) pnorm[j] = xnorm[src];
+        const int64_t g = idx[j];
+        const bool mine = g >= lo && g < hi;
+        const int64_t src = g - lo;
+        for (int f = threadIdx.x; f < ldp; f += blockDim.x) Xpiv[(int64_t)j * ldp + f] = (mine && f < d) ? X[src * ldx + f] : 0.0;
+        if (threadIdx.x == 0 && xnorm && pnorm) pnorm[j] = mine ? xnorm[src] : 0.0;
     }
 }
 
 extern "C" int rpc_gather_pivots(rpc_ctx *ctx, void *stream, const int64_t *idx, int m, const double *X,
                                  const double *xnorm, int d, int64_t ldx, double *Xpiv, double *pnorm, int64_t ldp,
-                                 const double *G, int64_t ldg, int c, double *P, int64_t ldP) {
+                                 const double *G, int64_t ldg, int c, double *P, int64_t ldP, int64_t lo, int64_t hi) {
     RPC_CHECK_ARG(ctx && idx && m >= 1 && c >= 0, "null pointer or bad sizes");
     RPC_CHECK_ARG(c == 0 || (G && P), "G and P required when c > 0");
     RPC_CHECK_ARG(!X || Xpiv, "Xpiv required when X is given");
+    RPC_CHECK_ARG(hi >= lo, "empty ownership range");
     int blocks = c + (X ? m : 0);
     if (blocks == 0) return 0;
     gather_pivots_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(idx, m, X, xnorm, d, ldx, Xpiv, pnorm, ldp, G, ldg, c, P,
-                                                                  ldP);
+                                                                  ldP, lo, hi);
     RPC_LAUNCHED(ctx);
     return 0;
 }
@@ -254,7 +260,7 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rejection_cholesky_kernel(doubl
                                                                           int32_t *__restrict__ acc, int32_t *__restrict__ info) {
     extern __shared__ double sh[];
     double *lcol = sh;                 // [m]
-    double *u0 = sh + m;               // [m] original diagonal
+    double *u0 = sh + m;               // [m] u[j] * original diagonal: the acceptance threshold of step j
     int32_t *accpos = (int32_t *)(sh + 2 * m);   // [m]
     double *T = PACKED ? sh + 3 * m : H;
     const int64_t ld = ldh;
@@ -265,18 +271,22 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rejection_cholesky_kernel(doubl
         for (int i = warp; i < m; i += NW)
             for (int l = lane; l <= i; l += 32) T[tri_at<true>(i, l, ld)] = H[(int64_t)i * ldh + l];
     }
-    for (int j = tid; j < m; j += RC_THREADS) u0[j] = H[(int64_t)j * ldh + j];
+    // trace check (np.trace(H) <= 0 -> RuntimeError): only the sign matters, so the summation order does not
+    if (warp == 0) {
+        double tr = 0.0;
+        for (int j = lane; j < m; j += 32) tr += H[(int64_t)j * ldh + j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, o);
+        if (lane == 0) {
+            info[2] = (mode == 0 && !(tr > 0.0)) ? 1 : 0;
+            info[1] = 0;
+        }
+    }
+    // rpcholesky.py:151 compares np.random.rand() * H0[j,j] with the residual H[j,j]; keep the product at hand
+    for (int j = tid; j < m; j += RC_THREADS) u0[j] = (mode == 0 ? u[j] : 0.0) * H[(int64_t)j * ldh + j];
     __syncthreads();
     if (mode == 1 && shift != 0.0) {
         for (int j = tid; j < m; j += RC_THREADS) T[tri_at<PACKED>(j, j, ld)] += shift;
-    }
-    // trace check (np.trace(H) <= 0 -> RuntimeError), sequential like np.trace's add.reduce is not
-    // needed: only the sign matters
-    if (tid == 0) {
-        double tr = 0.0;
-        for (int j = 0; j < m; ++j) tr += u0[j];
-        info[2] = (mode == 0 && !(tr > 0.0)) ? 1 : 0;
-        info[1] = 0;
     }
     __syncthreads();
 
@@ -291,7 +301,7 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rejection_cholesky_kernel(doubl
             }
             accept = true;
         } else {
-            accept = u[j] * u0[j] < hjj;      // rpcholesky.py:151
+            accept = u0[j] < hjj;             // rpcholesky.py:151 (u0[j] = u_j * H0[j,j])
         }
         if (!accept) continue;
         if (nacc == max_accept) break;        // truncation of rpcholesky.py:193-196
@@ -362,13 +372,21 @@ extern "C" int rpc_rejection_cholesky(rpc_ctx *ctx, void *stream, double *H, int
 constexpr int TS_RW = 4;        // panel rows solved together by one warp (re-uses every L load 4 times)
 constexpr int TS_WARPS = 4;
 
+template <bool LSMEM>
 __global__ void __launch_bounds__(TS_WARPS * 32) panel_trsm_kernel(const double *__restrict__ P, int64_t ldP, int c,
                                                                    const int32_t *__restrict__ acc, int s,
                                                                    const double *__restrict__ L, int64_t ldl,
                                                                    double *__restrict__ At, int64_t ldat, int k_pad) {
-    extern __shared__ double zs[];                  // [TS_WARPS][TS_RW][s]
+    extern __shared__ double zs[];                  // [TS_WARPS][TS_RW][s] (+ packed lower triangle of L when LSMEM)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r0 = (blockIdx.x * TS_WARPS + warp) * TS_RW;
+    double *Ls = zs + (size_t)TS_WARPS * TS_RW * s;
+    if (LSMEM) {
+        // every step of the substitution waits on one row of L: keep it in shared memory, not behind L2 latency
+        for (int i = warp; i < s; i += TS_WARPS)
+            for (int l = lane; l <= i; l += 32) Ls[(size_t)i * (i + 1) / 2 + l] = L[(int64_t)i * ldl + l];
+        __syncthreads();
+    }
     if (r0 >= k_pad) return;
     double *z = zs + (size_t)warp * TS_RW * s;
     if (r0 < c + s) {
@@ -389,7 +407,7 @@ __global__ void __launch_bounds__(TS_WARPS * 32) panel_trsm_kernel(const double 
             double part[TS_RW];
 #pragma unroll
             for (int w = 0; w < TS_RW; ++w) part[w] = 0.0;
-            const double *Lj = L + (int64_t)j * ldl;
+            const double *Lj = LSMEM ? Ls + (size_t)j * (j + 1) / 2 : L + (int64_t)j * ldl;
             for (int l = jstart + lane; l < j; l += 32) {
                 const double lv = Lj[l];
 #pragma unroll
@@ -473,14 +491,19 @@ extern "C" int rpc_build_panel(rpc_ctx *ctx, void *stream, const double *P, int6
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == 0) {
         size_t shm = (size_t)TS_WARPS * TS_RW * s * sizeof(double);
+        size_t shm_l = shm + (size_t)s * (s + 1) / 2 * sizeof(double);
         static bool configured = false;
         if (!configured) {
-            RPC_CUDA(cudaFuncSetAttribute(panel_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+            RPC_CUDA(cudaFuncSetAttribute(panel_trsm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+            RPC_CUDA(cudaFuncSetAttribute(panel_trsm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             configured = true;
         }
         int rows_per_cta = TS_WARPS * TS_RW;
         int blocks = (k_pad + rows_per_cta - 1) / rows_per_cta;
-        panel_trsm_kernel<<<blocks, TS_WARPS * 32, shm, st>>>(P, ldP, c, acc, s, L, ldl, At, ldat, k_pad);
+        if (shm_l <= 227 * 1024)
+            panel_trsm_kernel<true><<<blocks, TS_WARPS * 32, shm_l, st>>>(P, ldP, c, acc, s, L, ldl, At, ldat, k_pad);
+        else
+            panel_trsm_kernel<false><<<blocks, TS_WARPS * 32, shm, st>>>(P, ldP, c, acc, s, L, ldl, At, ldat, k_pad);
         RPC_LAUNCHED(ctx);
         return 0;
     }

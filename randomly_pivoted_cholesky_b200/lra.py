@@ -19,12 +19,24 @@ class AbstractPSDLowRank:
         self.idx = kwargs["idx"] if ("idx" in kwargs) else None
         self._rows = kwargs["rows"] if ("rows" in kwargs) else None
         self._rows_host = None
+        # row-sharded results (dist.ShardInfo): the tensors hold this rank's columns; `.G`/`.rows` assemble the
+        # full matrices with an all-gather, so every rank must touch them together
+        self.shard_info = kwargs["shard_info"] if ("shard_info" in kwargs) else None
+
+    def _sharded(self):
+        return self.shard_info is not None and self.shard_info.world > 1
+
+    def _materialise(self, t):
+        if self._sharded():
+            from . import dist as rdist
+            return rdist.gather_columns(self.shard_info, t).cpu().numpy()
+        return t.cpu().numpy()
 
     @property
     def rows(self):
         if isinstance(self._rows, torch.Tensor):
             if self._rows_host is None:
-                self._rows_host = self._rows.cpu().numpy()
+                self._rows_host = self._materialise(self._rows)
             return self._rows_host
         return self._rows
 
@@ -109,7 +121,7 @@ class PSDLowRank(AbstractPSDLowRank):
     def G(self):
         if isinstance(self._G, torch.Tensor):
             if self._G_host is None:
-                self._G_host = self._G.cpu().numpy()
+                self._G_host = self._materialise(self._G)
             return self._G_host
         return self._G
 
@@ -127,11 +139,16 @@ class PSDLowRank(AbstractPSDLowRank):
 
     def trace(self):
         if self._on_device():
+            if self._sharded():                                # local columns only (the shard is padded), then sum
+                import torch.distributed as tdist
+                t = torch.linalg.norm(self._G[:, :self.shard_info.n_loc]) ** 2
+                tdist.all_reduce(t, group=self.shard_info.group)
+                return float(t)
             return float(torch.linalg.norm(self._G) ** 2)      # lra.py:94-95, ||G||_F^2
         return np.linalg.norm(self.G, "fro") ** 2
 
     def __matmul__(self, other):
-        if self._on_device():
+        if self._on_device() and not self._sharded():
             o = torch.as_tensor(np.asarray(other, dtype=np.float64), device=self._G.device)
             return (self._G.T @ (self._G @ o)).cpu().numpy()
         return self.G.T @ (self.G @ other)
@@ -140,7 +157,7 @@ class PSDLowRank(AbstractPSDLowRank):
         return self._G.shape[0]
 
     def matrix(self):
-        if self._on_device():
+        if self._on_device() and not self._sharded():
             return (self._G.T @ self._G).cpu().numpy()
         return self.G.T @ self.G
 
@@ -148,7 +165,7 @@ class PSDLowRank(AbstractPSDLowRank):
         return CompactEigenvalueDecomposition.from_G(self.G, idx=self.idx, rows=self.rows)
 
     def scale(self, scaling):
-        if self._on_device():
+        if self._on_device() and not self._sharded():
             sc = torch.as_tensor(np.asarray(scaling, dtype=np.float64), device=self._G.device)
             return PSDLowRank(self._G * sc[None, :], idx=self.idx, rows=self._rows)
         return PSDLowRank(self.G * scaling[np.newaxis, :], idx=self.idx, rows=self.rows)

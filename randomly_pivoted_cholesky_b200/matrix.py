@@ -19,6 +19,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import dist as rdist
 from ._lib import COL_ALIGN, FEAT_ALIGN, KernelSpec, check
 
 
@@ -136,6 +137,7 @@ class PSDMatrix(AbstractPSDMatrix):
         self.shape = tuple(self._Ad.shape)
         self.device = dev
         self.n_pad = _round_up(self.shape[0], COL_ALIGN)
+        self.shard_info = rdist.make_shard_info(self.shape[0], 1, 0)     # a dense N x N operator is not sharded
         self._ctx = _lib.Context.get(dev.index)
 
     def _host(self):
@@ -201,22 +203,29 @@ class KernelMatrix(AbstractPSDMatrix):
     is rejected.  bandwidth may be a float, "median" or "approx_median" (matrix.py:168-176).
     """
 
-    def __init__(self, X, kernel="gaussian", bandwidth=1.0, device=None, **kwargs):
+    def __init__(self, X, kernel="gaussian", bandwidth=1.0, device=None, sharded=False, process_group=None, **kwargs):
+        """`sharded=True` (under an initialised torch.distributed NCCL group, one process per GPU): every rank
+        passes the SAME full X and keeps only its block of rows in HBM (dist.ShardInfo); the factorisation
+        drivers then run row-sharded and return the local column shard of G / rows."""
         super().__init__(**kwargs)
+        kwargs = {k: v for k, v in kwargs.items() if k != "count_queries"}
+        if not hasattr(X, "ndim") or X.ndim != 2:
+            raise RuntimeError("KernelMatrix requires an (N, d) array of points")
+        n, d = int(X.shape[0]), int(X.shape[1])
+        self.shape = (n, n)
+        self.shard_info = rdist.current_shard_info(n, process_group) if sharded else rdist.make_shard_info(n, 1, 0)
+        info = self.shard_info
+        # only this rank's block of rows crosses to the device
         if isinstance(X, torch.Tensor):
             dev = _cuda_device(device if device is not None else (X.device if X.is_cuda else None))
-            Xd = X.detach().to(dev, torch.float64)
+            Xd = X.detach()[info.lo:info.hi].to(dev, torch.float64, non_blocking=True)
             self.data = X.detach().cpu().numpy() if not X.is_cuda else None
         else:
             dev = _cuda_device(device)
             self.data = np.asarray(X)
-            Xd = torch.from_numpy(np.ascontiguousarray(self.data, dtype=np.float64)).to(dev)
-        if Xd.ndim != 2:
-            raise RuntimeError("KernelMatrix requires an (N, d) array of points")
-        n, d = Xd.shape
-        self.shape = (n, n)
+            Xd = torch.from_numpy(np.ascontiguousarray(self.data[info.lo:info.hi], dtype=np.float64)).to(dev)
         self.device = dev
-        self.n_pad = _round_up(n, COL_ALIGN)
+        self.n_pad = info.shard                       # LOCAL padded point count (== round_up(N,128) when not sharded)
         self.d = d
         self.d_pad = _round_up(d, FEAT_ALIGN)
         # point stride == 4 (mod 8) doubles: the DMMA fragment reads of a resident X tile are then bank-conflict free
@@ -248,13 +257,15 @@ class KernelMatrix(AbstractPSDMatrix):
             stab = False                                     # LaplaceKernel_mtx ignores it (kernels.py:16)
 
         Xp = torch.zeros((self.n_pad, self.ldx), dtype=torch.float64, device=dev)
-        Xp[:n, :d] = Xd
+        Xp[:info.n_loc, :d] = Xd
         self._Xd = Xp
         self._xnorm = torch.zeros((self.n_pad,), dtype=torch.float64, device=dev)
         check(self._ctx.lib.rpc_row_norms(self._ctx.handle, _stream(), _ptr(Xp), self.n_pad, self.d_pad, self.ldx,
                                           _ptr(self._xnorm)), "rpc_row_norms")
 
         if isinstance(bandwidth, str):
+            if info.world > 1:
+                raise NotImplementedError("'median' bandwidths need all pairwise distances: pass a float when sharded")
             bandwidth = self._median_bandwidth(bandwidth, kind)
         self.bandwidth = bandwidth
         self._spec = KernelSpec(kind, nu2, 1 if stab else 0, 0, float(bandwidth))
@@ -285,6 +296,9 @@ class KernelMatrix(AbstractPSDMatrix):
 
     def _cross(self, vec_i, vec_j):
         """kernel_mtx(X[vec_i], X[vec_j]) as a (len(vec_i), len(vec_j)) numpy array."""
+        if self.shard_info.world > 1:
+            raise NotImplementedError("host-side indexing A[i,j] of a sharded KernelMatrix is not supported; "
+                                      "use the factorisation drivers (device protocol) or an unsharded operator")
         n = self.shape[0]
         mi, mj = len(vec_i), len(vec_j)
         ti = torch.as_tensor(np.asarray(vec_i, dtype=np.int64), device=self.device)
@@ -325,7 +339,7 @@ class KernelMatrix(AbstractPSDMatrix):
 
     # -- device protocol ---------------------------------------------------------------------------
     def _dev_diag_into(self, diag):
-        check(self._ctx.lib.rpc_kernel_diag(self._ctx.handle, _stream(), _ptr(diag), self.shape[0], self.n_pad),
+        check(self._ctx.lib.rpc_kernel_diag(self._ctx.handle, _stream(), _ptr(diag), self.shard_info.n_loc, self.n_pad),
               "rpc_kernel_diag")
 
     def _dev_new_payload(self, m_max):
@@ -334,7 +348,7 @@ class KernelMatrix(AbstractPSDMatrix):
     def _dev_gather(self, idx_dev, m, piv):
         check(self._ctx.lib.rpc_gather_pivots(self._ctx.handle, _stream(), _ptr(idx_dev), m, _ptr(self._Xd), _ptr(self._xnorm),
                                               self.d_pad, self.ldx, _ptr(piv.X), _ptr(piv.norm), self.ldx, None, 0, 0,
-                                              None, 0), "rpc_gather_pivots")
+                                              None, 0, 0, self.shape[0]), "rpc_gather_pivots")
 
     def _dev_block_into(self, idx_dev, m, piv, H, ldh):
         check(self._ctx.lib.rpc_kernel_block(self._ctx.handle, _stream(), C.byref(self._spec), _ptr(piv.X), _ptr(piv.norm), m,

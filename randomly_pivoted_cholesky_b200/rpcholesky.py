@@ -23,6 +23,7 @@ import torch
 from . import _lib
 from ._lib import KT, check
 from .lra import PSDLowRank
+from . import dist as rdist
 from .matrix import AbstractPSDMatrix, PSDMatrix, _ptr, _round_up, _stream
 
 EPS = float(np.finfo(float).eps)
@@ -64,33 +65,53 @@ def _as_operator(A):
     raise RuntimeError("A must be an ndarray or an AbstractPSDMatrix")
 
 
+class _Payload:
+    """Views into the per-round pivot payload [X[idx] | |x|^2 | G[:c, idx]] (one flat buffer, one collective)."""
+
+    def __init__(self, X, norm):
+        self.X, self.norm = X, norm
+
+
 class _State:
-    """Device buffers of one factorisation (data layout in HBM)."""
+    """Device buffers of one factorisation (data layout in HBM).  Shard aware: every N-sized buffer
+    holds this rank's block of columns; the small replicated buffers are identical on all ranks."""
 
     def __init__(self, A, k, m_max):
         self.A = A
         self.dev = A.device
         self.ctx = A._ctx
         self.lib = self.ctx.lib
-        self.n = A.shape[0]
-        self.n_pad = A.n_pad
+        self.info = A.shard_info
+        self.n = A.shape[0]                      # global N
+        self.n_pad = A.n_pad                     # local padded column count
+        self.n_loc = self.info.n_loc
         self.k = k
         f64 = dict(dtype=torch.float64, device=self.dev)
         self.G = torch.empty((k, self.n_pad), **f64)
         self.rows = torch.empty((k, self.n_pad), **f64)
         self.diag = torch.empty((self.n_pad,), **f64)
+        self.diag_full = torch.empty((self.info.n_total_pad,), **f64) if self.info.world > 1 else self.diag
         self.m_max = m_max
         self.u_dev = torch.empty((2 * m_max,), **f64)
         self.idx_dev = torch.empty((m_max,), dtype=torch.int64, device=self.dev)
         self.sel_dev = torch.empty((m_max,), dtype=torch.int64, device=self.dev)
         self.stats = torch.zeros((4,), **f64)
-        self.piv = A._dev_new_payload(m_max)
-        self.sel = A._dev_new_payload(m_max)
-        self.P = torch.empty((max(k, 1), m_max), **f64)
+        # payload: [Xpiv (m_max x ldx) | pnorm (m_max) | P (k x m_max)] -- the used prefix is one contiguous range
+        self.ldx = getattr(A, "ldx", 0)
+        nx = m_max * self.ldx
+        self.payload = torch.zeros((nx + (m_max if self.ldx else 0) + max(k, 1) * m_max,), **f64)
+        if self.ldx:
+            self.piv = _Payload(self.payload[:nx].view(m_max, self.ldx), self.payload[nx:nx + m_max])
+            self.sel = _Payload(torch.zeros((m_max, self.ldx), **f64), torch.zeros((m_max,), **f64))
+            self.p_off = nx + m_max
+        else:
+            self.piv = self.sel = None
+            self.p_off = 0
+        self.P = self.payload[self.p_off:].view(max(k, 1), m_max)
         self.H = torch.empty((m_max, m_max), **f64)
         self.L = torch.empty((m_max, m_max), **f64)
         self.acc = torch.zeros((m_max,), dtype=torch.int32, device=self.dev)
-        self.info = torch.zeros((4,), dtype=torch.int32, device=self.dev)
+        self.info_dev = torch.zeros((4,), dtype=torch.int32, device=self.dev)
         self.k_pad_max = _round_up(k + m_max, KT)
         self.At = torch.empty((self.k_pad_max * (_round_up(m_max, AT_LD_ALIGN) + 16),), **f64)   # panel, per-round ld
         # pinned staging
@@ -110,26 +131,32 @@ class _State:
         self.u_dev[:tot].copy_(self.u_host[:tot], non_blocking=True)
 
     def sample(self, m, u_off=0):
+        """Every rank samples on the FULL residual diagonal (all-gathered when sharded): identical pivots everywhere."""
+        full = rdist.gather_diag(self.info, self.diag, self.diag_full)
         u = C.c_void_p(self.u_dev.data_ptr() + 8 * u_off)
-        check(self.lib.rpc_sample_pivots(self.ctx.handle, _stream(), _ptr(self.diag), self.n_pad, u, m, _ptr(self.idx_dev),
+        check(self.lib.rpc_sample_pivots(self.ctx.handle, _stream(), _ptr(full), full.numel(), u, m, _ptr(self.idx_dev),
                                          _ptr(self.stats)), "rpc_sample_pivots")
 
-    def gather(self, idx_dev, m, piv, c, with_P=True):
+    def gather(self, idx_dev, m, c):
+        """payload <- [X[idx] | |x|^2 | G[:c, idx]]; owners write, the others write zeros, then one sum all-reduce."""
         A = self.A
         X = getattr(A, "_Xd", None)
         xn = getattr(A, "_xnorm", None)
         d = getattr(A, "d_pad", 0)
-        ldx = getattr(A, "ldx", 0)
-        check(self.lib.rpc_gather_pivots(self.ctx.handle, _stream(), _ptr(idx_dev), m, _ptr(X), _ptr(xn), d, ldx,
+        piv = self.piv
+        check(self.lib.rpc_gather_pivots(self.ctx.handle, _stream(), _ptr(idx_dev), m, _ptr(X), _ptr(xn), d, self.ldx,
                                          _ptr(piv.X) if piv is not None else None,
-                                         _ptr(piv.norm) if piv is not None else None, ldx,
-                                         _ptr(self.G) if (with_P and c > 0) else None, self.n_pad, c if with_P else 0,
-                                         _ptr(self.P) if (with_P and c > 0) else None, self.m_max), "rpc_gather_pivots")
+                                         _ptr(piv.norm) if piv is not None else None, self.ldx,
+                                         _ptr(self.G) if c > 0 else None, self.n_pad, c,
+                                         _ptr(self.P) if c > 0 else None, self.m_max, self.info.lo, self.info.hi),
+              "rpc_gather_pivots")
+        if self.info.world > 1:
+            rdist.exchange_payload(self.info, self.payload[:self.p_off + c * self.m_max])
 
-    def residual_block(self, idx_dev, m, piv, c, count=True):
+    def residual_block(self, idx_dev, m, c, count=True):
         """H = A[idx,idx] - G[:c,idx]^T G[:c,idx]  (rpcholesky.py:189; also C of :103, which the reference
-        slices out of G_new and therefore does not count as queries)."""
-        self.A._dev_block_into(idx_dev, m, piv, self.H, self.m_max)
+        slices out of G_new and therefore does not count as queries).  Replicated on every rank."""
+        self.A._dev_block_into(idx_dev, m, self.piv, self.H, self.m_max)
         if count:
             self.A._count(m * m)
         check(self.lib.rpc_gram_residual(self.ctx.handle, _stream(), _ptr(self.P), c, m, self.m_max, _ptr(self.H),
@@ -138,11 +165,13 @@ class _State:
     def cholesky(self, m, mode, max_accept, shift, u_off):
         u = C.c_void_p(self.u_dev.data_ptr() + 8 * u_off)
         check(self.lib.rpc_rejection_cholesky(self.ctx.handle, _stream(), _ptr(self.H), m, self.m_max, u, max_accept, mode,
-                                              float(shift), _ptr(self.L), self.m_max, _ptr(self.acc), _ptr(self.info)),
+                                              float(shift), _ptr(self.L), self.m_max, _ptr(self.acc), _ptr(self.info_dev)),
               "rpc_rejection_cholesky")
 
-    def update(self, c, s, acc_dev, sel_idx_dev, sel_piv, panel_mode=0, Lmat=None):
-        """rows[c:c+s] = A[S,:]; G[c:c+s] = L^{-1}(rows - P^T G[:c]); diag update (rpcholesky.py:101-107,128-129 / 205-209)."""
+    def update(self, c, s, acc_dev, idx_dev, panel_mode=0, Lmat=None):
+        """rows[c:c+s] = A[S,:]; G[c:c+s] = L^{-1}(rows - P^T G[:c]); diag update (rpcholesky.py:101-107,128-129 /
+        205-209) on this rank's columns.  S = idx[acc] (acc None: all of idx); the selected pivot points are
+        compacted out of the (already exchanged) payload, so no further communication is needed."""
         k_pad = _round_up(c + s, KT)
         ldat = int(self.lib.rpc_panel_ld(s))          # stride that lets the kernel fetch a panel stage in one bulk copy
         Lm = self.L if Lmat is None else Lmat
@@ -150,9 +179,18 @@ class _State:
             check(self.lib.rpc_build_panel(self.ctx.handle, _stream(), _ptr(self.P), self.m_max, c, _ptr(acc_dev), s,
                                            _ptr(Lm), Lm.stride(0), panel_mode, _ptr(self.At), ldat, k_pad),
                   "rpc_build_panel")
-        rows_ptr = C.c_void_p(self.rows.data_ptr() + 8 * c * self.n_pad)
-        n, d = self.n, getattr(self.A, "d", 0)
         A = self.A
+        if acc_dev is not None:
+            accl = acc_dev[:s].to(torch.int64)
+            sel_idx = torch.index_select(idx_dev, 0, accl)
+            if self.piv is not None:
+                torch.index_select(self.piv.X, 0, accl, out=self.sel.X[:s])
+                torch.index_select(self.piv.norm, 0, accl, out=self.sel.norm[:s])
+            sel_piv = self.sel
+        else:
+            sel_idx, sel_piv = idx_dev, self.piv
+        rows_ptr = C.c_void_p(self.rows.data_ptr() + 8 * c * self.n_pad)
+        n, d = self.n_loc, getattr(A, "d", 0)
         spec = getattr(A, "_spec", None)
         if USE_FUSED and spec is not None and self.lib.rpc_fused_update_supported(C.byref(spec), s, A.ldx):
             # kernel rows evaluated and consumed in ONE pass over the column tile (fused update)
@@ -164,8 +202,8 @@ class _State:
             A._count(s * self.n)
             return
         with _timed("eval", 2.0 * s * n * d, 8.0 * n * (s + d)):
-            self.A._dev_rows_into(sel_idx_dev, s, sel_piv, rows_ptr, self.n_pad)
-        self.A._count(s * self.n)
+            A._dev_rows_into(sel_idx, s, sel_piv, rows_ptr, self.n_pad)
+        A._count(s * self.n)
         # algorithmic work of the Schur update: 2 s (c+s) N flops; reads G[:c] and rows_new, writes G_new
         with _timed("schur", 2.0 * s * (c + s) * n, 8.0 * n * (c + 2 * s + 2)):
             check(self.lib.rpc_schur_update(self.ctx.handle, _stream(), _ptr(self.G), self.n_pad, c, s, _ptr(self.At),
@@ -173,8 +211,9 @@ class _State:
                   "rpc_schur_update")
 
     def result(self, count, arr_idx):
-        n = self.n
-        return PSDLowRank(self.G[:count, :n], idx=arr_idx, rows=self.rows[:count, :n])
+        # sharded: keep the whole padded shard (equal widths on all ranks, so `.G` can all-gather); else cut to N
+        nl = self.n_pad if self.info.world > 1 else self.n_loc
+        return PSDLowRank(self.G[:count, :nl], n=self.n, idx=arr_idx, rows=self.rows[:count, :nl], shard_info=self.info)
 
 
 def _raise_if_invalid(stats_host):
@@ -199,6 +238,9 @@ def cholesky_helper(A, k, alg, stoptol=0):
     A = _as_operator(A)
     if stoptol is None:
         stoptol = 0
+    if A.shard_info.world > 1:
+        raise NotImplementedError("simple RPCholesky is not row-sharded (one pivot per step is latency bound); "
+                                  "use block or accelerated RPCholesky on a sharded operator")
     st = _State(A, k, 1)
     lib, ctx = st.lib, st.ctx
     rng = np.random.default_rng()
@@ -266,7 +308,7 @@ def block_cholesky_helper(A, k, b, alg, stoptol=1e-14, strategy="regularize", rb
         stoptol = 1e-14
     b = int(b)
     st = _State(A, k, 2 * min(b, k))
-    scale = 2.0 * float(torch.max(st.diag))                   # rpcholesky.py:72
+    scale = 2.0 * float(torch.max(rdist.gather_diag(st.info, st.diag, st.diag_full)))   # rpcholesky.py:72
     rng = np.random.default_rng()
     arr_idx = []
     counter = 0
@@ -290,11 +332,11 @@ def block_cholesky_helper(A, k, b, alg, stoptol=1e-14, strategy="regularize", rb
         arr_idx.extend(idx)
         st.sel_host[:block_size] = torch.from_numpy(idx)
         st.sel_dev[:block_size].copy_(st.sel_host[:block_size], non_blocking=True)
-        st.gather(st.sel_dev, block_size, st.sel, counter)
-        st.residual_block(st.sel_dev, block_size, st.sel, counter, count=False)   # C of :103
+        st.gather(st.sel_dev, block_size, counter)
+        st.residual_block(st.sel_dev, block_size, counter, count=False)       # C of :103
         Hcopy = st.H[:block_size, :block_size].clone()
         st.cholesky(block_size, 1, block_size, EPS * b * scale, 0)            # :106
-        info = st.info.cpu().numpy()
+        info = st.info_dev.cpu().numpy()
         if info[1] != 0:                                                       # :109-114
             warn("Cholesky failed in block partial Cholesky. Falling back to eigendecomposition")
             evals, evecs = torch.linalg.eigh(Hcopy)
@@ -302,9 +344,9 @@ def block_cholesky_helper(A, k, b, alg, stoptol=1e-14, strategy="regularize", rb
             scal = torch.where(pos, evals.clamp_min(1e-300) ** -0.5, torch.zeros_like(evals))
             scal = torch.where(evals < 0, torch.zeros_like(evals), scal)
             T = (scal[:, None] * evecs.T).contiguous()
-            st.update(counter, block_size, None, st.sel_dev, st.sel, panel_mode=1, Lmat=T)
+            st.update(counter, block_size, None, st.sel_dev, panel_mode=1, Lmat=T)
         else:
-            st.update(counter, block_size, None, st.sel_dev, st.sel)
+            st.update(counter, block_size, None, st.sel_dev)
         counter += block_size
     else:
         if stoptol > 0:
@@ -344,11 +386,11 @@ def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
         with _timed("sample", 0.0, 16.0 * st.n):
             st.sample(b)
         with _timed("gram", 2.0 * b * b * counter, 8.0 * counter * b):
-            st.gather(st.idx_dev, b, st.piv, counter)
-            st.residual_block(st.idx_dev, b, st.piv, counter)      # :189
+            st.gather(st.idx_dev, b, counter)
+            st.residual_block(st.idx_dev, b, counter)              # :189
         with _timed("reject", b ** 3 / 3.0, 8.0 * b * b):
             st.cholesky(b, 0, k - counter, 0.0, b)                 # :190 + truncation :193-196
-        host = torch.cat([st.stats, st.info.to(torch.float64), st.acc[:b].to(torch.float64),
+        host = torch.cat([st.stats, st.info_dev.to(torch.float64), st.acc[:b].to(torch.float64),
                           st.idx_dev[:b].to(torch.float64)]).cpu().numpy()          # the round's only sync
         stats_host, info = host[:4], host[4:8].astype(np.int64)
         _raise_if_invalid(stats_host)
@@ -367,10 +409,7 @@ def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
         arr_idx[counter:counter + num_sel] = idx
         t1 = time.perf_counter()
         if num_sel > 0:
-            st.sel_host[:num_sel] = torch.from_numpy(idx)
-            st.sel_dev[:num_sel].copy_(st.sel_host[:num_sel], non_blocking=True)
-            st.gather(st.sel_dev, num_sel, st.sel, 0, with_P=False)
-            st.update(counter, num_sel, st.acc, st.sel_dev, st.sel)
+            st.update(counter, num_sel, st.acc, st.idx_dev)
         counter += num_sel
         rounds.append(num_sel)
         if auto_b:                                             # :211-220, on device-synchronised wall time
