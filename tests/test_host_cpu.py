@@ -1,0 +1,108 @@
+"""CPU-only tests of the host side: the C-ABI library loads and exports every symbol declared in
+include/rpc_b200.h, the PSDLowRank container keeps the reference's semantics (modelled on the reference's
+tests/test_lra.py), the operator classes refuse to compute without a GPU, and bench.py's reference arm runs."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from randomly_pivoted_cholesky_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "rpc_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(rpc_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    path = _lib.build()                      # nvcc cross-compiles without a GPU; no-op when up to date
+    lib = ctypes.CDLL(path)
+    for name in sorted(declared):
+        assert hasattr(lib, name), "include/rpc_b200.h declares %s but librpc_b200.so does not export it" % name
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    loaded = _lib.load()
+    assert loaded.rpc_abi_version() == 1     # no device needed
+    assert loaded.rpc_panel_ld(200) % 16 == 4 and loaded.rpc_panel_ld(200) >= 200
+    assert loaded.rpc_last_error() is not None
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import randomly_pivoted_cholesky_b200 as rpc
+    with pytest.raises(RuntimeError):
+        rpc.KernelMatrix(np.zeros((8, 2)))
+    with pytest.raises(RuntimeError):
+        rpc.rpcholesky(np.eye(4), 2)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "randomly_pivoted_cholesky_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "rpc_oracle" not in src and "import oracle" not in src and "from oracle" not in src, f
+
+
+@pytest.fixture
+def lowrank_case():
+    rng = np.random.default_rng(42)
+    N, r = 50, 10
+    G = rng.standard_normal((r, N))
+    return rng, N, r, G, G.T @ G
+
+
+def test_psdlowrank_container(lowrank_case):
+    from randomly_pivoted_cholesky_b200 import CompactEigenvalueDecomposition, PSDLowRank
+    rng, N, r, G, A = lowrank_case
+    obj = PSDLowRank(G)
+    assert obj.shape == (N, N) and obj.rank() == r
+    assert obj.trace() == pytest.approx(np.linalg.norm(G, "fro") ** 2)
+    x = rng.standard_normal((N, 5))
+    np.testing.assert_allclose(obj @ x, A @ x)
+    np.testing.assert_allclose(obj.matrix(), A)
+    ced = obj.eigenvalue_decomposition()
+    assert isinstance(ced, CompactEigenvalueDecomposition)
+    np.testing.assert_allclose(ced.matrix(), A, atol=1e-10)
+    assert ced.trace() == pytest.approx(np.trace(A))
+    b = rng.standard_normal(N)
+    np.testing.assert_allclose(ced.krr(b, 0.1), np.linalg.solve(A + 0.1 * np.eye(N), b), atol=1e-5)
+    scaling = np.ones(N) * 2.0
+    Gs = G * scaling[None, :]
+    np.testing.assert_allclose(obj.scale(scaling).matrix(), Gs.T @ Gs)
+    np.testing.assert_array_equal(obj.get_left_factor(), G.T)
+    np.testing.assert_array_equal(obj.get_right_factor(), G)
+
+
+def test_psdlowrank_metadata(lowrank_case):
+    from randomly_pivoted_cholesky_b200 import PSDLowRank
+    _, N, r, G, A = lowrank_case
+    obj = PSDLowRank(G)
+    with pytest.raises(RuntimeError):
+        obj.get_indices()
+    with pytest.raises(RuntimeError):
+        obj.get_rows()
+    idx = list(range(r))
+    obj = PSDLowRank(G, idx=idx, rows=A[idx, :])
+    assert obj.get_indices() == idx
+    np.testing.assert_array_equal(obj.get_rows(), A[idx, :])
+    assert obj.G is G and obj.G_device is None and obj.rows_device is None
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["unit"] == "entries/s"
