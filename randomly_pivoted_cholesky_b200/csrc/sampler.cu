@@ -127,106 +127,197 @@ __global__ void __launch_bounds__(SC_WARPS * 32) sc_classify(const double *__res
     }
 }
 
-// 4. the walk: exact running sum before every chunk.  One warp; 32 chunk descriptors per step.
-// A run of regular chunks of ONE binade is folded with a warp prefix sum: all its D are multiples of
-// the same ulp q and their total is below 2^52 q, so the shuffled additions are exact in any order and
-// carry + prefix reproduces the sequential running sum bit for bit.  Chunks that need a replay
-// (cls == INT_MIN) are added element by element by lane 0.
+// 4. the walk: exact running sum before every chunk.  One CTA.
+// A run of regular chunks of ONE binade is folded with a prefix sum: all its D are multiples of the same ulp q and
+// their total is below 2^52 q, so the additions are exact in any order and carry + prefix reproduces the sequential
+// running sum bit for bit.
+//   phase A (all warps): per tile of 32 chunks, is it "clean" (32 regular chunks of one binade)?  If so its
+//            within-tile exclusive prefix and total are computed with warp shuffles.
+//   phase B (warp 0): carries across tiles -- one exact add per clean tile; dirty tiles (mixed binades, chunks
+//            that need a replay) are resolved run by run, the chunks marked INT_MIN with real sequential adds at
+//            8-element granularity.
+//   phase C (all warps): cstart = tile carry + within-tile prefix for the clean tiles.
+constexpr int SW_THREADS = 1024;
+
 template <bool DIV>
-__global__ void __launch_bounds__(32) sc_walk(const double *__restrict__ d, int64_t n, const double *Sptr,
-                                              const double *__restrict__ D, const int32_t *__restrict__ cls, int nch,
-                                              double *__restrict__ cstart, int32_t *__restrict__ bad) {
-    const int lane = threadIdx.x;
+__device__ __forceinline__ double walk_dirty_tile(const double *__restrict__ d, int64_t n, double S, int k0, int nch, int e,
+                                                  double Dk, double carry, double *__restrict__ cstart, int lane,
+                                                  int &violated, const double *xs) {
     const unsigned full = 0xffffffffu;
-    const double S = DIV ? *Sptr : 1.0;
-    double carry = 0.0;                              // identical in all lanes
-    int violated = 0;
-    for (int k0 = 0; k0 < nch; k0 += 32) {
-        const int k = k0 + lane;
-        const bool live = k < nch;
-        const int e = live ? cls[k] : INT_MIN + 1;   // INT_MIN + 1: past the end, never matches a binade
-        const double Dk = live ? D[k] : 0.0;
-        int pos = 0;
-        const int kend = min(32, nch - k0);
-        while (pos < kend) {
-            const int e0 = __shfl_sync(full, e, pos);
-            if (e0 == INT_MIN) {
-                // Chunk k0+pos could not be classified a priori (binade crossing, rounding tie, start of the
-                // array).  Now the EXACT carry is known, so the same argument is applied at a finer grain: lane l
-                // owns 8 consecutive elements; all lanes up to the first one that crosses the binade of the
-                // carry (or holds a tie) are folded in bulk, that lane's 8 elements are added one by one, repeat.
-                const int64_t base = (int64_t)(k0 + pos) * SC_CH + lane * 8;
-                double x[8];
+    const int k = k0 + lane;
+    int pos = 0;
+    const int kend = min(32, nch - k0);
+    while (pos < kend) {
+        const int e0 = __shfl_sync(full, e, pos);
+        if (e0 == INT_MIN) {
+            // Chunk k0+pos could not be classified a priori (binade crossing, rounding tie, start of the array).
+            // Now the EXACT carry is known, so the same argument is applied at a finer grain: lane l owns 8
+            // consecutive elements; all lanes up to the first one that crosses the binade of the carry (or holds a
+            // tie) are folded in bulk, that lane's 8 elements are added one by one, repeat.
+            const int64_t base = (int64_t)(k0 + pos) * SC_CH + lane * 8;
+            // phase A staged the chunk's elements in shared memory (slot id parked in the unused D entry)
+            const int slot = (int)(-__shfl_sync(full, Dk, pos)) - 1;
+            double x[8];
+            if (slot >= 0) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) x[t] = xs[slot * SC_CH + t * 32 + lane];
+            } else {
 #pragma unroll
                 for (int t = 0; t < 8; ++t) x[t] = (base + t) < n ? elem<DIV>(d, base + t, S) : 0.0;
-                if (lane == 0) cstart[k0 + pos] = carry;
-                int lpos = 0;
-                while (lpos < 32) {
-                    const int e = carry > 0.0 ? ilogb(carry) : INT_MIN;
-                    int f = lpos;                                  // first lane that needs the sequential treatment
-                    if (e >= -960 && e <= 1000) {
-                        const double scale = pow2d(52 - e), q = pow2d(e - 52), top = pow2d(e + 1);
-                        double A = 0.0;
-                        bool tie = false;
-                        if (lane >= lpos) {
+            }
+            if (lane == 0) cstart[k0 + pos] = carry;
+            int lpos = 0;
+            while (lpos < 32) {
+                const int eb = carry > 0.0 ? ilogb(carry) : INT_MIN;
+                int f = lpos;                                  // first lane that needs the sequential treatment
+                if (eb >= -960 && eb <= 1000) {
+                    const double scale = pow2d(52 - eb), q = pow2d(eb - 52), top = pow2d(eb + 1);
+                    double A = 0.0;
+                    bool tie = false;
+                    if (lane >= lpos) {
 #pragma unroll
-                            for (int t = 0; t < 8; ++t) {
-                                double v = x[t] * scale;
-                                double kf = floor(v);
-                                double fr = v - kf;
-                                tie |= (fr == 0.5);
-                                A += kf + (fr > 0.5 ? 1.0 : 0.0);
-                            }
-                        }
-                        double pre = A;                            // inclusive prefix over lanes >= lpos (exact integers)
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            double t2 = __shfl_up_sync(full, pre, o);
-                            if (lane >= o) pre += t2;
-                        }
-                        // lanes below lpos contributed 0, so `pre` is already the prefix over [lpos, lane]
-                        const bool bad = lane >= lpos && (tie || !isfinite(pre) || !(carry + pre * q < top));
-                        const unsigned badmask = __ballot_sync(full, bad);
-                        f = badmask ? __ffs(badmask) - 1 : 32;
-                        if (f > lpos) {
-                            const double upto = __shfl_sync(full, pre, f - 1);
-                            carry += upto * q;                     // exact: all terms are multiples of q below 2^53 q
+                        for (int t = 0; t < 8; ++t) {
+                            double v = x[t] * scale;
+                            double kf = floor(v);
+                            double fr = v - kf;
+                            tie |= (fr == 0.5);
+                            A += kf + (fr > 0.5 ? 1.0 : 0.0);
                         }
                     }
-                    if (f < 32) {
+                    double pre = A;                            // inclusive prefix over lanes >= lpos (exact integers)
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) carry += __shfl_sync(full, x[t], f);   // the real sequential adds
-                        lpos = f + 1;
-                    } else {
-                        lpos = 32;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        double t2 = __shfl_up_sync(full, pre, o);
+                        if (lane >= o) pre += t2;
+                    }
+                    const bool bad = lane >= lpos && (tie || !isfinite(pre) || !(carry + pre * q < top));
+                    const unsigned badmask = __ballot_sync(full, bad);
+                    f = badmask ? __ffs(badmask) - 1 : 32;
+                    if (f > lpos) {
+                        const double upto = __shfl_sync(full, pre, f - 1);
+                        carry += upto * q;                     // exact: all terms are multiples of q below 2^53 q
                     }
                 }
-                ++pos;
-                continue;
-            }
-            // maximal run [pos, end) of chunks with binade e0
-            const unsigned same = __ballot_sync(full, e == e0);
-            const unsigned from = same >> pos;                        // bit i <-> lane pos+i
-            const int len = (~from == 0u) ? 32 - pos : __ffs(~from) - 1;
-            const int end = pos + len;
-            const bool in_run = lane >= pos && lane < end;
-            double v = in_run ? Dk : 0.0;
-            // inclusive warp prefix sum (exact: see above)
+                if (f < 32) {
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                double t = __shfl_up_sync(full, v, o);
-                if (lane >= o) v += t;
+                    for (int t = 0; t < 8; ++t) carry += __shfl_sync(full, x[t], f);   // the real sequential adds
+                    lpos = f + 1;
+                } else {
+                    lpos = 32;
+                }
             }
-            const double total = __shfl_sync(full, v, 31);
-            if (in_run) cstart[k] = carry + (v - Dk);                  // exclusive prefix, exact
-            if (ilogb(carry) != e0 || !(carry + total <= pow2d(e0 + 1))) violated = 1;
-            carry += total;                                            // exact
-            pos = end;
+            ++pos;
+            continue;
+        }
+        // maximal run [pos, end) of chunks with binade e0
+        const unsigned same = __ballot_sync(full, e == e0);
+        const unsigned from = same >> pos;                        // bit i <-> lane pos+i
+        const int len = (~from == 0u) ? 32 - pos : __ffs(~from) - 1;
+        const int end = pos + len;
+        const bool in_run = lane >= pos && lane < end;
+        double v = in_run ? Dk : 0.0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double t = __shfl_up_sync(full, v, o);
+            if (lane >= o) v += t;
+        }
+        const double total = __shfl_sync(full, v, 31);
+        if (in_run) cstart[k] = carry + (v - Dk);                  // exclusive prefix, exact
+        if (ilogb(carry) != e0 || !(carry + total <= pow2d(e0 + 1))) violated = 1;
+        carry += total;                                            // exact
+        pos = end;
+    }
+    return carry;
+}
+
+constexpr int SW_SLOTS = 64;      // replay chunks staged in shared memory (64 x 2 KB); more fall back to global loads
+
+template <bool DIV>
+__global__ void __launch_bounds__(SW_THREADS) sc_walk(const double *__restrict__ d, int64_t n, const double *Sptr,
+                                                      double *__restrict__ D, const int32_t *__restrict__ cls, int nch,
+                                                      double *__restrict__ cstart, double *__restrict__ tile_tot,
+                                                      double *__restrict__ tile_carry, int32_t *__restrict__ tile_e,
+                                                      int32_t *__restrict__ bad) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned full = 0xffffffffu;
+    const double S = DIV ? *Sptr : 1.0;
+    const int ntile = (nch + 31) / 32;
+    constexpr int NW = SW_THREADS / 32;
+    extern __shared__ double xs[];                               // [SW_SLOTS][SC_CH], element (lane*8+t) at [t*32+lane]
+    __shared__ int nslots;
+    if (threadIdx.x == 0) nslots = 0;
+    __syncthreads();
+
+    // ---- phase A
+    for (int t = warp; t < ntile; t += NW) {
+        const int k = t * 32 + lane;
+        const bool live = k < nch;
+        const int e = live ? cls[k] : INT_MIN + 1;
+        double Dk = live ? D[k] : 0.0;
+        // stage the elements of the chunks that phase B has to replay (keeps global latency off the serial path)
+        unsigned dirty = __ballot_sync(full, e == INT_MIN);
+        while (dirty) {
+            const int src = __ffs(dirty) - 1;
+            dirty &= dirty - 1;
+            int slot = 0;
+            if (lane == 0) slot = atomicAdd(&nslots, 1);
+            slot = __shfl_sync(full, slot, 0);
+            if (slot < SW_SLOTS) {
+                const int64_t base = (int64_t)(t * 32 + src) * SC_CH + lane * 8;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) xs[slot * SC_CH + q * 32 + lane] = (base + q) < n ? elem<DIV>(d, base + q, S) : 0.0;
+                if (lane == src) D[k] = -(double)(slot + 1);
+            }
+        }
+        const int e0 = __shfl_sync(full, e, 0);
+        const bool clean = __all_sync(full, e == e0) && e0 != INT_MIN && e0 != INT_MIN + 1;   // a full tile, one binade
+        double v = Dk;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double t2 = __shfl_up_sync(full, v, o);
+            if (lane >= o) v += t2;
+        }
+        if (clean) cstart[k] = v - Dk;                           // within-tile exclusive prefix (exact)
+        if (lane == 31) { tile_tot[t] = v; tile_e[t] = clean ? e0 : INT_MIN; }
+    }
+    __syncthreads();
+
+    // ---- phase B
+    if (warp == 0) {
+        double carry = 0.0;                                      // identical in all lanes
+        int violated = 0;
+        for (int t0 = 0; t0 < ntile; t0 += 32) {
+            const int tl = t0 + lane;
+            const int te = tl < ntile ? tile_e[tl] : INT_MIN;
+            const double tt = tl < ntile ? tile_tot[tl] : 0.0;
+            const int tend = min(32, ntile - t0);
+            for (int q = 0; q < tend; ++q) {
+                const int e0 = __shfl_sync(full, te, q);
+                const double tot = __shfl_sync(full, tt, q);
+                if (lane == 0) tile_carry[t0 + q] = carry;
+                if (e0 != INT_MIN) {
+                    if (ilogb(carry) != e0 || !(carry + tot <= pow2d(e0 + 1))) violated = 1;
+                    carry += tot;                                // exact
+                } else {
+                    const int k0 = (t0 + q) * 32, k = k0 + lane;
+                    const bool live = k < nch;
+                    carry = walk_dirty_tile<DIV>(d, n, S, k0, nch, live ? cls[k] : INT_MIN + 1, live ? D[k] : 0.0, carry, cstart,
+                                                 lane, violated, xs);
+                }
+            }
+        }
+        if (lane == 0) {
+            cstart[nch] = carry;
+            if (violated) atomicExch(bad, 2);
         }
     }
-    if (lane == 0) {
-        cstart[nch] = carry;
-        if (violated) atomicExch(bad, 2);
+    __syncthreads();
+
+    // ---- phase C
+    for (int t = warp; t < ntile; t += NW) {
+        if (tile_e[t] == INT_MIN) continue;
+        const int k = t * 32 + lane;
+        cstart[k] = tile_carry[t] + cstart[k];                   // exact (carry and prefix are multiples of q)
     }
 }
 
@@ -283,15 +374,24 @@ extern "C" int rpc_sample_pivots(rpc_ctx *ctx, void *stream, const double *diag,
     RPC_CHECK_ARG(m == 0 || (u && idx), "uniforms and idx required when m > 0");
     cudaStream_t st = (cudaStream_t)stream;
     const int nch = (int)((n_pad + SC_CH - 1) / SC_CH);
-    // workspace layout (doubles): csum[nch+1] | D[nch] | cstartA[nch+1] | cstartB[nch+1] ; ints: cls[nch] | bad[2]
-    size_t nd = (size_t)4 * (nch + 2);
+    // workspace layout (doubles): csum[nch+1] | D[nch] | cstartA[nch+1] | cstartB[nch+1] | tile_tot | tile_carry ;
+    // ints: cls[nch] | bad[2] | tile_e
+    const int ntile = (nch + 31) / 32;
+    size_t nd = (size_t)4 * (nch + 2) + 2 * (size_t)(ntile + 2);
     int rc = rpc_ws_reserve(ctx, nd * sizeof(double));
     if (rc) return rc;
-    rc = rpc_flags_reserve(ctx, (size_t)(nch + 8) * sizeof(int32_t));
+    rc = rpc_flags_reserve(ctx, (size_t)(nch + ntile + 16) * sizeof(int32_t));
     if (rc) return rc;
     double *csum = ctx->ws, *D = csum + (nch + 2), *cA = D + (nch + 2), *cB = cA + (nch + 2);
-    int32_t *cls = ctx->flags, *bad = ctx->flags + nch;
+    double *tile_tot = cB + (nch + 2), *tile_carry = tile_tot + (ntile + 2);
+    int32_t *cls = ctx->flags, *bad = ctx->flags + nch, *tile_e = ctx->flags + nch + 8;
     RPC_CUDA(cudaMemsetAsync(bad, 0, 2 * sizeof(int32_t), st));
+    static bool configured = false;
+    if (!configured) {
+        RPC_CUDA(cudaFuncSetAttribute(sc_walk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SLOTS * SC_CH * 8));
+        RPC_CUDA(cudaFuncSetAttribute(sc_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SLOTS * SC_CH * 8));
+        configured = true;
+    }
     const double delta = ((double)n_pad + 256.0) * 1.1102230246251565e-16 * 1.01;
     const unsigned grid = (unsigned)((nch + SC_WARPS - 1) / SC_WARPS);
     const double *Sptr = cA + nch;     // exact python sum(diags)
@@ -302,7 +402,7 @@ extern "C" int rpc_sample_pivots(rpc_ctx *ctx, void *stream, const double *diag,
     RPC_LAUNCHED(ctx);
     sc_classify<false><<<grid, SC_WARPS * 32, 0, st>>>(diag, n_pad, nullptr, csum, delta, D, cls);
     RPC_LAUNCHED(ctx);
-    sc_walk<false><<<1, 32, 0, st>>>(diag, n_pad, nullptr, D, cls, nch, cA, bad);
+    sc_walk<false><<<1, SW_THREADS, SW_SLOTS * SC_CH * sizeof(double), st>>>(diag, n_pad, nullptr, D, cls, nch, cA, tile_tot, tile_carry, tile_e, bad);
     RPC_LAUNCHED(ctx);
 
     sc_chunk_sums<true><<<grid, SC_WARPS * 32, 0, st>>>(diag, n_pad, Sptr, csum, bad);
@@ -311,7 +411,7 @@ extern "C" int rpc_sample_pivots(rpc_ctx *ctx, void *stream, const double *diag,
     RPC_LAUNCHED(ctx);
     sc_classify<true><<<grid, SC_WARPS * 32, 0, st>>>(diag, n_pad, Sptr, csum, delta, D, cls);
     RPC_LAUNCHED(ctx);
-    sc_walk<true><<<1, 32, 0, st>>>(diag, n_pad, Sptr, D, cls, nch, cB, bad);
+    sc_walk<true><<<1, SW_THREADS, SW_SLOTS * SC_CH * sizeof(double), st>>>(diag, n_pad, Sptr, D, cls, nch, cB, tile_tot, tile_carry, tile_e, bad);
     RPC_LAUNCHED(ctx);
     if (m > 0) {
         sc_locate<<<m, 32, 0, st>>>(diag, n_pad, Sptr, cB, nch, u, idx);

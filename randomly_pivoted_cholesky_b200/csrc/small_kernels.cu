@@ -244,13 +244,22 @@ extern "C" int rpc_gram_residual(rpc_ctx *ctx, void *stream, const double *P, in
 // rejection_cholesky (rpcholesky.py:140-157) / shifted Cholesky (rpcholesky.py:106): ONE CTA, the
 // lower triangle of H packed in shared memory when it fits (m <= 232), right-looking.
 // ------------------------------------------------------------------------------------------------
-constexpr int RC_THREADS = 1024;
-constexpr int RC_SMEM_MAX_M = 228;
+constexpr int RC_THREADS = 512;
+constexpr int RC_SMEM_MAX_M = 224;
 
 template <bool PACKED>
 __device__ __forceinline__ size_t tri_at(int i, int l, int64_t ld) {
     return PACKED ? (size_t)i * (i + 1) / 2 + l : (size_t)i * ld + l;
 }
+
+// Blocked right-looking formulation, RB columns at a time:
+//   step 1 (warp 0): the RB x RB diagonal block is eliminated in registers, lane r holding row r: the b sequential
+//           accept tests u_j H0[j,j] < H[j,j] (rpcholesky.py:151), sqrt and column scaling never touch a barrier;
+//   step 2 (all threads): rows below the block get their entries of the accepted columns by a tiny forward
+//           substitution against the block;
+//   step 3 (all warps): ONE rank-(#accepted) update of the trailing lower triangle.
+// Three barriers per RB columns instead of two per column, and RB FMAs per trailing-matrix access.
+constexpr int RB = 8;
 
 template <bool PACKED>
 __global__ void __launch_bounds__(RC_THREADS, 1) rejection_cholesky_kernel(double *__restrict__ H, int m, int64_t ldh,
@@ -259,13 +268,16 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rejection_cholesky_kernel(doubl
                                                                           double *__restrict__ L, int64_t ldl,
                                                                           int32_t *__restrict__ acc, int32_t *__restrict__ info) {
     extern __shared__ double sh[];
-    double *lcol = sh;                 // [m]
-    double *u0 = sh + m;               // [m] u[j] * original diagonal: the acceptance threshold of step j
-    int32_t *accpos = (int32_t *)(sh + 2 * m);   // [m]
-    double *T = PACKED ? sh + 3 * m : H;
+    double *thr = sh;                                  // [m] u[j] * original diagonal: acceptance threshold of step j
+    double *Lb = sh + m;                               // [RB][m] entries of the block's accepted columns, all rows
+    int32_t *accpos = (int32_t *)(sh + m + RB * m);    // [m] accepted positions so far
+    int32_t *blk = accpos + m;                         // [0] #accepted in the block, [1] stop flag, [2..2+RB) their columns
+    double *rpiv = sh + m + RB * m + (m + 16) / 2 + 8; // [RB] 1/sqrt(pivot) of the block's accepted columns
+    double *T = PACKED ? rpiv + RB : H;
     const int64_t ld = ldh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = RC_THREADS / 32;
+    const unsigned full = 0xffffffffu;
 
     if (PACKED) {
         for (int i = warp; i < m; i += NW)
@@ -276,14 +288,13 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rejection_cholesky_kernel(doubl
         double tr = 0.0;
         for (int j = lane; j < m; j += 32) tr += H[(int64_t)j * ldh + j];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, o);
+        for (int o = 16; o > 0; o >>= 1) tr += __shfl_xor_sync(full, tr, o);
         if (lane == 0) {
             info[2] = (mode == 0 && !(tr > 0.0)) ? 1 : 0;
             info[1] = 0;
         }
     }
-    // rpcholesky.py:151 compares np.random.rand() * H0[j,j] with the residual H[j,j]; keep the product at hand
-    for (int j = tid; j < m; j += RC_THREADS) u0[j] = (mode == 0 ? u[j] : 0.0) * H[(int64_t)j * ldh + j];
+    for (int j = tid; j < m; j += RC_THREADS) thr[j] = (mode == 0 ? u[j] : 0.0) * H[(int64_t)j * ldh + j];
     __syncthreads();
     if (mode == 1 && shift != 0.0) {
         for (int j = tid; j < m; j += RC_THREADS) T[tri_at<PACKED>(j, j, ld)] += shift;
@@ -291,38 +302,120 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rejection_cholesky_kernel(doubl
     __syncthreads();
 
     int nacc = 0;
-    for (int j = 0; j < m; ++j) {
-        const double hjj = T[tri_at<PACKED>(j, j, ld)];
-        bool accept;
-        if (mode == 1) {
-            if (!(hjj > 0.0)) {               // numpy.linalg.cholesky would raise LinAlgError
-                if (tid == 0) info[1] = j + 1;
-                break;
+    for (int j0 = 0; j0 < m; j0 += RB) {
+        const int nb = min(RB, m - j0);
+        // ---- step 1: eliminate the diagonal block in registers (warp 0; lane r < nb holds row j0 + r)
+        if (warp == 0) {
+            const int r = lane;
+            double drow[RB], lrow[RB];
+#pragma unroll
+            for (int cc = 0; cc < RB; ++cc) {
+                drow[cc] = (r < nb && cc <= r) ? T[tri_at<PACKED>(j0 + r, j0 + cc, ld)] : 0.0;
+                lrow[cc] = 0.0;
             }
-            accept = true;
-        } else {
-            accept = u0[j] < hjj;             // rpcholesky.py:151 (u0[j] = u_j * H0[j,j])
-        }
-        if (!accept) continue;
-        if (nacc == max_accept) break;        // truncation of rpcholesky.py:193-196
-        const double piv = sqrt(hjj);
-        for (int i = j + tid; i < m; i += RC_THREADS) {
-            double v = T[tri_at<PACKED>(i, j, ld)] / piv;
-            lcol[i] = v;
-            Lfull[(size_t)i * m + nacc] = v;
-        }
-        if (tid == 0) accpos[nacc] = j;
-        ++nacc;
-        __syncthreads();
-        // trailing update of the lower triangle: T[i,l] -= l_i l_l, j < l <= i
-        for (int i = j + 1 + warp; i < m; i += NW) {
-            const double li = lcol[i];
-            for (int l = j + 1 + lane; l <= i; l += 32) {
-                size_t a = tri_at<PACKED>(i, l, ld);
-                T[a] = T[a] - li * lcol[l];
+            int na = 0, stop = 0, cols[RB];
+            double rinvs[RB];
+#pragma unroll
+            for (int jj = 0; jj < RB; ++jj) {
+                if (jj < nb && !stop) {                                   // warp-uniform
+                    const double hjj = __shfl_sync(full, drow[jj], jj);
+                    bool accept;
+                    if (mode == 1) {
+                        accept = true;
+                        if (!(hjj > 0.0)) {                               // numpy.linalg.cholesky would raise LinAlgError
+                            if (lane == 0) info[1] = j0 + jj + 1;
+                            stop = 1;
+                            accept = false;
+                        }
+                    } else {
+                        accept = thr[j0 + jj] < hjj;                      // rpcholesky.py:151
+                    }
+                    if (accept && nacc + na == max_accept) { stop = 1; accept = false; }   // truncation, :193-196
+                    if (accept) {
+                        // L[:,j] = H[:,j] / sqrt(H[j,j]) as a multiplication by rsqrt (1-2 ulp from the division;
+                        // sqrt + divide are ~300 dependent cycles on the one serial chain of the whole factorisation)
+                        const double rinv = rsqrt(hjj);
+                        const double lv = (r >= jj && r < nb) ? (r == jj ? hjj * rinv : drow[jj] * rinv) : 0.0;
+#pragma unroll
+                        for (int cc = jj + 1; cc < RB; ++cc) {
+                            const double lcc = __shfl_sync(full, lv, cc);
+                            if (cc <= r) drow[cc] = drow[cc] - lv * lcc;
+                        }
+#pragma unroll
+                        for (int a = 0; a < RB; ++a) if (a == na) { lrow[a] = lv; cols[a] = j0 + jj; rinvs[a] = rinv; }
+                        ++na;
+                    }
+                }
+            }
+            if (r < nb) {
+#pragma unroll
+                for (int a = 0; a < RB; ++a)
+                    if (a < na) {
+                        Lb[a * m + j0 + r] = lrow[a];
+                        Lfull[(size_t)(j0 + r) * m + nacc + a] = lrow[a];
+                    }
+            }
+            if (lane == 0) {
+                blk[0] = na;
+                blk[1] = stop;
+#pragma unroll
+                for (int a = 0; a < RB; ++a) if (a < na) { blk[2 + a] = cols[a]; accpos[nacc + a] = cols[a]; rpiv[a] = rinvs[a]; }
             }
         }
         __syncthreads();
+        const int na = blk[0];
+        const int stop = blk[1];
+        if (na > 0 && !stop) {
+            // ---- step 2: rows below the block, one thread per row: l[a] = (T[i, col_a] - sum_{a'<a} l[a'] L[col_a, a']) / L[col_a, a]
+            for (int i = j0 + nb + tid; i < m; i += RC_THREADS) {
+                double l[RB];
+#pragma unroll
+                for (int a = 0; a < RB; ++a) {
+                    l[a] = 0.0;
+                    if (a < na) {
+                        const int ca = blk[2 + a];
+                        double v = T[tri_at<PACKED>(i, ca, ld)];
+#pragma unroll
+                        for (int a2 = 0; a2 < RB; ++a2)
+                            if (a2 < a) v = v - l[a2] * Lb[a2 * m + ca];
+                        l[a] = v * rpiv[a];
+                        Lb[a * m + i] = l[a];
+                        Lfull[(size_t)i * m + nacc + a] = l[a];
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- step 3: trailing lower triangle T[i,l] -= sum_a L[i,a] L[l,a], j0+nb <= l <= i; a warp takes two
+            // rows at a time (two independent FMA chains per L[l,a] load)
+            for (int i = j0 + nb + 2 * warp; i < m; i += 2 * NW) {
+                const bool two = i + 1 < m;
+                double li0[RB], li1[RB];
+#pragma unroll
+                for (int a = 0; a < RB; ++a) {
+                    li0[a] = a < na ? Lb[a * m + i] : 0.0;
+                    li1[a] = (a < na && two) ? Lb[a * m + i + 1] : 0.0;
+                }
+                const int lmax = two ? i + 1 : i;
+                for (int l = j0 + nb + lane; l <= lmax; l += 32) {
+                    const bool in0 = l <= i, in1 = two;            // row i+1 holds columns up to i+1
+                    const size_t at0 = tri_at<PACKED>(i, in0 ? l : i, ld);
+                    const size_t at1 = tri_at<PACKED>(two ? i + 1 : i, l <= i + 1 ? l : i, ld);
+                    double t0 = in0 ? T[at0] : 0.0, t1 = in1 ? T[at1] : 0.0;
+#pragma unroll
+                    for (int a = 0; a < RB; ++a)
+                        if (a < na) {
+                            const double lb = Lb[a * m + l];
+                            t0 = t0 - li0[a] * lb;
+                            t1 = t1 - li1[a] * lb;
+                        }
+                    if (in0) T[at0] = t0;
+                    if (in1) T[at1] = t1;
+                }
+            }
+        }
+        nacc += na;
+        __syncthreads();
+        if (stop) break;
     }
     __syncthreads();
     // L = Lfull[acc, acc] (rpcholesky.py:155-156)
@@ -351,12 +444,14 @@ extern "C" int rpc_rejection_cholesky(rpc_ctx *ctx, void *stream, double *H, int
                                       220 * 1024));
         configured = true;
     }
+    // thr[m] | Lb[RB][m] | accpos[m] + blk ints | (packed lower triangle)
+    const size_t head = ((size_t)m + RB * m + (m + 16) / 2 + 8 + RB) * sizeof(double);
     if (m <= RC_SMEM_MAX_M) {
-        size_t shm = ((size_t)3 * m + (size_t)m * (m + 1) / 2) * sizeof(double);
+        size_t shm = head + (size_t)m * (m + 1) / 2 * sizeof(double);
         rejection_cholesky_kernel<true><<<1, RC_THREADS, shm, st>>>(H, m, ldh, u, max_accept, mode, shift, ctx->ws, L, ldl,
                                                                   acc, info);
     } else {
-        size_t shm = (size_t)3 * m * sizeof(double);
+        size_t shm = head;
         rejection_cholesky_kernel<false><<<1, RC_THREADS, shm, st>>>(H, m, ldh, u, max_accept, mode, shift, ctx->ws, L, ldl,
                                                                    acc, info);
     }
@@ -371,27 +466,34 @@ extern "C" int rpc_rejection_cholesky(rpc_ctx *ctx, void *stream, double *H, int
 // ------------------------------------------------------------------------------------------------
 constexpr int TS_RW = 4;        // panel rows solved together by one warp (re-uses every L load 4 times)
 constexpr int TS_WARPS = 4;
+constexpr int TS_NJ = 4;        // columns solved per dependent step
 
+// Right-looking (column-oriented) forward substitution: once z_j is known every lane updates ITS OWN right-hand
+// side entries l > j, so no warp reduction sits on the j -> j+1 dependency chain.  L is staged transposed
+// (Lt[j][l] = L[l][j], packed rows j of length s-j) so the column reads are contiguous, plus 1/L_jj.
 template <bool LSMEM>
 __global__ void __launch_bounds__(TS_WARPS * 32) panel_trsm_kernel(const double *__restrict__ P, int64_t ldP, int c,
                                                                    const int32_t *__restrict__ acc, int s,
                                                                    const double *__restrict__ L, int64_t ldl,
                                                                    double *__restrict__ At, int64_t ldat, int k_pad) {
-    extern __shared__ double zs[];                  // [TS_WARPS][TS_RW][s] (+ packed lower triangle of L when LSMEM)
+    extern __shared__ double zs[];                  // [TS_WARPS][TS_RW][s] | inv[s] | Lt packed (when LSMEM)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r0 = (blockIdx.x * TS_WARPS + warp) * TS_RW;
-    double *Ls = zs + (size_t)TS_WARPS * TS_RW * s;
+    double *inv = zs + (size_t)TS_WARPS * TS_RW * s;
+    double *Lt = inv + s;
+    // row j of Lt starts at j*s - j*(j-1)/2 and holds L[j..s-1][j]
+    auto lt_row = [&](int j) -> size_t { return (size_t)j * s - (size_t)j * (j - 1) / 2; };
+    for (int j = threadIdx.x; j < s; j += blockDim.x) inv[j] = 1.0 / L[(int64_t)j * ldl + j];
     if (LSMEM) {
-        // every step of the substitution waits on one row of L: keep it in shared memory, not behind L2 latency
-        for (int i = warp; i < s; i += TS_WARPS)
-            for (int l = lane; l <= i; l += 32) Ls[(size_t)i * (i + 1) / 2 + l] = L[(int64_t)i * ldl + l];
-        __syncthreads();
+        for (int i = warp; i < s; i += TS_WARPS)     // coalesced read of row i of L, scattered write into the columns
+            for (int l = lane; l <= i; l += 32) Lt[lt_row(l) + (i - l)] = L[(int64_t)i * ldl + l];
     }
+    __syncthreads();
     if (r0 >= k_pad) return;
     double *z = zs + (size_t)warp * TS_RW * s;
     if (r0 < c + s) {
         // rows r < c start from -P[r, acc]; row c+i is e_i, whose solution is zero before column i
-        int jstart = r0 >= c ? r0 - c : 0;
+        const int jstart = r0 >= c ? r0 - c : 0;
         for (int j = lane; j < s; j += 32) {
 #pragma unroll
             for (int w = 0; w < TS_RW; ++w) {
@@ -399,31 +501,57 @@ __global__ void __launch_bounds__(TS_WARPS * 32) panel_trsm_kernel(const double 
                 double v = 0.0;
                 if (r < c) v = -P[(int64_t)r * ldP + (acc ? acc[j] : j)];
                 else if (r - c == j) v = 1.0;
-                z[w * s + j] = v;                  // holds the right-hand side until column j is solved
+                z[w * s + j] = v;                  // right-hand side, overwritten by the solution column by column
             }
         }
         __syncwarp();
-        for (int j = jstart; j < s; ++j) {
-            double part[TS_RW];
+        // TS_NJ columns per dependent step: the small TS_NJ x TS_NJ triangle is solved redundantly by every lane
+        // from broadcast reads, then each lane applies the TS_NJ columns to its own entries l >= j + TS_NJ
+        for (int j = jstart; j < s; j += TS_NJ) {
+            const int nj = min(TS_NJ, s - j);
+            double zj[TS_RW][TS_NJ];
 #pragma unroll
-            for (int w = 0; w < TS_RW; ++w) part[w] = 0.0;
-            const double *Lj = LSMEM ? Ls + (size_t)j * (j + 1) / 2 : L + (int64_t)j * ldl;
-            for (int l = jstart + lane; l < j; l += 32) {
-                const double lv = Lj[l];
+            for (int q = 0; q < TS_NJ; ++q) {
+                if (q < nj) {
 #pragma unroll
-                for (int w = 0; w < TS_RW; ++w) part[w] = fma(lv, z[w * s + l], part[w]);
+                    for (int w = 0; w < TS_RW; ++w) {
+                        double v = z[w * s + j + q];
+#pragma unroll
+                        for (int q2 = 0; q2 < TS_NJ; ++q2)
+                            if (q2 < q) {
+                                const double lv = LSMEM ? Lt[lt_row(j + q2) + (q - q2)] : L[(int64_t)(j + q) * ldl + j + q2];
+                                v = fma(-lv, zj[w][q2], v);
+                            }
+                        zj[w][q] = v * inv[j + q];
+                    }
+                } else {
+#pragma unroll
+                    for (int w = 0; w < TS_RW; ++w) zj[w][q] = 0.0;
+                }
             }
+            __syncwarp();
+            if (lane < TS_RW * TS_NJ) {                       // lane (w, q) stores z_{j+q} of row w
+                const int w = lane / TS_NJ, q = lane % TS_NJ;
+                double v = 0.0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
+                for (int w2 = 0; w2 < TS_RW; ++w2)
 #pragma unroll
-                for (int w = 0; w < TS_RW; ++w) part[w] += __shfl_xor_sync(0xffffffffu, part[w], o);
-            const double ljj = Lj[j];
-            if (lane < TS_RW) {
-                // lane w finishes row w (all lanes hold the reduced sums)
-                double sum = part[0];
+                    for (int q2 = 0; q2 < TS_NJ; ++q2)
+                        if (w2 == w && q2 == q) v = zj[w2][q2];
+                if (q < nj) z[w * s + j + q] = v;
+            }
+            for (int l = j + nj + lane; l < s; l += 32) {
+                double lv[TS_NJ];
 #pragma unroll
-                for (int w = 1; w < TS_RW; ++w) if (lane == w) sum = part[w];
-                z[lane * s + j] = (z[lane * s + j] - sum) / ljj;
+                for (int q = 0; q < TS_NJ; ++q)
+                    lv[q] = q < nj ? (LSMEM ? Lt[lt_row(j + q) + (l - j - q)] : L[(int64_t)l * ldl + j + q]) : 0.0;
+#pragma unroll
+                for (int w = 0; w < TS_RW; ++w) {
+                    double v = z[w * s + l];
+#pragma unroll
+                    for (int q = 0; q < TS_NJ; ++q) v = fma(-lv[q], zj[w][q], v);
+                    z[w * s + l] = v;
+                }
             }
             __syncwarp();
         }
@@ -490,7 +618,7 @@ extern "C" int rpc_build_panel(rpc_ctx *ctx, void *stream, const double *P, int6
     RPC_CHECK_ARG(k_pad >= c + s && ldat >= s, "k_pad >= c+s and ldat >= s required");
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == 0) {
-        size_t shm = (size_t)TS_WARPS * TS_RW * s * sizeof(double);
+        size_t shm = ((size_t)TS_WARPS * TS_RW * s + s) * sizeof(double);
         size_t shm_l = shm + (size_t)s * (s + 1) / 2 * sizeof(double);
         static bool configured = false;
         if (!configured) {

@@ -117,8 +117,24 @@ class _State:
         # pinned staging
         self.u_host = torch.empty((2 * m_max,), dtype=torch.float64).pin_memory()
         self.sel_host = torch.empty((m_max,), dtype=torch.int64).pin_memory()
+        self.rb_host = None
+        self.rb_event = None
         A._dev_diag_into(self.diag)
         A._count(self.n)                                       # A.diag() counts N queries (matrix.py:33-39)
+
+    def readback(self, tensors):
+        """The round's host sync: concatenate small device tensors (as float64), copy them to pinned memory and spin
+        on an event query (a blocking synchronize costs ~100 us of wake-up latency on this box, a query loop ~10)."""
+        cat = torch.cat([t if t.dtype == torch.float64 else t.to(torch.float64) for t in tensors])
+        n = cat.numel()
+        if self.rb_host is None or self.rb_host.numel() < n:
+            self.rb_host = torch.empty((max(n, 4096),), dtype=torch.float64).pin_memory()
+            self.rb_event = torch.cuda.Event()
+        self.rb_host[:n].copy_(cat, non_blocking=True)
+        self.rb_event.record()
+        while not self.rb_event.query():
+            pass
+        return self.rb_host[:n].numpy().copy()
 
     # ---- thin wrappers over the C ABI ------------------------------------------------------------
     def upload_uniforms(self, up, ur=None):
@@ -319,7 +335,7 @@ def block_cholesky_helper(A, k, b, alg, stoptol=1e-14, strategy="regularize", rb
         up = rng.random(2 * block_size)                        # rng.choice(..., size=2*block_size) (:91)
         st.upload_uniforms(up)
         st.sample(2 * block_size)
-        host = torch.cat([st.stats, st.idx_dev[:2 * block_size].to(torch.float64)]).cpu().numpy()   # one sync
+        host = st.readback([st.stats, st.idx_dev[:2 * block_size]])                                  # one sync
         stats_host = host[:4]
         _raise_if_invalid(stats_host)
         if orig_trace is None:
@@ -390,8 +406,7 @@ def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
             st.residual_block(st.idx_dev, b, counter)              # :189
         with _timed("reject", b ** 3 / 3.0, 8.0 * b * b):
             st.cholesky(b, 0, k - counter, 0.0, b)                 # :190 + truncation :193-196
-        host = torch.cat([st.stats, st.info_dev.to(torch.float64), st.acc[:b].to(torch.float64),
-                          st.idx_dev[:b].to(torch.float64)]).cpu().numpy()          # the round's only sync
+        host = st.readback([st.stats, st.info_dev, st.acc[:b], st.idx_dev[:b]])     # the round's only sync
         stats_host, info = host[:4], host[4:8].astype(np.int64)
         _raise_if_invalid(stats_host)
         if orig_trace is None:
