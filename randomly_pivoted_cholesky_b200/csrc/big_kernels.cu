@@ -36,6 +36,11 @@ typedef Cfg<4, 2, 8, 4> C256;   // 256 x 64
 typedef Cfg<4, 2, 7, 4> C224;   // 224 x 64
 typedef Cfg<4, 2, 6, 4> C192;   // 192 x 64
 typedef Cfg<4, 2, 5, 4> C160;   // 160 x 64
+// 16-row steps between the 32-row tiles: two warp rows of MI fragments, four warp columns (Schur update only)
+typedef Cfg<2, 4, 15, 2> C240;  // 240 x 64
+typedef Cfg<2, 4, 13, 2> C208;  // 208 x 64
+typedef Cfg<2, 4, 11, 2> C176;  // 176 x 64
+typedef Cfg<2, 4, 9, 2> C144;   // 144 x 64
 typedef Cfg<2, 4, 8, 4> C128;   // 128 x 128
 typedef Cfg<2, 4, 6, 4> C96;    //  96 x 128
 typedef Cfg<2, 4, 4, 4> C64;    //  64 x 128
@@ -44,7 +49,8 @@ typedef Cfg<1, 8, 2, 2> C16;    //  16 x 128
 
 int rpc_gemm_max_m(void) { return C256::M_TILE; }
 
-static int tile_rows_for(int m) {
+static int tile_rows_for(int m, bool fine = false) {
+    if (fine && m > 128) return m <= 256 ? (m + 15) / 16 * 16 : 256;      // 144, 160, ..., 256
     const int tiles[] = {16, 32, 64, 96, 128, 160, 192, 224, 256};
     for (int t : tiles) if (m <= t) return t;
     return 256;
@@ -52,6 +58,15 @@ static int tile_rows_for(int m) {
 
 template <int MODE>
 static int dispatch_gemm(rpc_ctx *ctx, cudaStream_t st, const Params &p, int m, int64_t n_pad) {
+    if (MODE == MODE_SCHUR) {
+        switch (tile_rows_for(m, true)) {
+            case 144: return launch_gemm<C144, MODE_SCHUR>(ctx, st, p, n_pad);
+            case 176: return launch_gemm<C176, MODE_SCHUR>(ctx, st, p, n_pad);
+            case 208: return launch_gemm<C208, MODE_SCHUR>(ctx, st, p, n_pad);
+            case 240: return launch_gemm<C240, MODE_SCHUR>(ctx, st, p, n_pad);
+            default: break;
+        }
+    }
     switch (tile_rows_for(m)) {
         case 16: return launch_gemm<C16, MODE>(ctx, st, p, n_pad);
         case 32: return launch_gemm<C32, MODE>(ctx, st, p, n_pad);
@@ -66,7 +81,16 @@ static int dispatch_gemm(rpc_ctx *ctx, cudaStream_t st, const Params &p, int m, 
 }
 
 // leading dimension of a panel whose k-stages can be fetched with ONE bulk copy by the tile chosen for m rows
-static int panel_ld_for(int m) {
+static int panel_ld_for(int m, bool fine = false) {
+    if (fine) {
+        switch (tile_rows_for(m, true)) {
+            case 144: return C144::LDA;
+            case 176: return C176::LDA;
+            case 208: return C208::LDA;
+            case 240: return C240::LDA;
+            default: break;
+        }
+    }
     switch (tile_rows_for(m)) {
         case 16: return C16::LDA;
         case 32: return C32::LDA;
@@ -79,7 +103,7 @@ static int panel_ld_for(int m) {
         default: return C256::LDA;
     }
 }
-extern "C" int rpc_panel_ld(int s) { return s <= 256 ? panel_ld_for(s) : (s + 255) / 256 * 256; }
+extern "C" int rpc_panel_ld(int s) { return s <= 256 ? panel_ld_for(s, true) : (s + 255) / 256 * 256; }
 
 // shared-memory need of the fused kernel for a given row count / point stride (0 if no tile fits)
 static bool fused_fits(int m, int64_t ldx) {
@@ -107,7 +131,7 @@ extern "C" int rpc_schur_update(rpc_ctx *ctx, void *stream, double *G, int64_t l
     cudaStream_t st = (cudaStream_t)stream;
     for (int m0 = 0; m0 < s; m0 += 256) {
         int m = s - m0 < 256 ? s - m0 : 256;
-        RPC_CHECK_ARG(ldat >= m0 + tile_rows_for(m), "ldat too small for the zero-padded row tile");
+        RPC_CHECK_ARG(ldat >= m0 + tile_rows_for(m, true), "ldat too small for the zero-padded row tile");
         Params p{};
         p.At = At + m0; p.ldat = ldat; p.k_pad = k_pad; p.m_valid = m;
         p.G = G; p.ldg = ldg; p.c = c; p.R = rows_new; p.ldr = ldr; p.K = c + s;

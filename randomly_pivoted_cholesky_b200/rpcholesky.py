@@ -352,7 +352,7 @@ def block_cholesky_helper(A, k, b, alg, stoptol=1e-14, strategy="regularize", rb
         st.residual_block(st.sel_dev, block_size, counter, count=False)       # C of :103
         Hcopy = st.H[:block_size, :block_size].clone()
         st.cholesky(block_size, 1, block_size, EPS * b * scale, 0)            # :106
-        info = st.info_dev.cpu().numpy()
+        info = st.readback([st.info_dev])
         if info[1] != 0:                                                       # :109-114
             warn("Cholesky failed in block partial Cholesky. Falling back to eigendecomposition")
             evals, evecs = torch.linalg.eigh(Hcopy)
