@@ -110,6 +110,11 @@ int rpc_gather_pivots(rpc_ctx *ctx, void *stream, const int64_t *idx, int m, con
                       int d, int64_t ldx, double *Xpiv, double *pnorm, int64_t ldp, const double *G, int64_t ldg,
                       int c, double *P, int64_t ldP, int64_t lo, int64_t hi);
 
+/* Selected pivots S = idx[acc] (rpcholesky.py:198): sel_idx[j] = idx[acc[j]], Xsel[j,:] = Xpiv[acc[j],:],
+ * nsel[j] = pnorm[acc[j]] for j < s.  acc NULL = identity; Xpiv/pnorm NULL for the dense operator. */
+int rpc_compact_selected(rpc_ctx *ctx, void *stream, const int32_t *acc, int s, const int64_t *idx, const double *Xpiv,
+                         const double *pnorm, int64_t ldp, int64_t *sel_idx, double *Xsel, double *nsel);
+
 /* H -= P^T P (H is m x m, P is c x m): residual Gram of the proposals (rpcholesky.py:189). */
 int rpc_gram_residual(rpc_ctx *ctx, void *stream, const double *P, int c, int m, int64_t ldP, double *H, int64_t ldh);
 

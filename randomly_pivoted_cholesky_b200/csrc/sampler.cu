@@ -96,7 +96,9 @@ __global__ void __launch_bounds__(SC_WARPS * 32) sc_classify(const double *__res
     const int64_t base = k * SC_CH;
     if (base >= n) return;
     const double S = DIV ? *Sptr : 1.0;
-    const double lo = P[k] * (1.0 - delta), hi = P[k + 1] * (1.0 + delta);
+    // pass B (x = d/S): the exact pass-A carries divided by S enclose the running sums of the quotients
+    // (each quotient and each sequential add is off by at most one rounding: delta covers both passes)
+    const double lo = (DIV ? P[k] / S : P[k]) * (1.0 - delta), hi = (DIV ? P[k + 1] / S : P[k + 1]) * (1.0 + delta);
     bool regular = lo > 0.0 && isfinite(hi);
     int e = 0;
     if (regular) {
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(SW_THREADS) sc_walk(const double *__restrict__
                                                       double *__restrict__ D, const int32_t *__restrict__ cls, int nch,
                                                       double *__restrict__ cstart, double *__restrict__ tile_tot,
                                                       double *__restrict__ tile_carry, int32_t *__restrict__ tile_e,
-                                                      int32_t *__restrict__ bad) {
+                                                      int32_t *__restrict__ bad, double *__restrict__ stats) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned full = 0xffffffffu;
     const double S = DIV ? *Sptr : 1.0;
@@ -309,6 +311,14 @@ __global__ void __launch_bounds__(SW_THREADS) sc_walk(const double *__restrict__
         if (lane == 0) {
             cstart[nch] = carry;
             if (violated) atomicExch(bad, 2);
+            if (DIV && stats) {
+                // numpy raises ValueError when p holds NaN / negatives or does not sum to 1 (S == 0, inf, NaN)
+                const int b = violated ? 2 : *bad;
+                const bool invalid = (b == 1) || !(S > 0.0) || !isfinite(S) || !(fabs(carry - 1.0) <= 1.4901161193847656e-08);
+                stats[0] = S;
+                stats[1] = invalid ? 1.0 : 0.0;
+                stats[2] = (b == 2) ? 1.0 : 0.0;
+            }
         }
     }
     __syncthreads();
@@ -321,7 +331,20 @@ __global__ void __launch_bounds__(SW_THREADS) sc_walk(const double *__restrict__
     }
 }
 
-// 5. locate the draws: idx = #{ j : fl(c_j / c_last) <= u }
+// 5. locate the draws: idx = #{ j : fl(c_j / c_last) <= u }.  Division by c_last > 0 is monotone, so the predicate
+// equals c_j <= t with t the LARGEST double whose quotient rounds to <= u; t is found once per draw and the
+// per-element division disappears from the sequential replay.
+__device__ __forceinline__ double quotient_threshold(double u, double clast) {
+    double t = u * clast;
+    if (!(t == t) || !(clast > 0.0) || !isfinite(clast)) return t;
+    for (int it = 0; it < 8 && !(t / clast <= u); ++it) t = __longlong_as_double(__double_as_longlong(t) - 1);   // t > 0 here
+    for (int it = 0; it < 8; ++it) {
+        const double up = t == 0.0 ? __longlong_as_double(1) : __longlong_as_double(__double_as_longlong(t) + 1);
+        if (up / clast <= u) t = up; else break;
+    }
+    return t;
+}
+
 __global__ void __launch_bounds__(32) sc_locate(const double *__restrict__ d, int64_t n, const double *Sptr,
                                                 const double *__restrict__ cstart, int nch, const double *__restrict__ u,
                                                 int64_t *__restrict__ idx) {
@@ -329,12 +352,12 @@ __global__ void __launch_bounds__(32) sc_locate(const double *__restrict__ d, in
     const int lane = threadIdx.x;
     const double S = *Sptr;
     const double clast = cstart[nch];
-    const double uu = u[blockIdx.x];
-    // first chunk whose END value exceeds u: cdf is non-decreasing, cstart[k+1] is the value at chunk k's end
+    const double thr = quotient_threshold(u[blockIdx.x], clast);
+    // first chunk whose END value exceeds the threshold: cdf is non-decreasing, cstart[k+1] is the value at chunk k's end
     int lo = 0, hi = nch - 1;
     while (lo < hi) {
         int mid = (lo + hi) >> 1;
-        if (cstart[mid + 1] / clast > uu) hi = mid; else lo = mid + 1;
+        if (cstart[mid + 1] > thr) hi = mid; else lo = mid + 1;
     }
     const int64_t base = (int64_t)lo * SC_CH;
 #pragma unroll
@@ -348,23 +371,11 @@ __global__ void __launch_bounds__(32) sc_locate(const double *__restrict__ d, in
         int cnt = 0;
         for (int j = 0; j < SC_CH; ++j) {
             c += xs[j];
-            if (c / clast <= uu) ++cnt; else break;
+            if (c <= thr) ++cnt; else break;
         }
         int64_t r = base + cnt;
         idx[blockIdx.x] = r < n ? r : n - 1;
     }
-}
-
-__global__ void sc_finish(const double *__restrict__ Sptr, const double *__restrict__ ctot, const int32_t *__restrict__ bad,
-                          double *__restrict__ stats) {
-    double S = *Sptr;
-    int b = *bad;
-    stats[0] = S;
-    // numpy raises ValueError when p holds NaN / negatives or does not sum to 1 (S == 0, inf, NaN)
-    double tot = *ctot;
-    bool invalid = (b == 1) || !(S > 0.0) || !isfinite(S) || !(fabs(tot - 1.0) <= 1.4901161193847656e-08);
-    stats[1] = invalid ? 1.0 : 0.0;
-    stats[2] = (b == 2) ? 1.0 : 0.0;
 }
 
 extern "C" int rpc_sample_pivots(rpc_ctx *ctx, void *stream, const double *diag, int64_t n_pad, const double *u, int m,
@@ -402,22 +413,20 @@ extern "C" int rpc_sample_pivots(rpc_ctx *ctx, void *stream, const double *diag,
     RPC_LAUNCHED(ctx);
     sc_classify<false><<<grid, SC_WARPS * 32, 0, st>>>(diag, n_pad, nullptr, csum, delta, D, cls);
     RPC_LAUNCHED(ctx);
-    sc_walk<false><<<1, SW_THREADS, SW_SLOTS * SC_CH * sizeof(double), st>>>(diag, n_pad, nullptr, D, cls, nch, cA, tile_tot, tile_carry, tile_e, bad);
+    sc_walk<false><<<1, SW_THREADS, SW_SLOTS * SC_CH * sizeof(double), st>>>(diag, n_pad, nullptr, D, cls, nch, cA, tile_tot, tile_carry,
+                                                                             tile_e, bad, nullptr);
     RPC_LAUNCHED(ctx);
 
-    sc_chunk_sums<true><<<grid, SC_WARPS * 32, 0, st>>>(diag, n_pad, Sptr, csum, bad);
+    // pass B: x_j = d_j / S.  Its approximate prefix comes from the exact pass-A carries (no second reduction).
+    const double delta_b = (2.0 * (double)n_pad + 512.0) * 1.1102230246251565e-16 * 1.01;
+    sc_classify<true><<<grid, SC_WARPS * 32, 0, st>>>(diag, n_pad, Sptr, cA, delta_b, D, cls);
     RPC_LAUNCHED(ctx);
-    sc_scan_chunks<<<1, 1024, 0, st>>>(csum, nch);
-    RPC_LAUNCHED(ctx);
-    sc_classify<true><<<grid, SC_WARPS * 32, 0, st>>>(diag, n_pad, Sptr, csum, delta, D, cls);
-    RPC_LAUNCHED(ctx);
-    sc_walk<true><<<1, SW_THREADS, SW_SLOTS * SC_CH * sizeof(double), st>>>(diag, n_pad, Sptr, D, cls, nch, cB, tile_tot, tile_carry, tile_e, bad);
+    sc_walk<true><<<1, SW_THREADS, SW_SLOTS * SC_CH * sizeof(double), st>>>(diag, n_pad, Sptr, D, cls, nch, cB, tile_tot, tile_carry,
+                                                                            tile_e, bad, stats);
     RPC_LAUNCHED(ctx);
     if (m > 0) {
         sc_locate<<<m, 32, 0, st>>>(diag, n_pad, Sptr, cB, nch, u, idx);
         RPC_LAUNCHED(ctx);
     }
-    sc_finish<<<1, 1, 0, st>>>(Sptr, cB + nch, bad, stats);
-    RPC_LAUNCHED(ctx);
     return 0;
 }

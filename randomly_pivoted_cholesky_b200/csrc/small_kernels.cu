@@ -648,3 +648,28 @@ extern "C" int rpc_build_panel(rpc_ctx *ctx, void *stream, const double *P, int6
     RPC_LAUNCHED(ctx);
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// selected pivots S = idx[acc]: compact the payload rows of the accepted proposals (rpcholesky.py:198 `idx = idx[accepted]`)
+// ------------------------------------------------------------------------------------------------
+__global__ void compact_selected_kernel(const int32_t *__restrict__ acc, int s, const int64_t *__restrict__ idx,
+                                        const double *__restrict__ Xpiv, const double *__restrict__ pnorm, int64_t ldp,
+                                        int64_t *__restrict__ sel_idx, double *__restrict__ Xsel, double *__restrict__ nsel) {
+    const int j = blockIdx.x;
+    const int src = acc ? acc[j] : j;
+    if (threadIdx.x == 0) {
+        sel_idx[j] = idx[src];
+        if (pnorm && nsel) nsel[j] = pnorm[src];
+    }
+    if (Xpiv && Xsel)
+        for (int f = threadIdx.x; f < ldp; f += blockDim.x) Xsel[(int64_t)j * ldp + f] = Xpiv[(int64_t)src * ldp + f];
+}
+
+extern "C" int rpc_compact_selected(rpc_ctx *ctx, void *stream, const int32_t *acc, int s, const int64_t *idx,
+                                    const double *Xpiv, const double *pnorm, int64_t ldp, int64_t *sel_idx, double *Xsel,
+                                    double *nsel) {
+    RPC_CHECK_ARG(ctx && idx && sel_idx && s >= 1, "null pointer or bad sizes");
+    compact_selected_kernel<<<s, 64, 0, (cudaStream_t)stream>>>(acc, s, idx, Xpiv, pnorm, ldp, sel_idx, Xsel, nsel);
+    RPC_LAUNCHED(ctx);
+    return 0;
+}

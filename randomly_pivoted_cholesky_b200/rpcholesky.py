@@ -197,12 +197,13 @@ class _State:
                   "rpc_build_panel")
         A = self.A
         if acc_dev is not None:
-            accl = acc_dev[:s].to(torch.int64)
-            sel_idx = torch.index_select(idx_dev, 0, accl)
-            if self.piv is not None:
-                torch.index_select(self.piv.X, 0, accl, out=self.sel.X[:s])
-                torch.index_select(self.piv.norm, 0, accl, out=self.sel.norm[:s])
-            sel_piv = self.sel
+            piv = self.piv
+            check(self.lib.rpc_compact_selected(self.ctx.handle, _stream(), _ptr(acc_dev), s, _ptr(idx_dev),
+                                                _ptr(piv.X) if piv is not None else None,
+                                                _ptr(piv.norm) if piv is not None else None, self.ldx, _ptr(self.sel_dev),
+                                                _ptr(self.sel.X) if piv is not None else None,
+                                                _ptr(self.sel.norm) if piv is not None else None), "rpc_compact_selected")
+            sel_idx, sel_piv = self.sel_dev, self.sel
         else:
             sel_idx, sel_piv = idx_dev, self.piv
         rows_ptr = C.c_void_p(self.rows.data_ptr() + 8 * c * self.n_pad)
