@@ -250,7 +250,7 @@ extern "C" int rpc_kernel_rows(rpc_ctx *ctx, void *stream, const rpc_kernel_spec
     RPC_CHECK_ARG(ctx && spec && X && Xpiv && out, "null pointer");
     RPC_CHECK_ARG(s >= 1, "s >= 1");
     RPC_CHECK_ARG(n_pad > 0 && n_pad % RPC_COL_ALIGN == 0, "n_pad must be a positive multiple of RPC_COL_ALIGN");
-    RPC_CHECK_ARG(d >= 1 && d % RPC_FEAT_ALIGN == 0 && ldx % 2 == 0, "d must be a multiple of RPC_FEAT_ALIGN, ldx even");
+    RPC_CHECK_ARG(d >= 1 && d % RPC_FEAT_ALIGN == 0 && ldx >= d, "d must be a multiple of RPC_FEAT_ALIGN, ldx >= d");
     RPC_CHECK_ARG(ldo % 2 == 0, "ldo must be even");
     RPC_CHECK_ARG(spec->kind >= 0 && spec->kind <= 2, "unknown kernel kind");
     RPC_CHECK_ARG(spec->kind != RPC_KERN_MATERN || spec->nu2 == 1 || spec->nu2 == 3 || spec->nu2 == 5,
@@ -258,6 +258,21 @@ extern "C" int rpc_kernel_rows(rpc_ctx *ctx, void *stream, const rpc_kernel_spec
     cudaStream_t st = (cudaStream_t)stream;
     KernParams kp = make_kern_params(spec);
     if (spec->kind == RPC_KERN_LAPLACE || spec->extra_stability) {
+        const bool l1 = spec->kind == RPC_KERN_LAPLACE;
+        // fast path: pivots resident in shared memory, point tiles streamed by TMA (csrc/direct_eval.cu)
+        bool done = true;
+        for (int m0 = 0; m0 < s && done; m0 += 256) {
+            const int m = s - m0 < 256 ? s - m0 : 256;
+            const int ldpt = 16 * rpc_direct_pi_for(m, l1);
+            int rc = rpc_ws_reserve(ctx, (size_t)d * ldpt * sizeof(double));
+            if (rc) return rc;
+            rc = rpc_transpose_pad(ctx, st, Xpiv + (int64_t)m0 * ldp, ldp, m, d, ctx->ws, ldpt, d);
+            if (rc) return rc;
+            rc = rpc_direct_rows_tma(ctx, st, kp, l1, X, ldx, d, ctx->ws, ldpt, m, out + (int64_t)m0 * ldo, ldo, n_pad);
+            if (rc == -100) { done = false; break; }
+            if (rc) return rc;
+        }
+        if (done) return 0;
         dim3 grid((unsigned)(n_pad / DK_TN));
         if (spec->kind == RPC_KERN_LAPLACE)
             direct_rows_kernel<true><<<grid, 256, 0, st>>>(kp, X, ldx, d, Xpiv, ldp, s, out, ldo);
@@ -267,6 +282,7 @@ extern "C" int rpc_kernel_rows(rpc_ctx *ctx, void *stream, const rpc_kernel_spec
         return 0;
     }
     RPC_CHECK_ARG(xnorm && pnorm, "row norms required for the expanded Euclidean form");
+    RPC_CHECK_ARG(ldx % 2 == 0, "the DMMA evaluator needs an even point stride (16-byte rows)");
     // A operand = Xpiv^T (d x s) zero padded to (k_pad x ld) in the context workspace
     const int k_pad = (d + RPC_KT - 1) / RPC_KT * RPC_KT;
     for (int m0 = 0; m0 < s; m0 += 256) {

@@ -1,0 +1,143 @@
+// Kernel rows for the kernels that are NOT a contraction: Laplace (L1 distance, kernels.py:16-21) and the
+// direct-difference Euclidean form (extra_stability, kernels.py:35-36,74-75).  FP64 vector pipe bound:
+// 2 DADD (or DADD + DFMA) per (pivot, point, feature).
+//
+// Persistent CTAs (one per SM): the transposed pivot panel Pt[f][m] is copied into shared memory ONCE per CTA and
+// the point tiles (64 points x ldx, one contiguous block because X is point-major) stream through a two-stage
+// TMA bulk-copy + mbarrier ring, so the FP64 pipe never waits for a load.  Thread (tx, ty) owns pivots
+// ty + 16 i and points tx + 16 j; X is stored with an ODD point stride for these kernels so the 16 points a
+// half warp reads per feature fall in 16 different bank pairs, and pivots are broadcast reads.  The L1 distance is
+// accumulated strictly in feature order, which makes it bit-equal to scipy's cdist(..., 'cityblock').
+#include "dmma_gemm.cuh"
+
+using namespace dg;
+
+constexpr int DE_TN = 64;          // points per tile
+constexpr int DE_THREADS = 256;    // 16 x 16
+
+template <bool L1, int PI>
+__global__ void __launch_bounds__(DE_THREADS, 1) direct_rows_tma(const KernParams kp, const double *__restrict__ X, int64_t ldx,
+                                                                 int d, const double *__restrict__ Pt, int ldpt, int s,
+                                                                 double *__restrict__ out, int64_t ldo, int ntiles) {
+    extern __shared__ __align__(16) double sm[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm);          // [0] panel, [1..2] X tiles
+    double *Ps = sm + 4;                                        // [d][ldpt]
+    double *Xs = Ps + (size_t)d * ldpt;                         // [2][DE_TN * ldx]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tile_doubles = DE_TN * (int)ldx;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_init(&bars[2], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const int first = blockIdx.x;
+    if (tid == 0) {
+        const unsigned pb = (unsigned)((size_t)d * ldpt * 8);
+        mbar_expect_tx(&bars[0], pb);
+        bulk_g2s(Ps, Pt, pb, &bars[0]);
+        if (first < ntiles) {
+            mbar_expect_tx(&bars[1], (unsigned)tile_doubles * 8);
+            bulk_g2s(Xs, X + (int64_t)first * DE_TN * ldx, (unsigned)tile_doubles * 8, &bars[1]);
+        }
+    }
+    mbar_wait(&bars[0], 0);
+
+    int it = 0;
+    for (int tile = first; tile < ntiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int nxt = tile + gridDim.x;
+        if (tid == 0 && nxt < ntiles) {     // buffer buf^1 was released by the barrier that ended the previous iteration
+            mbar_expect_tx(&bars[1 + (buf ^ 1)], (unsigned)tile_doubles * 8);
+            bulk_g2s(Xs + (buf ^ 1) * tile_doubles, X + (int64_t)nxt * DE_TN * ldx, (unsigned)tile_doubles * 8, &bars[1 + (buf ^ 1)]);
+        }
+        mbar_wait(&bars[1 + buf], (it >> 1) & 1);
+        const double *xs = Xs + buf * tile_doubles;
+
+        double acc[PI][4];
+#pragma unroll
+        for (int i = 0; i < PI; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+#pragma unroll 2
+        for (int f = 0; f < d; ++f) {
+            double xp[PI], yv[4];
+#pragma unroll
+            for (int i = 0; i < PI; ++i) xp[i] = Ps[f * ldpt + ty + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) yv[j] = xs[(tx + 16 * j) * ldx + f];
+#pragma unroll
+            for (int i = 0; i < PI; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double df = xp[i] - yv[j];
+                    if (L1) acc[i][j] += fabs(df);                // sequential in f: bit-equal to cdist 'cityblock'
+                    else acc[i][j] = fma(df, df, acc[i][j]);
+                }
+        }
+        const int64_t col0 = (int64_t)tile * DE_TN;
+#pragma unroll
+        for (int i = 0; i < PI; ++i) {
+            const int row = ty + 16 * i;
+            if (row < s) {
+#pragma unroll
+                for (int j = 0; j < 4; j += 2) {
+                    const double2 v = L1 ? kern_from_l1_pair(kp, acc[i][j], acc[i][j + 1])
+                                         : kern_from_d2_pair(kp, acc[i][j], acc[i][j + 1]);
+                    out[(int64_t)row * ldo + col0 + tx + 16 * j] = v.x;
+                    out[(int64_t)row * ldo + col0 + tx + 16 * (j + 1)] = v.y;
+                }
+            }
+        }
+        __syncthreads();      // every thread is done with xs before it is refilled two iterations later
+    }
+}
+
+template <bool L1, int PI>
+static int launch_direct(rpc_ctx *ctx, cudaStream_t st, const KernParams &kp, const double *X, int64_t ldx, int d, const double *Pt,
+                         int ldpt, int s, double *out, int64_t ldo, int64_t n_pad, size_t shm) {
+    static bool configured = false;
+    if (!configured) {
+        RPC_CUDA(cudaFuncSetAttribute(direct_rows_tma<L1, PI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    const int ntiles = (int)(n_pad / DE_TN);
+    const int grid = ntiles < ctx->sm_count ? ntiles : ctx->sm_count;
+    direct_rows_tma<L1, PI><<<grid, DE_THREADS, shm, st>>>(kp, X, ldx, d, Pt, ldpt, s, out, ldo, ntiles);
+    RPC_LAUNCHED(ctx);
+    return 0;
+}
+
+// s <= 256 pivots, panel Pt (d x ldpt, ldpt = 16 * PI) already built.  Returns -100 if the shape does not fit.
+int rpc_direct_rows_tma(rpc_ctx *ctx, cudaStream_t st, const KernParams &kp, bool l1, const double *X, int64_t ldx, int d,
+                        const double *Pt, int ldpt, int s, double *out, int64_t ldo, int64_t n_pad) {
+    const int pi = ldpt / 16;
+    const size_t shm = (4 + (size_t)d * ldpt + 2 * (size_t)DE_TN * ldx) * sizeof(double);
+    if (shm > 227 * 1024 || (ldx * 8 * DE_TN) % 16 != 0) return -100;
+#define DE_CASE(L, P) \
+    case P: return launch_direct<L, P>(ctx, st, kp, X, ldx, d, Pt, ldpt, s, out, ldo, n_pad, shm);
+    if (l1) {
+        switch (pi) {
+            DE_CASE(true, 1) DE_CASE(true, 2) DE_CASE(true, 4) DE_CASE(true, 6) DE_CASE(true, 8) DE_CASE(true, 10)
+            DE_CASE(true, 11) DE_CASE(true, 12) DE_CASE(true, 13) DE_CASE(true, 14) DE_CASE(true, 16)
+            default: return -100;
+        }
+    }
+    switch (pi) {
+        DE_CASE(false, 2) DE_CASE(false, 4) DE_CASE(false, 8) DE_CASE(false, 12) DE_CASE(false, 16)
+        default: return -100;
+    }
+#undef DE_CASE
+}
+
+// pivots-per-thread variant that covers s rows (multiples instantiated above)
+int rpc_direct_pi_for(int s, bool l1) {
+    const int need = (s + 15) / 16;
+    const int l1_set[] = {1, 2, 4, 6, 8, 10, 11, 12, 13, 14, 16};
+    const int d2_set[] = {2, 4, 8, 12, 16};
+    if (l1) { for (int p : l1_set) if (p >= need) return p; }
+    else { for (int p : d2_set) if (p >= need) return p; }
+    return 16;
+}

@@ -95,3 +95,13 @@ static __device__ __noinline__ double2 kern_from_d2_pair(const KernParams kp, do
 }
 
 __device__ __forceinline__ double kern_from_l1(const KernParams &kp, double l1) { return exp(-l1 / kp.bw); }
+static __device__ __noinline__ double2 kern_from_l1_pair(const KernParams kp, double a, double b) {
+    return make_double2(exp(-a / kp.bw), exp(-b / kp.bw));
+}
+
+struct rpc_ctx;
+// csrc/direct_eval.cu: persistent TMA-staged evaluator for the non-contraction kernels (returns -100 if the shape
+// does not fit in shared memory; the caller then uses the chunked kernel)
+int rpc_direct_rows_tma(rpc_ctx *ctx, cudaStream_t st, const KernParams &kp, bool l1, const double *X, int64_t ldx, int d,
+                        const double *Pt, int ldpt, int s, double *out, int64_t ldo, int64_t n_pad);
+int rpc_direct_pi_for(int s, bool l1);

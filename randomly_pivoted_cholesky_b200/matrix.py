@@ -229,6 +229,7 @@ class KernelMatrix(AbstractPSDMatrix):
         self.d = d
         self.d_pad = _round_up(d, FEAT_ALIGN)
         # point stride == 4 (mod 8) doubles: the DMMA fragment reads of a resident X tile are then bank-conflict free
+        # (the non-contraction kernels -- Laplace, extra_stability -- want an ODD stride instead, set below)
         self.ldx = self.d_pad if self.d_pad % 8 == 4 else self.d_pad + 4
         self._ctx = _lib.Context.get(dev.index)
         self.kernel_kwargs = dict(kwargs)
@@ -255,6 +256,8 @@ class KernelMatrix(AbstractPSDMatrix):
         stab = bool(kwargs.get("extra_stability", False))
         if kind == _lib.KERN_LAPLACE:
             stab = False                                     # LaplaceKernel_mtx ignores it (kernels.py:16)
+        if kind == _lib.KERN_LAPLACE or stab:
+            self.ldx = self.d_pad + 1                        # 16 points x one feature -> 16 distinct bank pairs
 
         Xp = torch.zeros((self.n_pad, self.ldx), dtype=torch.float64, device=dev)
         Xp[:info.n_loc, :d] = Xd

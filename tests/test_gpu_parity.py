@@ -320,3 +320,32 @@ def test_reconstruction_property_large(rpc):
     resid = 1.0 - (G * G).sum(0)
     assert float(resid.min()) >= -1e-12
     assert abs(float(resid.clamp_min(0).sum()) - (n - lra.trace())) <= 1e-6 * n
+
+
+@pytest.mark.parametrize("kernel,kw,b,k", [("matern", {"nu": 2.5}, 400, 900), ("gaussian", {}, 640, 1400),
+                                           ("laplace", {}, 288, 600)])
+def test_large_proposal_blocks_against_oracle(rpc, kernel, kw, b, k):
+    """configs[3] shape (accelerated, b = 400 > one 256-row tile, Matern-5/2, d = 3) at N = 24,000 and two more
+    kernels: exercises the row-chunked evaluator / Schur update and the global-memory rejection path."""
+    d = 3 if kernel == "matern" else 6
+    X = np.random.default_rng(11).standard_normal((24000, d))
+    bw = float(d) if kernel == "laplace" else float(np.sqrt(d))
+    with replay(31):
+        lra = rpc.accelerated_rpcholesky(rpc.KernelMatrix(X, kernel=kernel, bandwidth=bw, **kw), k, b=b)
+    rng, legacy = orc.make_streams(31)
+    ref = orc.accelerated_rpcholesky(orc.OracleKernelMatrix(X, kernel=kernel, bandwidth=bw, **kw), k, b, rng, legacy)
+    assert np.array_equal(np.asarray(lra.idx), ref.idx)
+    assert lra.rounds == ref.rounds
+    if b > 600:
+        assert max(ref.rounds) > 256          # more accepted pivots than one 256-row tile: row-chunked update
+    assert relerr(lra.G, ref.G) <= 1e-9 and relerr(lra.rows, ref.rows) <= F_TOL
+
+
+def test_block_large_b_against_oracle(rpc):
+    X = np.random.default_rng(12).standard_normal((20000, 5))
+    with replay(41):
+        lra = rpc.block_rpcholesky(rpc.KernelMatrix(X, kernel="gaussian", bandwidth=float(np.sqrt(5))), 700, b=320)
+    rng, _ = orc.make_streams(41)
+    ref = orc.block_rpcholesky(orc.OracleKernelMatrix(X, kernel="gaussian", bandwidth=float(np.sqrt(5))), 700, 320, rng)
+    assert [int(i) for i in lra.idx] == [int(i) for i in ref.idx]
+    assert relerr(lra.G, ref.G) <= 1e-9 and relerr(lra.rows, ref.rows) <= F_TOL
