@@ -1,0 +1,119 @@
+"""Kernel ridge regression on top of the RPCholesky hot path -- first "next" row of SURVEY.md section 8(f).
+
+Same class and method names as the reference's KRR_Nystrom.py (:9-66).  `fit_Nystrom` keeps the factor rows in HBM:
+the normal equations  (K_Mn K_nM + N lambda K_MM + 100 max(K_MM) eps I) beta = K_Mn y  (KRR_Nystrom.py:52-54) are
+formed with one k x N x k DGEMM (cuBLAS through torch; summed over the shards with an all-reduce when the operator
+is row-sharded) and solved by Cholesky (scipy's assume_a='pos').  `predict_Nystrom` implements the evident intent of
+the reference's broken method (:60-66 multiplies an undefined `KtM`): K(Xts, Xtr[S]) @ sol, evaluated by the CUDA
+kernel-row evaluator with the pivots in the role of the rows.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+
+import numpy as np
+import torch
+
+from . import dist as rdist
+from .matrix import COL_ALIGN, KernelMatrix, _round_up
+
+
+class KRR_Nystrom:
+    def __init__(self, kernel="gaussian", bandwidth=1, **kernel_kwargs):
+        self.kernel = kernel
+        self.bandwidth = bandwidth
+        self.kernel_kwargs = kernel_kwargs          # nu / extra_stability (an extension: the reference passes none)
+
+    # -- exact KRR (KRR_Nystrom.py:16-32): needs all N^2 entries, small N only -----------------------------------
+    def fit(self, Xtr, Ytr, lamb):
+        self.Xtr = Xtr
+        ts = time.time()
+        self.K = KernelMatrix(Xtr, kernel=self.kernel, bandwidth=self.bandwidth, **self.kernel_kwargs)
+        K_exact = torch.from_numpy(np.ascontiguousarray(self.K[:, :])).to(self.K.device)
+        n = K_exact.shape[0]
+        rhs = torch.from_numpy(np.ascontiguousarray(np.asarray(Ytr, dtype=np.float64))).to(self.K.device)
+        Lc = torch.linalg.cholesky(K_exact + lamb * n * torch.eye(n, dtype=torch.float64, device=self.K.device))
+        sol = torch.cholesky_solve(rhs.reshape(n, -1), Lc)
+        self.sol = sol.reshape(rhs.shape).cpu().numpy()
+        self.linsolve_time = time.time() - ts
+
+    def predict(self, Xts):
+        ts = time.time()
+        n = self.K.shape[0]
+        preds = self._cross_times(Xts, np.arange(n, dtype=np.int64), self.sol)
+        self.pred_time = time.time() - ts
+        return preds
+
+    # -- restricted Nystrom KRR (KRR_Nystrom.py:34-58) -----------------------------------------------------------------
+    def fit_Nystrom(self, Xtr, Ytr, lamb, sample_num, sample_method, solve_method="Direct", ite=400, sharded=False):
+        self.Xtr = Xtr
+        self.K = KernelMatrix(Xtr, kernel=self.kernel, bandwidth=self.bandwidth, sharded=sharded, **self.kernel_kwargs)
+        ts = time.time()
+        lra = sample_method(self.K, sample_num)
+        arr_idx = lra.get_indices()
+        te = time.time()
+        self.sample_idx = arr_idx
+        self.sample_time = te - ts
+        self.queries = self.K.num_queries()
+
+        trK = self.K.trace()
+        self.reltrace_err = (trK - lra.trace()) / trK
+
+        self.K.reset()
+        ts = time.time()
+        if solve_method == "Direct":
+            self.sol = self._direct_solve(lra, np.asarray(arr_idx, dtype=np.int64), Ytr, lamb, sample_num)
+        else:
+            raise RuntimeError("Solve method '{}' undefined".format(solve_method))
+        te = time.time()
+        self.linsolve_time = te - ts
+        self.lra = lra
+
+    def _direct_solve(self, lra, idx, Ytr, lamb, sample_num):
+        info = self.K.shard_info
+        dev = self.K.device
+        rows = lra.rows_device
+        if rows is None:                                      # a host-side result (not from our drivers)
+            rows = torch.from_numpy(np.ascontiguousarray(lra.get_rows())).to(dev)
+        k = rows.shape[0]
+        R = rows[:, :info.n_loc]                              # this rank's columns of K_Mn
+        y = torch.from_numpy(np.ascontiguousarray(np.asarray(Ytr, dtype=np.float64)[info.lo:info.hi])).to(dev)
+        M = R @ R.T                                           # K_Mn K_nM  (k x N x k DGEMM)
+        rhs = R @ y
+        # K_MM = K_Mn[:, idx]: every rank contributes the columns it owns
+        idx_t = torch.as_tensor(idx[:k], device=dev)
+        mine = (idx_t >= info.lo) & (idx_t < info.hi)
+        local = torch.where(mine, idx_t - info.lo, torch.zeros_like(idx_t))
+        KMM = torch.where(mine[None, :], R[:, local], torch.zeros((), dtype=torch.float64, device=dev))
+        if info.world > 1:
+            packed = torch.cat([M.reshape(-1), KMM.reshape(-1), rhs.reshape(-1)])
+            rdist.exchange_payload(info, packed)
+            M = packed[:k * k].view(k, k)
+            KMM = packed[k * k:2 * k * k].view(k, k)
+            rhs = packed[2 * k * k:].view(rhs.shape)
+        n = info.n
+        M = M + n * lamb * KMM + 100 * KMM.max() * np.finfo(float).eps * torch.eye(sample_num, dtype=torch.float64, device=dev)
+        Lc = torch.linalg.cholesky(M)                         # scipy.linalg.solve(..., assume_a='pos')
+        sol = torch.cholesky_solve(rhs.reshape(k, -1), Lc).reshape(rhs.shape)
+        return sol.cpu().numpy()
+
+    def _cross_times(self, Xts, idx, sol):
+        """K(Xts, Xtr[idx]) @ sol on the device: the training pivots play the rows, the test points the columns."""
+        K = self.K
+        dev = K.device
+        m = len(idx)
+        Kt = KernelMatrix(Xts, kernel=self.kernel, bandwidth=self.bandwidth, device=dev, **self.kernel_kwargs)
+        piv = K._dev_new_payload(m)
+        K._dev_gather(torch.as_tensor(np.asarray(idx, dtype=np.int64), device=dev), m, piv)
+        out = torch.empty((m, Kt.n_pad), dtype=torch.float64, device=dev)
+        Kt._dev_rows_into(None, m, piv, C.c_void_p(out.data_ptr()), Kt.n_pad)
+        s = torch.from_numpy(np.ascontiguousarray(np.asarray(sol, dtype=np.float64))).to(dev)
+        preds = out[:, :Kt.shape[0]].T @ s
+        return preds.cpu().numpy()
+
+    def predict_Nystrom(self, Xts):
+        ts = time.time()
+        preds = self._cross_times(Xts, np.asarray(self.sample_idx, dtype=np.int64), self.sol)
+        self.pred_time = time.time() - ts
+        return preds

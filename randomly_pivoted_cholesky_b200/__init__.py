@@ -9,12 +9,13 @@ All numerical work is done by hand-written sm_100a CUDA kernels behind the C ABI
 """
 from .lra import AbstractPSDLowRank, CompactEigenvalueDecomposition, PSDLowRank
 from .matrix import AbstractPSDMatrix, KernelMatrix, PSDMatrix
+from .KRR_Nystrom import KRR_Nystrom
 from .rpcholesky import (accelerated_rpcholesky, block_cholesky_helper, block_rpcholesky, cholesky_helper, greedy,
                          rpcholesky, simple_rpcholesky)
 from ._lib import build, load, total_launches
 
 __all__ = [
     "AbstractPSDLowRank", "CompactEigenvalueDecomposition", "PSDLowRank", "AbstractPSDMatrix", "KernelMatrix",
-    "PSDMatrix", "accelerated_rpcholesky", "block_cholesky_helper", "block_rpcholesky", "cholesky_helper", "greedy",
+    "PSDMatrix", "KRR_Nystrom", "accelerated_rpcholesky", "block_cholesky_helper", "block_rpcholesky", "cholesky_helper", "greedy",
     "rpcholesky", "simple_rpcholesky", "build", "load", "total_launches",
 ]

@@ -349,9 +349,14 @@ class KernelMatrix(AbstractPSDMatrix):
         return _PivotPayload(m_max, self.ldx, self.device)
 
     def _dev_gather(self, idx_dev, m, piv):
+        """piv <- X[idx] and their squared norms (global indices; assembled with a sum all-reduce when sharded)."""
+        info = self.shard_info
         check(self._ctx.lib.rpc_gather_pivots(self._ctx.handle, _stream(), _ptr(idx_dev), m, _ptr(self._Xd), _ptr(self._xnorm),
                                               self.d_pad, self.ldx, _ptr(piv.X), _ptr(piv.norm), self.ldx, None, 0, 0,
-                                              None, 0, 0, self.shape[0]), "rpc_gather_pivots")
+                                              None, 0, info.lo, info.hi), "rpc_gather_pivots")
+        if info.world > 1:
+            rdist.exchange_payload(info, piv.X)
+            rdist.exchange_payload(info, piv.norm)
 
     def _dev_block_into(self, idx_dev, m, piv, H, ldh):
         check(self._ctx.lib.rpc_kernel_block(self._ctx.handle, _stream(), C.byref(self._spec), _ptr(piv.X), _ptr(piv.norm), m,

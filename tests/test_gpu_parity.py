@@ -349,3 +349,39 @@ def test_block_large_b_against_oracle(rpc):
     ref = orc.block_rpcholesky(orc.OracleKernelMatrix(X, kernel="gaussian", bandwidth=float(np.sqrt(5))), 700, 320, rng)
     assert [int(i) for i in lra.idx] == [int(i) for i in ref.idx]
     assert relerr(lra.G, ref.G) <= 1e-9 and relerr(lra.rows, ref.rows) <= F_TOL
+
+
+# ---- first "next" row: KRR_Nystrom on top of the hot path ------------------------------------------
+from make_golden_krr import KRR_CASES, krr_inputs  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(KRR_CASES))
+def test_krr_nystrom_matches_reference(rpc, name):
+    spec = KRR_CASES[name]
+    gold = load(name)
+    Xtr, ytr, Xts, _ = krr_inputs(spec)
+    if spec["alg"] == "accel":
+        method = lambda A, k: rpc.accelerated_rpcholesky(A, k, b=spec["b"])
+    else:
+        method = lambda A, k: rpc.block_rpcholesky(A, k, b=spec["b"])
+    model = rpc.KRR_Nystrom(kernel=spec["kernel"], bandwidth=spec["bw"])
+    with replay(spec["seed"]):
+        model.fit_Nystrom(Xtr, ytr, spec["lamb"], spec["k"], method)
+    assert np.array_equal(np.asarray(model.sample_idx, dtype=np.int64), gold["sample_idx"])
+    assert model.queries == int(gold["queries"])
+    assert abs(model.reltrace_err - float(gold["reltrace_err"])) <= 1e-12
+    preds = model.predict_Nystrom(Xts)
+    # the normal equations square the condition number of K_MM: compare what the model predicts, not beta itself
+    np.testing.assert_allclose(preds, gold["preds"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(model.sol, gold["sol"], rtol=1e-4, atol=1e-5 * np.abs(gold["sol"]).max())
+
+
+def test_exact_krr_small(rpc):
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((300, 4)); y = np.sin(X[:, 0]) + X[:, 1] ** 2
+    Xt = rng.standard_normal((40, 4))
+    model = rpc.KRR_Nystrom(kernel="gaussian", bandwidth=1.5)
+    model.fit(X, y, 1e-4)
+    Kx = orc.gaussian_mtx(X, X, bandwidth=1.5)
+    want = orc.gaussian_mtx(Xt, X, bandwidth=1.5) @ np.linalg.solve(Kx + 1e-4 * 300 * np.eye(300), y)
+    np.testing.assert_allclose(model.predict(Xt), want, rtol=1e-7, atol=1e-8)

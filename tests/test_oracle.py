@@ -122,3 +122,23 @@ def test_rejection_cholesky_properties():
         orc.rejection_cholesky(-np.eye(3), np.zeros(3))
     with pytest.raises(RuntimeError):
         orc.rejection_cholesky(np.ones((2, 3)), np.zeros(2))
+
+
+# ---- first "next" row: KRR_Nystrom (oracle/krr_oracle.py vs the live reference) ---------------------------------
+from make_golden_krr import KRR_CASES, krr_inputs  # noqa: E402
+from oracle import krr_oracle  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(KRR_CASES))
+def test_krr_oracle_matches_reference(name):
+    spec = KRR_CASES[name]
+    gold = load(name)
+    Xtr, ytr, Xts, _ = krr_inputs(spec)
+    sol, idx, err, queries = krr_oracle.fit_nystrom(Xtr, ytr, spec["lamb"], spec["k"], spec["kernel"], spec["bw"], spec["alg"],
+                                                    spec["b"], spec["seed"])
+    assert np.array_equal(idx, gold["sample_idx"])
+    assert queries == int(gold["queries"])
+    assert abs(err - float(gold["reltrace_err"])) <= 1e-13
+    np.testing.assert_allclose(sol, gold["sol"], rtol=1e-7, atol=1e-9)
+    preds = krr_oracle.predict_nystrom(Xts, Xtr, idx, sol, spec["kernel"], spec["bw"])
+    np.testing.assert_allclose(preds, gold["preds"], rtol=1e-8, atol=1e-10)
