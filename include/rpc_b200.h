@@ -98,6 +98,10 @@ int rpc_psd_block(rpc_ctx *ctx, void *stream, const double *A, int64_t lda, cons
 int rpc_sample_pivots(rpc_ctx *ctx, void *stream, const double *diag, int64_t n_pad, const double *u, int m,
                       int64_t *idx, double *stats);
 
+/* Greedy pivoting (rpcholesky.py:33,35): idx[0] = np.argmax(diag[0:n]) (first maximum), stats[0] = the maximum,
+ * stats[1] = number of entries equal to it (the randomized tie-break of 'rgreedy' draws among them on the host). */
+int rpc_argmax(rpc_ctx *ctx, void *stream, const double *diag, int64_t n, int64_t *idx, double *stats);
+
 /* ---- per-round small dense work (rpcholesky.py:102-107, 140-157, 189-190, 206-207) -------------- */
 
 /* Xpiv[j,:] = X[idx[j],:], pnorm[j] = xnorm[idx[j]] (matrix.py:189 `self.data[vec_i,:]`) and

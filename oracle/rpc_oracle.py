@@ -244,9 +244,10 @@ def _as_operator(A):
     return OracleDenseMatrix(A)
 
 
-def simple_rpcholesky(A, k, rng, stoptol=0):
-    """cholesky_helper(A, k, 'rp', stoptol) -- rpcholesky.py:12-50.  `rng` supplies the proposal
-    stream exactly as `np.random.default_rng()` does in the reference (one double per step)."""
+def simple_rpcholesky(A, k, rng, stoptol=0, alg="rp"):
+    """cholesky_helper(A, k, alg, stoptol) -- rpcholesky.py:12-50.  `rng` supplies the proposal
+    stream exactly as `np.random.default_rng()` does in the reference (one double per step for 'rp';
+    'rgreedy' draws through rng.choice over the tied maxima, 'greedy' draws nothing)."""
     A = _as_operator(A)
     n = A.shape[0]
     diags = A.diag().copy()
@@ -257,7 +258,14 @@ def simple_rpcholesky(A, k, rng, stoptol=0):
     rows = np.zeros((k, n))
     arr_idx = []
     for i in range(k):
-        idx = int(sample_pivots(diags, np.array([rng.random()]))[0])          # :31
+        if alg == "rp":
+            idx = int(sample_pivots(diags, np.array([rng.random()]))[0])      # :31
+        elif alg == "rgreedy":
+            idx = int(rng.choice(np.where(diags == np.max(diags))[0]))        # :33
+        elif alg == "greedy":
+            idx = int(np.argmax(diags))                                        # :35
+        else:
+            raise RuntimeError("Algorithm '{}' not recognized".format(alg))
         arr_idx.append(idx)
         rows[i, :] = A.rows(idx)[0]                                            # :40
         G[i, :] = (rows[i, :] - G[:i, idx].T @ G[:i, :]) / np.sqrt(diags[idx])  # :41

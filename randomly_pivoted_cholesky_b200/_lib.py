@@ -88,6 +88,7 @@ _SIGNATURES = {
     "rpc_psd_rows": (_INT, [_P, _P, _P, _I64, _I64, _P, _INT, _P, _I64, _I64]),
     "rpc_psd_block": (_INT, [_P, _P, _P, _I64, _P, _INT, _P, _I64]),
     "rpc_sample_pivots": (_INT, [_P, _P, _P, _I64, _P, _INT, _P, _P]),
+    "rpc_argmax": (_INT, [_P, _P, _P, _I64, _P, _P]),
     "rpc_gather_pivots": (_INT, [_P, _P, _P, _INT, _P, _P, _INT, _I64, _P, _P, _I64, _P, _I64, _INT, _P, _I64, _I64, _I64]),
     "rpc_compact_selected": (_INT, [_P, _P, _P, _INT, _P, _P, _P, _I64, _P, _P, _P]),
     "rpc_gram_residual": (_INT, [_P, _P, _P, _INT, _INT, _I64, _P, _I64]),

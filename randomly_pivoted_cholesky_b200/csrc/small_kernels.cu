@@ -673,3 +673,60 @@ extern "C" int rpc_compact_selected(rpc_ctx *ctx, void *stream, const int32_t *a
     RPC_LAUNCHED(ctx);
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// greedy pivoting: np.argmax(diags) (first maximum, rpcholesky.py:35) and the number of entries tied at the
+// maximum (rgreedy draws among them on the host, rpcholesky.py:33)
+// ------------------------------------------------------------------------------------------------
+struct MaxRec { double v; long long i; long long cnt; };
+
+__device__ __forceinline__ MaxRec max_combine(MaxRec a, MaxRec b) {     // a precedes b in index order
+    if (b.v > a.v) return b;
+    if (b.v == a.v) { a.cnt += b.cnt; if (a.cnt == b.cnt) a.i = b.i; return a; }
+    return a;
+}
+
+__global__ void __launch_bounds__(256) argmax_partial_kernel(const double *__restrict__ d, int64_t n, MaxRec *__restrict__ part) {
+    __shared__ MaxRec sm[256];
+    const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * per, hi = lo + per < n ? lo + per : n;
+    // thread t scans a contiguous sub-range so that combining in thread order keeps "first maximum"
+    const int64_t sub = (hi - lo + 255) / 256;
+    const int64_t a = lo + (int64_t)threadIdx.x * sub, b = a + sub < hi ? a + sub : hi;
+    MaxRec r{-INFINITY, -1, 0};
+    for (int64_t j = a; j < b; ++j) {
+        const double v = d[j];
+        if (v > r.v) { r.v = v; r.i = j; r.cnt = 1; }
+        else if (v == r.v) r.cnt++;
+    }
+    sm[threadIdx.x] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        MaxRec t = sm[0];
+        for (int q = 1; q < 256; ++q) if (sm[q].cnt > 0) t = t.cnt > 0 ? max_combine(t, sm[q]) : sm[q];
+        part[blockIdx.x] = t;
+    }
+}
+
+__global__ void argmax_final_kernel(const MaxRec *__restrict__ part, int nparts, int64_t *__restrict__ idx, double *__restrict__ stats) {
+    MaxRec t = part[0];
+    for (int q = 1; q < nparts; ++q) if (part[q].cnt > 0) t = t.cnt > 0 ? max_combine(t, part[q]) : part[q];
+    idx[0] = t.i;
+    stats[0] = t.v;
+    stats[1] = (double)t.cnt;
+}
+
+extern "C" int rpc_argmax(rpc_ctx *ctx, void *stream, const double *diag, int64_t n, int64_t *idx, double *stats) {
+    RPC_CHECK_ARG(ctx && diag && idx && stats && n > 0, "null pointer or empty");
+    cudaStream_t st = (cudaStream_t)stream;
+    int parts = (int)((n + 8191) / 8192);
+    if (parts > 2 * ctx->sm_count) parts = 2 * ctx->sm_count;
+    int rc = rpc_ws_reserve(ctx, (size_t)parts * sizeof(MaxRec));
+    if (rc) return rc;
+    MaxRec *part = reinterpret_cast<MaxRec *>(ctx->ws);
+    argmax_partial_kernel<<<parts, 256, 0, st>>>(diag, n, part);
+    RPC_LAUNCHED(ctx);
+    argmax_final_kernel<<<1, 1, 0, st>>>(part, parts, idx, stats);
+    RPC_LAUNCHED(ctx);
+    return 0;
+}

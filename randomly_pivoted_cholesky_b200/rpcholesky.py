@@ -247,10 +247,7 @@ def _raise_if_invalid(stats_host):
 # simple RPCholesky: cholesky_helper(A, k, 'rp', stoptol) -- rpcholesky.py:12-50
 # --------------------------------------------------------------------------------------------------
 def cholesky_helper(A, k, alg, stoptol=0):
-    if alg != "rp":
-        if alg in ("greedy", "rgreedy"):
-            # they share the loop but are SURVEY.md section 8(f) rows, not built yet
-            raise NotImplementedError("greedy pivoting is outside the round-1 hot path")
+    if alg not in ("rp", "greedy", "rgreedy"):
         raise RuntimeError("Algorithm '{}' not recognized".format(alg))
     A = _as_operator(A)
     if stoptol is None:
@@ -268,7 +265,7 @@ def cholesky_helper(A, k, alg, stoptol=0):
     stats_all = torch.zeros((k + 1, 4), dtype=torch.float64, device=st.dev)
     # one uniform per step (rng.choice(range(n), p=...), rpcholesky.py:31); the stream is state independent,
     # so all k are drawn and uploaded at once and the loop below never waits for the device
-    u_all = torch.from_numpy(rng.random(k)).to(st.dev)
+    u_all = torch.from_numpy(rng.random(k) if alg == "rp" else np.zeros(1)).to(st.dev)
     count = k
     arr_len = k
     check_every_step = stoptol > 0
@@ -280,11 +277,28 @@ def cholesky_helper(A, k, alg, stoptol=0):
                                     C.c_void_p(idx_all.data_ptr() + 8 * i) if m else None,
                                     C.c_void_p(stats_all.data_ptr() + 32 * i)), "rpc_sample_pivots")
 
+    def pick_greedy(i):
+        """np.argmax(diags) (:35) or, for 'rgreedy', rng.choice over the tied maxima (:33, drawn on the host)."""
+        gstats = stats_all[k]                  # scratch row: [max, #ties]
+        check(lib.rpc_argmax(ctx.handle, _stream(), _ptr(st.diag), st.n, C.c_void_p(idx_all.data_ptr() + 8 * i),
+                             _ptr(gstats)), "rpc_argmax")
+        if alg == "rgreedy":
+            mx, ties = (float(v) for v in gstats[:2].cpu().numpy())
+            if ties > 1:
+                cand = torch.nonzero(st.diag[:st.n] == mx).flatten().cpu().numpy()
+                idx_all[i] = int(rng.choice(cand))
+
     for i in range(k):
-        sample_into(i, 1)
+        if alg == "rp":
+            sample_into(i, 1)
+        else:
+            if check_every_step or i == 0:
+                sample_into(i, 0)               # python sum(diags) for the stoptol test (exact, like the reference's)
+            pick_greedy(i)
         if check_every_step:
             sh = stats_all[i].cpu().numpy()
-            _raise_if_invalid(sh)
+            if alg == "rp":
+                _raise_if_invalid(sh)
             if i == 0:
                 orig_trace = float(sh[0])
             elif float(sh[0]) <= stoptol * orig_trace:         # rpcholesky.py:45-48 (drops row i-1, keeps its index)
@@ -301,9 +315,10 @@ def cholesky_helper(A, k, alg, stoptol=0):
             sh = stats_all[k].cpu().numpy()
             if float(sh[0]) <= stoptol * orig_trace:
                 count = k - 1
-    stats_host = stats_all[:arr_len].cpu().numpy()
-    for r in range(arr_len):
-        _raise_if_invalid(stats_host[r])
+    if alg == "rp":
+        stats_host = stats_all[:arr_len].cpu().numpy()
+        for r in range(arr_len):
+            _raise_if_invalid(stats_host[r])
     arr_idx = [int(v) for v in idx_all[:arr_len].cpu().numpy()]
     return st.result(count, arr_idx)
 
@@ -470,4 +485,9 @@ def block_rpcholesky(A, k, b=100, **kwargs):
 
 
 def greedy(A, k, randomized_tiebreaking=False, b=1, **kwargs):
-    raise NotImplementedError("greedy pivoting (rpcholesky.py:245-251) is a SURVEY.md section 8(f) row, not built yet")
+    """rpcholesky.py:245-251.  b == 1: greedy / randomized-greedy pivoting through the simple loop."""
+    if b == 1:
+        return cholesky_helper(A, k, "rgreedy" if randomized_tiebreaking else "greedy", **kwargs)
+    # np.argpartition's order inside the selected block is an implementation detail of numpy's introselect, so the
+    # reference's block-greedy factor cannot be reproduced row for row; not built
+    raise NotImplementedError("block greedy pivoting (rpcholesky.py:94-95) is not built")

@@ -34,6 +34,10 @@ CASES = {
     "accel_stoptol":    dict(alg="accel", N=200, dense_rank=12, k=40, b=10, seed=24),
     "block_stoptol":    dict(alg="block", N=200, dense_rank=12, k=40, b=10, seed=25),
     "simple_stoptol":   dict(alg="simple", N=100, dense_rank=6, k=20, seed=26, stoptol=1e-10),
+    # greedy / randomized-greedy pivoting through the same loop (rpcholesky.py:32-35, 245-251)
+    "greedy_gauss":     dict(alg="greedy", N=450, d=5, kernel="gaussian", bw="sqrtd", k=28, seed=27),
+    "greedy_dense":     dict(alg="greedy", N=130, dense_rank=50, k=24, seed=28),
+    "rgreedy_laplace":  dict(alg="rgreedy", N=380, d=6, kernel="laplace", bw="d", k=22, seed=29),
 }
 
 KERNEL_CASES = {
@@ -90,7 +94,9 @@ def main():
         kw = {"stoptol": spec["stoptol"]} if "stoptol" in spec else {}
         with mock.patch("numpy.random.default_rng", lambda *a, **k: np.random.Generator(np.random.PCG64(seed))):
             np.random.seed(seed)
-            if spec["alg"] == "simple":
+            if spec["alg"] in ("greedy", "rgreedy"):
+                lra = ref.greedy(A, spec["k"], randomized_tiebreaking=spec["alg"] == "rgreedy", **kw)
+            elif spec["alg"] == "simple":
                 lra = ref.simple_rpcholesky(A, spec["k"], **kw)
             elif spec["alg"] == "block":
                 lra = ref.block_rpcholesky(A, spec["k"], b=spec["b"], **kw)
@@ -101,11 +107,16 @@ def main():
             out["queries"] = np.int64(A.num_queries())
         return out
 
+    only = set(sys.argv[1:])
     for name, spec in CASES.items():
+        if only and name not in only:
+            continue
         out = run(spec)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print(name, out["G"].shape, out["idx"][:6])
 
+    if only:
+        return
     for name, spec in KERNEL_CASES.items():
         X, idx, kw = kernel_inputs(spec)
         A = KernelMatrix(X, kernel=spec["kernel"], bandwidth=spec["bw"], **kw)

@@ -52,7 +52,9 @@ def run_gpu(rpc, spec):
     A = make_operator(rpc, inp)
     kw = {"stoptol": spec["stoptol"]} if "stoptol" in spec else {}
     with replay(spec["seed"]):
-        if spec["alg"] == "simple":
+        if spec["alg"] in ("greedy", "rgreedy"):
+            lra = rpc.greedy(A, spec["k"], randomized_tiebreaking=spec["alg"] == "rgreedy", **kw)
+        elif spec["alg"] == "simple":
             lra = rpc.simple_rpcholesky(A, spec["k"], **kw)
         elif spec["alg"] == "block":
             lra = rpc.block_rpcholesky(A, spec["k"], b=spec["b"], **kw)

@@ -25,8 +25,8 @@ def run_oracle(spec):
         inp["X"], kernel=inp["kernel"], bandwidth=inp["bandwidth"], **inp["kw"])
     rng, legacy = orc.make_streams(spec["seed"])
     kw = {"stoptol": spec["stoptol"]} if "stoptol" in spec else {}
-    if spec["alg"] == "simple":
-        res = orc.simple_rpcholesky(A, spec["k"], rng, **kw)
+    if spec["alg"] in ("simple", "greedy", "rgreedy"):
+        res = orc.simple_rpcholesky(A, spec["k"], rng, alg={"simple": "rp"}.get(spec["alg"], spec["alg"]), **kw)
     elif spec["alg"] == "block":
         res = orc.block_rpcholesky(A, spec["k"], spec["b"], rng, **kw)
     else:
