@@ -335,11 +335,18 @@ def gpu_arm(args, w):
                     "launches": cnt, "avg_launch_ms": 1e3 * sec / cnt, "share_of_step": sec / (ms * 1e-3),
                     "algorithmic_flops_per_launch": flops / cnt, "algorithmic_bytes_per_launch": nbytes / cnt,
                     "hbm_gbs_achieved": nbytes / sec / 1e9, "hbm_peak_gbs": hbm}
+    elif "simple" in phases:
+        sec, flops, nbytes, cnt = phases["simple"]
+        ach = nbytes / sec / 1e9
+        roofline = {"bound": "hbm", "kernel": "simple_step_kernel (fused GEMV over G[:i] + kernel row + diag update)",
+                    "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm if hbm else None, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs", "launches": cnt, "avg_launch_ms": 1e3 * sec / cnt,
+                    "share_of_step": sec / (ms * 1e-3), "algorithmic_bytes_per_launch": nbytes / cnt}
     phase_ms = {k: 1e3 * v[0] / args.steps for k, v in phases.items()}
     # per-launch detail of the dominant kernel over the LAST timed step: (ms, TFLOP/s)
     per_step = max(1, len([1 for t in timers if t[2] == "schur"]) // args.steps)
     detail = [[round(t[0].elapsed_time(t[1]), 3), round(t[3] / t[0].elapsed_time(t[1]) / 1e9, 2)]
-              for t in timers if t[2] == "schur"][-per_step:]
+              for t in timers if t[2] == "schur"][-per_step:] if "schur" in phases else []
 
     # ---- e2e: host X -> H2D -> factorise -> D2H pivots + trace-norm error, through the public API ----
     sync_all()

@@ -317,6 +317,29 @@ extern "C" int rpc_kernel_rows(rpc_ctx *ctx, void *stream, const rpc_kernel_spec
 constexpr int SS_THREADS = 256;
 constexpr int SS_MAXD = 1024;   // features cached in smem
 
+__device__ __forceinline__ double simple_row_entry(int has_spec, const KernParams &kp, const double *__restrict__ X,
+                                                   const double *__restrict__ xnorm, int d, int64_t ldx,
+                                                   const double *__restrict__ A, int64_t lda, int64_t n, int64_t piv,
+                                                   const double *xp, double pn, int64_t col) {
+    if (!has_spec) return col < n ? A[piv * lda + col] : 0.0;
+    if (kp.kind == RPC_KERN_LAPLACE) {
+        double l1 = 0.0;
+        for (int f = 0; f < d; ++f) l1 += fabs(xp[f] - X[col * ldx + f]);
+        return kern_from_l1(kp, l1);
+    }
+    if (kp.stab) {
+        double d2 = 0.0;
+        for (int f = 0; f < d; ++f) { double df = xp[f] - X[col * ldx + f]; d2 = fma(df, df, d2); }
+        return kern_from_d2(kp, d2);
+    }
+    double dot = 0.0;
+    for (int f = 0; f < d; ++f) dot = fma(xp[f], X[col * ldx + f], dot);
+    double d2 = (-2.0 * dot + pn) + xnorm[col];
+    return kern_from_d2(kp, d2 > 0.0 ? d2 : 0.0);
+}
+
+// Each thread owns two adjacent columns (16-byte loads) and keeps 8 independent row loads in flight: the kernel
+// streams G[:i] once, 8 N i bytes, which is all the HBM traffic of a simple-RPCholesky step.
 __global__ void __launch_bounds__(SS_THREADS) simple_step_kernel(int has_spec, KernParams kp, const double *__restrict__ X,
                                                                  const double *__restrict__ xnorm, int d, int64_t ldx,
                                                                  const double *__restrict__ A, int64_t lda, int64_t n,
@@ -336,39 +359,40 @@ __global__ void __launch_bounds__(SS_THREADS) simple_step_kernel(int has_spec, K
     const double dpiv = diag_in[piv];
     const double scale = sqrt(dpiv);
     const double pn = has_spec && xnorm ? xnorm[piv] : 0.0;
-    for (int64_t col = (int64_t)blockIdx.x * SS_THREADS + threadIdx.x; col < n_pad; col += (int64_t)gridDim.x * SS_THREADS) {
-        double row;
-        if (!has_spec) {
-            row = col < n ? A[piv * lda + col] : 0.0;
-        } else if (kp.kind == RPC_KERN_LAPLACE) {
-            double l1 = 0.0;
-            for (int f = 0; f < d; ++f) l1 += fabs(xp[f] - X[col * ldx + f]);
-            row = kern_from_l1(kp, l1);
-        } else if (kp.stab) {
-            double d2 = 0.0;
-            for (int f = 0; f < d; ++f) { double df = xp[f] - X[col * ldx + f]; d2 = fma(df, df, d2); }
-            row = kern_from_d2(kp, d2);
-        } else {
-            double dot = 0.0;
-            for (int f = 0; f < d; ++f) dot = fma(xp[f], X[col * ldx + f], dot);
-            double d2 = (-2.0 * dot + pn) + xnorm[col];
-            row = kern_from_d2(kp, d2 > 0.0 ? d2 : 0.0);
-        }
+    for (int64_t col = 2 * ((int64_t)blockIdx.x * SS_THREADS + threadIdx.x); col < n_pad;
+         col += 2 * (int64_t)gridDim.x * SS_THREADS) {
+        const double row0 = simple_row_entry(has_spec, kp, X, xnorm, d, ldx, A, lda, n, piv, xp, pn, col);
+        const double row1 = simple_row_entry(has_spec, kp, X, xnorm, d, ldx, A, lda, n, piv, xp, pn, col + 1);
         // g = (row - G[:i,piv]^T G[:i,col]) / sqrt(diag[piv])   (rpcholesky.py:41)
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        double2 acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = make_double2(0.0, 0.0);
+        const double *Gc = G + col;
         int r = 0;
-        for (; r + 4 <= i; r += 4) {
-            a0 = fma(pcol[r], G[(int64_t)r * ldg + col], a0);
-            a1 = fma(pcol[r + 1], G[(int64_t)(r + 1) * ldg + col], a1);
-            a2 = fma(pcol[r + 2], G[(int64_t)(r + 2) * ldg + col], a2);
-            a3 = fma(pcol[r + 3], G[(int64_t)(r + 3) * ldg + col], a3);
+        for (; r + 8 <= i; r += 8) {
+            double2 g[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) g[q] = *reinterpret_cast<const double2 *>(Gc + (int64_t)(r + q) * ldg);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const double pc = pcol[r + q];
+                acc[q].x = fma(pc, g[q].x, acc[q].x);
+                acc[q].y = fma(pc, g[q].y, acc[q].y);
+            }
         }
-        for (; r < i; ++r) a0 = fma(pcol[r], G[(int64_t)r * ldg + col], a0);
-        double g = (row - ((a0 + a1) + (a2 + a3))) / scale;
-        rows[(int64_t)i * ldr + col] = row;
-        G[(int64_t)i * ldg + col] = g;
-        double dv = diag_in[col] - g * g;
-        diag_out[col] = dv > 0.0 ? dv : 0.0;
+        for (; r < i; ++r) {
+            const double2 g = *reinterpret_cast<const double2 *>(Gc + (int64_t)r * ldg);
+            acc[0].x = fma(pcol[r], g.x, acc[0].x);
+            acc[0].y = fma(pcol[r], g.y, acc[0].y);
+        }
+        const double s0 = ((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x)) + ((acc[4].x + acc[5].x) + (acc[6].x + acc[7].x));
+        const double s1 = ((acc[0].y + acc[1].y) + (acc[2].y + acc[3].y)) + ((acc[4].y + acc[5].y) + (acc[6].y + acc[7].y));
+        const double g0 = (row0 - s0) / scale, g1 = (row1 - s1) / scale;
+        *reinterpret_cast<double2 *>(rows + (int64_t)i * ldr + col) = make_double2(row0, row1);
+        *reinterpret_cast<double2 *>(G + (int64_t)i * ldg + col) = make_double2(g0, g1);
+        const double2 dv = *reinterpret_cast<const double2 *>(diag_in + col);
+        const double d0 = dv.x - g0 * g0, d1 = dv.y - g1 * g1;
+        *reinterpret_cast<double2 *>(diag_out + col) = make_double2(d0 > 0.0 ? d0 : 0.0, d1 > 0.0 ? d1 : 0.0);
     }
 }
 
@@ -378,7 +402,7 @@ extern "C" int rpc_simple_step(rpc_ctx *ctx, void *stream, const rpc_kernel_spec
                                double *diag, int64_t n_pad) {
     RPC_CHECK_ARG(ctx && idx_dev && G && rows && diag, "null pointer");
     RPC_CHECK_ARG((spec && X) || A, "either a kernel spec with X or a dense A is required");
-    RPC_CHECK_ARG(i >= 0 && n_pad > 0, "i >= 0, n_pad > 0");
+    RPC_CHECK_ARG(i >= 0 && n_pad > 0 && n_pad % 2 == 0 && ldg % 2 == 0 && ldr % 2 == 0, "i >= 0, even n_pad / ldg / ldr");
     RPC_CHECK_ARG(!spec || d <= SS_MAXD, "d too large for the fused simple step");
     cudaStream_t st = (cudaStream_t)stream;
     KernParams kp{};
@@ -386,7 +410,7 @@ extern "C" int rpc_simple_step(rpc_ctx *ctx, void *stream, const rpc_kernel_spec
     // the step reads diag[piv] while other CTAs overwrite diag: double-buffer through the workspace
     int rc = rpc_ws_reserve(ctx, (size_t)n_pad * sizeof(double));
     if (rc) return rc;
-    int grid = (int)((n_pad + SS_THREADS - 1) / SS_THREADS);
+    int grid = (int)((n_pad / 2 + SS_THREADS - 1) / SS_THREADS);
     int cap = ctx->sm_count * 8;
     if (grid > cap) grid = cap;
     size_t shm = (size_t)(i + (spec ? d : 0) + 1) * sizeof(double);

@@ -305,9 +305,11 @@ def cholesky_helper(A, k, alg, stoptol=0):
                 count = i - 1
                 arr_len = i
                 break
-        check(lib.rpc_simple_step(ctx.handle, _stream(), spec_ref, _ptr(X), _ptr(xn), d, ldx, _ptr(Ad), lda, st.n,
-                                  _ptr(idx_all), i, _ptr(st.G), st.n_pad, _ptr(st.rows), st.n_pad, _ptr(st.diag), st.n_pad),
-              "rpc_simple_step")
+        # algorithmic traffic of one step: stream G[:i], read X, write G[i] and rows[i], diag read + write
+        with _timed("simple", 2.0 * st.n * (i + d), 8.0 * st.n * (i + d + 5)):
+            check(lib.rpc_simple_step(ctx.handle, _stream(), spec_ref, _ptr(X), _ptr(xn), d, ldx, _ptr(Ad), lda, st.n,
+                                      _ptr(idx_all), i, _ptr(st.G), st.n_pad, _ptr(st.rows), st.n_pad, _ptr(st.diag),
+                                      st.n_pad), "rpc_simple_step")
         A._count(st.n)
     else:
         if check_every_step:
