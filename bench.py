@@ -258,12 +258,13 @@ def gpu_arm(args, w):
             def num_queries(self): return self.q
         A = _KrrOperator()
 
-        def factorise(rpc_, A_, w_):             # noqa: F811  one step = fit + predict
+        def step_fn(rpc_, A_, w_):               # one step = fit + predict
             model, preds = run_krr(rpc_, X, y, Xts, w_, dev, sharded)
             A_.q = model.queries
             return _KrrResult(model, preds, w_["k"])
     else:
         A = rpc.KernelMatrix(Xpin, kernel=w["kernel"], bandwidth=bandwidth(w), device=dev, sharded=sharded)
+        step_fn = factorise
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -273,7 +274,7 @@ def gpu_arm(args, w):
 
     for _ in range(args.warmup):
         A.reset()
-        lra = factorise(rpc, A, w)
+        lra = step_fn(rpc, A, w)
         del lra
     sync_all()
 
@@ -290,7 +291,7 @@ def gpu_arm(args, w):
     queries = 0
     for _ in range(args.steps):
         A.reset()
-        lra = factorise(rpc, A, w)
+        lra = step_fn(rpc, A, w)
         queries += A.num_queries()
         rank_k = lra.rank()
         del lra
@@ -326,11 +327,18 @@ def gpu_arm(args, w):
     except Exception:
         pass
     roofline = None
+    traffic = None
+    if args.workload == "tstar" and world == 1:
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of this command
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))["schur"]["avg_dram_bytes_per_launch"]
+        except Exception:
+            traffic = None
     if "schur" in phases:
         sec, flops, nbytes, cnt = phases["schur"]
         ach = flops / sec / 1e12
         roofline = {"bound": "tensor", "kernel": "dg::gemm_kernel<MODE_SCHUR> (FP64 DMMA, fused diag update)",
-                    "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                    "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
+                    "traffic_source": "profiles/traffic_r01.json (ncu, same command)" if traffic else None,
                     "peak_source": "measured FP64 DMMA peak, profiles/fp64_peaks_r01.json (MEASURED_PEAKS.json holds bf16/HBM only)",
                     "launches": cnt, "avg_launch_ms": 1e3 * sec / cnt, "share_of_step": sec / (ms * 1e-3),
                     "algorithmic_flops_per_launch": flops / cnt, "algorithmic_bytes_per_launch": nbytes / cnt,
@@ -358,14 +366,14 @@ def gpu_arm(args, w):
     for _ in range(args.steps):
         if is_krr:
             A.reset()
-            lra = factorise(rpc, A, w)
+            lra = step_fn(rpc, A, w)
             idx, err = lra.idx, lra.model.reltrace_err
             q2 += A.num_queries()
             d2h = idx.nbytes + 8 + lra.preds.nbytes + lra.model.sol.nbytes
             del lra
             continue
         A2 = rpc.KernelMatrix(Xpin, kernel=w["kernel"], bandwidth=bandwidth(w), device=dev, sharded=sharded)
-        lra = factorise(rpc, A2, w)
+        lra = step_fn(rpc, A2, w)
         idx = np.asarray(lra.idx)
         err = (n - lra.trace()) / n                      # utils.approximation_error with trace(A) = N
         q2 += A2.num_queries()
