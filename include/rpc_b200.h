@@ -148,6 +148,12 @@ int rpc_build_panel(rpc_ctx *ctx, void *stream, const double *P, int64_t ldP, in
  * height works; this one is the fast one. */
 int rpc_panel_ld(int s);
 
+/* The round's host read-back without a stream synchronisation: writes [seq | stats(4) | info(4) | acc(m) | idx(m)] as
+ * doubles into `host_mapped`, a PINNED host buffer of at least 9 + 2m doubles addressed through UVA, the sequence number
+ * last (after a system-scope fence); the host spins until host_mapped[0] == seq.  info / acc may be NULL. */
+int rpc_publish_round(rpc_ctx *ctx, void *stream, const double *stats, const int32_t *info, const int32_t *acc,
+                      const int64_t *idx, int m, double *host_mapped, double seq);
+
 /* ---- the N-proportional update (rpcholesky.py:41-43, 102-107+128-129, 206-209) ---------------- */
 
 /* G[c:c+s, :] = At^T [G[0:c, :]; rows_new] ; diag = max(diag - colsum(G[c:c+s,:]^2), 0).

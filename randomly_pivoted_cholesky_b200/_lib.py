@@ -91,6 +91,7 @@ _SIGNATURES = {
     "rpc_argmax": (_INT, [_P, _P, _P, _I64, _P, _P]),
     "rpc_gather_pivots": (_INT, [_P, _P, _P, _INT, _P, _P, _INT, _I64, _P, _P, _I64, _P, _I64, _INT, _P, _I64, _I64, _I64]),
     "rpc_compact_selected": (_INT, [_P, _P, _P, _INT, _P, _P, _P, _I64, _P, _P, _P]),
+    "rpc_publish_round": (_INT, [_P, _P, _P, _P, _P, _P, _INT, _P, _DBL]),
     "rpc_gram_residual": (_INT, [_P, _P, _P, _INT, _INT, _I64, _P, _I64]),
     "rpc_rejection_cholesky": (_INT, [_P, _P, _P, _INT, _I64, _P, _INT, _INT, _DBL, _P, _I64, _P, _P]),
     "rpc_build_panel": (_INT, [_P, _P, _P, _I64, _INT, _P, _INT, _P, _I64, _INT, _P, _I64, _INT]),

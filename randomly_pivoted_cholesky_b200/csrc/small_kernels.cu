@@ -730,3 +730,34 @@ extern "C" int rpc_argmax(rpc_ctx *ctx, void *stream, const double *diag, int64_
     RPC_LAUNCHED(ctx);
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// the round's host read-back: [seq | stats(4) | info(4) | acc(m) | idx(m)] written as doubles into PINNED HOST
+// memory (UVA: the device writes it directly), the sequence number last, so the host can spin on one word
+// instead of paying a stream synchronisation.
+// ------------------------------------------------------------------------------------------------
+__global__ void publish_round_kernel(const double *__restrict__ stats, const int32_t *__restrict__ info,
+                                     const int32_t *__restrict__ acc, const int64_t *__restrict__ idx, int m,
+                                     volatile double *host, double seq) {
+    const int t = threadIdx.x;
+    if (t < 4) host[1 + t] = stats[t];
+    if (t < 4) host[5 + t] = info ? (double)info[t] : 0.0;
+    for (int j = t; j < m; j += blockDim.x) {
+        host[9 + j] = acc ? (double)acc[j] : 0.0;
+        host[9 + m + j] = (double)idx[j];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t == 0) {
+        __threadfence_system();
+        host[0] = seq;
+    }
+}
+
+extern "C" int rpc_publish_round(rpc_ctx *ctx, void *stream, const double *stats, const int32_t *info, const int32_t *acc,
+                                 const int64_t *idx, int m, double *host_mapped, double seq) {
+    RPC_CHECK_ARG(ctx && stats && idx && host_mapped && m >= 0, "null pointer or bad sizes");
+    publish_round_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(stats, info, acc, idx, m, host_mapped, seq);
+    RPC_LAUNCHED(ctx);
+    return 0;
+}

@@ -141,10 +141,10 @@ class PSDLowRank(AbstractPSDLowRank):
         if self._on_device():
             if self._sharded():                                # local columns only (the shard is padded), then sum
                 import torch.distributed as tdist
-                t = torch.linalg.norm(self._G[:, :self.shard_info.n_loc]) ** 2
+                t = torch.linalg.vector_norm(self._G[:, :self.shard_info.n_loc]) ** 2      # strided reduction, no copy
                 tdist.all_reduce(t, group=self.shard_info.group)
                 return float(t)
-            return float(torch.linalg.norm(self._G) ** 2)      # lra.py:94-95, ||G||_F^2
+            return float(torch.linalg.vector_norm(self._G) ** 2)   # lra.py:94-95, ||G||_F^2 (no contiguous copy of the view)
         return np.linalg.norm(self.G, "fro") ** 2
 
     def __matmul__(self, other):

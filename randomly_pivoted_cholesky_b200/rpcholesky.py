@@ -118,23 +118,34 @@ class _State:
         self.u_host = torch.empty((2 * m_max,), dtype=torch.float64).pin_memory()
         self.sel_host = torch.empty((m_max,), dtype=torch.int64).pin_memory()
         self.rb_host = None
-        self.rb_event = None
         A._dev_diag_into(self.diag)
         A._count(self.n)                                       # A.diag() counts N queries (matrix.py:33-39)
 
-    def readback(self, tensors):
-        """The round's host sync: concatenate small device tensors (as float64), copy them to pinned memory and spin
-        on an event query (a blocking synchronize costs ~100 us of wake-up latency on this box, a query loop ~10)."""
-        cat = torch.cat([t if t.dtype == torch.float64 else t.to(torch.float64) for t in tensors])
-        n = cat.numel()
-        if self.rb_host is None or self.rb_host.numel() < n:
-            self.rb_host = torch.empty((max(n, 4096),), dtype=torch.float64).pin_memory()
-            self.rb_event = torch.cuda.Event()
-        self.rb_host[:n].copy_(cat, non_blocking=True)
-        self.rb_event.record()
-        while not self.rb_event.query():
-            pass
-        return self.rb_host[:n].numpy().copy()
+    def readback(self, m, with_chol=True):
+        """The round's host sync.  A tiny kernel writes [seq | stats | info | acc[:m] | idx[:m]] straight into pinned
+        host memory and the host spins on the sequence word: no stream synchronisation (~100 us of wake-up latency
+        on this box), no staging copies.  Returns (stats[4], info[4], acc[m], idx[m]) as numpy arrays."""
+        need = 9 + 2 * m
+        if self.rb_host is None or self.rb_host.numel() < need:
+            self.rb_host = torch.zeros((max(need, 4096),), dtype=torch.float64).pin_memory()
+            self.rb_np = self.rb_host.numpy()
+            self.rb_seq = 0
+        self.rb_seq += 1
+        seq = float(self.rb_seq)
+        check(self.lib.rpc_publish_round(self.ctx.handle, _stream(), _ptr(self.stats), _ptr(self.info_dev) if with_chol else None,
+                                         _ptr(self.acc) if with_chol else None, _ptr(self.idx_dev), m,
+                                         C.c_void_p(self.rb_host.data_ptr()), seq), "rpc_publish_round")
+        buf = self.rb_np
+        spins = 0
+        while buf[0] != seq:
+            spins += 1
+            if spins & 0xFFFF == 0 and torch.cuda.current_stream().query():     # the stream drained without publishing
+                if buf[0] != seq:
+                    torch.cuda.synchronize(self.dev)                            # surfaces the CUDA error, if any
+                    if buf[0] != seq:
+                        raise RuntimeError("read-back kernel did not publish its result")
+        out = buf[1:need].copy()
+        return out[0:4], out[4:8].astype(np.int64), out[8:8 + m].astype(np.int64), out[8 + m:8 + 2 * m].astype(np.int64)
 
     # ---- thin wrappers over the C ABI ------------------------------------------------------------
     def upload_uniforms(self, up, ur=None):
@@ -353,15 +364,14 @@ def block_cholesky_helper(A, k, b, alg, stoptol=1e-14, strategy="regularize", rb
         up = rng.random(2 * block_size)                        # rng.choice(..., size=2*block_size) (:91)
         st.upload_uniforms(up)
         st.sample(2 * block_size)
-        host = st.readback([st.stats, st.idx_dev[:2 * block_size]])                                  # one sync
-        stats_host = host[:4]
+        stats_host, _, _, drawn = st.readback(2 * block_size, with_chol=False)                     # one sync
         _raise_if_invalid(stats_host)
         if orig_trace is None:
             orig_trace = float(stats_host[0])
         elif stoptol > 0 and float(stats_host[0]) <= stoptol * orig_trace:     # :133-136, checked after the previous block
             count = counter
             break
-        idx = np.unique(host[4:].astype(np.int64))[:block_size]                # :92
+        idx = np.unique(drawn)[:block_size]                                   # :92
         block_size = len(idx)
         arr_idx.extend(idx)
         st.sel_host[:block_size] = torch.from_numpy(idx)
@@ -370,7 +380,7 @@ def block_cholesky_helper(A, k, b, alg, stoptol=1e-14, strategy="regularize", rb
         st.residual_block(st.sel_dev, block_size, counter, count=False)       # C of :103
         Hcopy = st.H[:block_size, :block_size].clone()
         st.cholesky(block_size, 1, block_size, EPS * b * scale, 0)            # :106
-        info = st.readback([st.info_dev])
+        _, info, _, _ = st.readback(0)
         if info[1] != 0:                                                       # :109-114
             warn("Cholesky failed in block partial Cholesky. Falling back to eigendecomposition")
             evals, evecs = torch.linalg.eigh(Hcopy)
@@ -424,8 +434,7 @@ def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
             st.residual_block(st.idx_dev, b, counter)              # :189
         with _timed("reject", b ** 3 / 3.0, 8.0 * b * b):
             st.cholesky(b, 0, k - counter, 0.0, b)                 # :190 + truncation :193-196
-        host = st.readback([st.stats, st.info_dev, st.acc[:b], st.idx_dev[:b]])     # the round's only sync
-        stats_host, info = host[:4], host[4:8].astype(np.int64)
+        stats_host, info, acc_host, idx_host = st.readback(b)                       # the round's only sync
         _raise_if_invalid(stats_host)
         if orig_trace is None:
             orig_trace = float(stats_host[0])
@@ -437,8 +446,8 @@ def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
         if info[2] != 0:
             raise RuntimeError("rejection_cholesky requires a strictly positive trace")      # :145
         num_sel = int(info[0])
-        accepted = host[8:8 + num_sel].astype(np.int64)
-        idx = host[8 + b:8 + 2 * b].astype(np.int64)[accepted]
+        accepted = acc_host[:num_sel]
+        idx = idx_host[accepted]
         arr_idx[counter:counter + num_sel] = idx
         t1 = time.perf_counter()
         if num_sel > 0:
