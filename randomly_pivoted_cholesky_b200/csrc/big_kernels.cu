@@ -47,8 +47,6 @@ typedef Cfg<2, 4, 4, 4> C64;    //  64 x 128
 typedef Cfg<1, 8, 4, 2> C32;    //  32 x 128
 typedef Cfg<1, 8, 2, 2> C16;    //  16 x 128
 
-int rpc_gemm_max_m(void) { return C256::M_TILE; }
-
 static int tile_rows_for(int m, bool fine = false) {
     if (fine && m > 128) return m <= 256 ? (m + 15) / 16 * 16 : 256;      // 144, 160, ..., 256
     const int tiles[] = {16, 32, 64, 96, 128, 160, 192, 224, 256};

@@ -11,10 +11,10 @@
 //   1. plain parallel sums give an approximate prefix P with a rigorous bound |c - P| <= delta*P;
 //   2. a chunk whose running sums provably stay in one binade and that holds no rounding tie is
 //      "regular": its exact contribution D = q * sum_j rne(x_j/q) is computed in parallel;
-//   3. one thread walks the chunks: carry += D (an exact fp64 add) for regular chunks and replays the
-//      few others (binade crossings, ties: ~20 per scan) element by element with real fp64 adds;
-//   4. each draw binary-searches the exact chunk carries with numpy's own predicate
-//      fl(c/c_last) <= u and replays one chunk sequentially to land on the element.
+//   3. one CTA walks the chunks: runs of regular chunks of one binade are folded with exact prefix sums, the
+//      few others (binade crossings, ties: ~20 per scan) are resolved with real fp64 adds at 8-element grain;
+//   4. each draw binary-searches the exact chunk carries with numpy's own predicate fl(c/c_last) <= u
+//      (as a division-free threshold test) and replays one chunk sequentially to land on the element.
 // The same machinery run on diag itself yields python's sum(diags) bit-exactly (stoptol tests,
 // rpcholesky.py:45,133,224, therefore agree with the reference too).
 #include "rpc_common.cuh"
@@ -22,12 +22,6 @@
 constexpr int SC_CH = 256;            // elements per chunk (one warp, 8 per lane)
 constexpr int SC_WARPS = 8;           // chunks per CTA in the parallel passes
 
-struct ScanBufs {
-    double *csum;     // [nch+1] approximate chunk sums -> exclusive prefix P
-    double *D;        // [nch]   exact chunk contribution (regular chunks)
-    int32_t *cls;     // [nch]   binade exponent e of a regular chunk, or INT_MIN if it must be replayed
-    double *cstart;   // [nch+1] exact sequential running sum before each chunk; [nch] = total
-};
 
 __device__ __forceinline__ double pow2d(int e) {   // 2^e for e in [-1022, 1023]
     return __longlong_as_double((long long)(e + 1023) << 52);

@@ -291,6 +291,12 @@ class KernelMatrix(AbstractPSDMatrix):
         med = vals[m // 2] if m % 2 else 0.5 * (vals[m // 2 - 1] + vals[m // 2])
         return float(med)
 
+    def trace(self):
+        # matrix.py:44-45 is python's sum(self.diag()); the built-in kernels have an all-ones diagonal (distance
+        # exactly 0), whose left-to-right float64 sum is exactly N -- same value, same query count, no O(N) host loop
+        self.queries += self.shape[0]
+        return np.float64(self.shape[0])
+
     # -- host-facing evaluation (numpy out) --------------------------------------------------------
     def _diag_helper(self, *args):
         if len(args) > 0:
