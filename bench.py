@@ -294,6 +294,7 @@ def gpu_arm(args, w):
         lra = step_fn(rpc, A, w)
         queries += A.num_queries()
         rank_k = lra.rank()
+        rounds = getattr(lra, "rounds", None)
         del lra
     e1.record()
     sync_all()
@@ -411,7 +412,7 @@ def gpu_arm(args, w):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": w["text"], "rank": rank_k, "l2": "inputs (G: %.1f GB) larger than L2" % (8e-9 * w["k"] * n),
+            "config": {"workload": w["text"], "rank": rank_k, "accepted_per_round": rounds, "l2": "inputs (G: %.1f GB) larger than L2" % (8e-9 * w["k"] * n),
                        "parallelism": "row-sharded x%d (N/%d points per GPU, NCCL diag all-gather + payload all-reduce per round)"
                        % (world, world) if world > 1 else "single GPU"},
             "wall_time_s": ms * 1e-3 / args.steps, "phase_ms_per_step": phase_ms, "dominant_kernel_launches_ms_tflops": detail,

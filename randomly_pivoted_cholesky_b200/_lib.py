@@ -114,7 +114,10 @@ def load():
         if _lib is not None:
             return _lib
         if _stale():
-            build()
+            have_nvcc = bool(shutil.which("nvcc")) or os.path.exists("/usr/local/cuda/bin/nvcc")
+            if have_nvcc or not os.path.exists(LIB_PATH):
+                build()                          # raises if nvcc is missing: there is nothing else to run
+            # else: a prebuilt library travelled with the tree (file times may be newer than it): use it
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(lib, name)          # AttributeError if the symbol is missing: fail loudly

@@ -36,11 +36,13 @@ typedef Cfg<4, 2, 8, 4> C256;   // 256 x 64
 typedef Cfg<4, 2, 7, 4> C224;   // 224 x 64
 typedef Cfg<4, 2, 6, 4> C192;   // 192 x 64
 typedef Cfg<4, 2, 5, 4> C160;   // 160 x 64
-// 16-row steps between the 32-row tiles: two warp rows of MI fragments, four warp columns (Schur update only)
-typedef Cfg<2, 4, 15, 2> C240;  // 240 x 64
-typedef Cfg<2, 4, 13, 2> C208;  // 208 x 64
-typedef Cfg<2, 4, 11, 2> C176;  // 176 x 64
-typedef Cfg<2, 4, 9, 2> C144;   // 144 x 64
+// above 128 rows: 2 x 4 warps of (MI x 2) fragments, N tile 64; ODD tiles give 8-row steps (Schur update only)
+#define RPC_FINE_TILES(X) X(136, 9, true) X(144, 9, false) X(152, 10, true) X(160, 10, false) X(168, 11, true) \
+    X(176, 11, false) X(184, 12, true) X(192, 12, false) X(200, 13, true) X(208, 13, false) X(216, 14, true) \
+    X(224, 14, false) X(232, 15, true) X(240, 15, false) X(248, 16, true)
+#define RPC_DECL_TILE(M, MI, ODD) typedef Cfg<2, 4, MI, 2, ODD> F##M;
+RPC_FINE_TILES(RPC_DECL_TILE)
+#undef RPC_DECL_TILE
 typedef Cfg<2, 4, 8, 4> C128;   // 128 x 128
 typedef Cfg<2, 4, 6, 4> C96;    //  96 x 128
 typedef Cfg<2, 4, 4, 4> C64;    //  64 x 128
@@ -48,7 +50,7 @@ typedef Cfg<1, 8, 4, 2> C32;    //  32 x 128
 typedef Cfg<1, 8, 2, 2> C16;    //  16 x 128
 
 static int tile_rows_for(int m, bool fine = false) {
-    if (fine && m > 128) return m <= 256 ? (m + 15) / 16 * 16 : 256;      // 144, 160, ..., 256
+    if (fine && m > 128) return m <= 256 ? (m + 7) / 8 * 8 : 256;         // 136, 144, ..., 256
     const int tiles[] = {16, 32, 64, 96, 128, 160, 192, 224, 256};
     for (int t : tiles) if (m <= t) return t;
     return 256;
@@ -58,10 +60,9 @@ template <int MODE>
 static int dispatch_gemm(rpc_ctx *ctx, cudaStream_t st, const Params &p, int m, int64_t n_pad) {
     if (MODE == MODE_SCHUR) {
         switch (tile_rows_for(m, true)) {
-            case 144: return launch_gemm<C144, MODE_SCHUR>(ctx, st, p, n_pad);
-            case 176: return launch_gemm<C176, MODE_SCHUR>(ctx, st, p, n_pad);
-            case 208: return launch_gemm<C208, MODE_SCHUR>(ctx, st, p, n_pad);
-            case 240: return launch_gemm<C240, MODE_SCHUR>(ctx, st, p, n_pad);
+#define RPC_CASE_TILE(M, MI, ODD) case M: return launch_gemm<F##M, MODE_SCHUR>(ctx, st, p, n_pad);
+            RPC_FINE_TILES(RPC_CASE_TILE)
+#undef RPC_CASE_TILE
             default: break;
         }
     }
@@ -82,10 +83,9 @@ static int dispatch_gemm(rpc_ctx *ctx, cudaStream_t st, const Params &p, int m, 
 static int panel_ld_for(int m, bool fine = false) {
     if (fine) {
         switch (tile_rows_for(m, true)) {
-            case 144: return C144::LDA;
-            case 176: return C176::LDA;
-            case 208: return C208::LDA;
-            case 240: return C240::LDA;
+#define RPC_LD_TILE(M, MI, ODD) case M: return F##M::LDA;
+            RPC_FINE_TILES(RPC_LD_TILE)
+#undef RPC_LD_TILE
             default: break;
         }
     }

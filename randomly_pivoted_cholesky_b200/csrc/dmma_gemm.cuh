@@ -28,13 +28,17 @@ constexpr int LDBK = KT + 4;    // point-major B stage: [n][LDBK]
 
 enum { MODE_SCHUR = 0, MODE_EVAL = 1, MODE_FUSED = 2, MODE_EVALX = 3 };   // EVALX: EVAL with the X tile resident (phase 1 of FUSED only)
 
-template <int WM_, int WN_, int MI_, int NI_>
+// ODD (only with WM == 2): the second warp row owns MI-1 fragments, so tiles come in 8-row steps.  The two warps an
+// SM sub-partition hosts (w and w+4) are then given different warp rows, which keeps the four DMMA pipes balanced.
+template <int WM_, int WN_, int MI_, int NI_, bool ODD_ = false>
 struct Cfg {
     static constexpr int WM = WM_, WN = WN_, MI = MI_, NI = NI_;
+    static constexpr bool ODD = ODD_;
+    static_assert(!ODD_ || (WM_ == 2 && WN_ == 4), "ODD tiles are 2 x 4 warps");
     static constexpr int CONSUMERS = WM * WN;                // consumer warps
     static constexpr int THREADS = (CONSUMERS + 4) * 32;     // + one producer warpgroup (one warp of it works)
     static_assert(CONSUMERS % 4 == 0, "consumer warps must form whole warpgroups (setmaxnreg, even SMSP load)");
-    static constexpr int M_TILE = WM * MI * 8;
+    static constexpr int M_TILE = (WM * MI - (ODD ? 1 : 0)) * 8;
     static constexpr int N_TILE = WN * NI * 8;
     static constexpr int LDA = (M_TILE % 16 == 0) ? M_TILE + 4 : M_TILE + 12;   // == 4 (mod 16)
     static constexpr int LDB = N_TILE + 4;
@@ -178,9 +182,10 @@ __device__ __forceinline__ void produce_stage(const Params &p, double *As, doubl
 
 // one k-stage of DMMAs with double-buffered fragments; `ksteps` (1..4) k4-steps hold non-zero panel rows.
 // BKIND 0: B stage is k-major [KT][LDB]; BKIND 1: point-major [N_TILE][LDBK]; BKIND 2: resident X tile [N_TILE][ldx]
-template <class C, int BKIND>
-__device__ __forceinline__ void consume_stage(double (&acc)[C::MI][C::NI][2], const double *As, const double *Bs, int ldx,
-                                              int lk, int ksteps, int mi_cnt) {
+template <class C, int BKIND, int CMI>
+__device__ __forceinline__ void consume_stage_n(double (&acc)[C::MI][C::NI][2], const double *As, const double *Bs, int ldx,
+                                                int lk, int ksteps) {
+    constexpr int mi_cnt = CMI;
     double a[2][C::MI], b[2][C::NI];
     auto ldb = [&](int j, int kk) -> double {
         if (BKIND == 0) return Bs[kk * C::LDB + j * 8];
@@ -210,6 +215,14 @@ __device__ __forceinline__ void consume_stage(double (&acc)[C::MI][C::NI][2], co
                 }
         }
     }
+}
+
+// warp rows of an ODD tile own MI or MI-1 fragments: two instantiations, chosen by a warp-uniform branch
+template <class C, int BKIND>
+__device__ __forceinline__ void consume_stage(double (&acc)[C::MI][C::NI][2], const double *As, const double *Bs, int ldx,
+                                              int lk, int ksteps, int mi_cnt) {
+    if (C::ODD && mi_cnt != C::MI) consume_stage_n<C, BKIND, (C::ODD ? C::MI - 1 : C::MI)>(acc, As, Bs, ldx, lk, ksteps);
+    else consume_stage_n<C, BKIND, C::MI>(acc, As, Bs, ldx, lk, ksteps);
 }
 
 // kernel values from the x.y accumulators -> Cout (MODE_EVAL and phase 1 of MODE_FUSED)
@@ -332,13 +345,21 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
 
     // ----------------------------------- consumer warps ------------------------------------------
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
-    const int wm = warp % C::WM, wn = warp / C::WM;
+    // Warp w runs on SM sub-partition w % 4.  ODD tiles pair an MI-fragment warp with an (MI-1)-fragment warp on every
+    // sub-partition: wm = (w + w/4) % 2.  (Dealing fragments at RUN time with predicated DMMAs was measured 2% slower
+    // than padding; here the fragment count is a compile-time constant of each branch.)
+    int wm, wn;
+    if (C::ODD) {
+        const int half = warp >> 2, sp = warp & 3;
+        wm = (sp + half) & 1;
+        wn = (sp >> 1) + 2 * half;
+    } else {
+        wm = warp % C::WM;
+        wn = warp / C::WM;
+    }
     const int n0 = wn * C::NI * 8;
     const int lr = lane >> 2, lk = lane & 3;
-    // Every warp row owns MI fragments of 8 rows.  (Dealing ceil(m/8) fragments unevenly over the warp rows, to
-    // get an 8-row instead of a 32-row tile granularity, was measured 2% SLOWER on B200: the predicated DMMAs cost
-    // more than the idle fragments they save -- profiles/schur_micro_r01.jsonl.)
-    constexpr int mi_cnt = C::MI;
+    const int mi_cnt = (C::ODD && wm == 1) ? C::MI - 1 : C::MI;
     const int m0 = wm * C::MI * 8;
     const int k_real = (MODE == MODE_EVAL) ? p.d : p.K;
 
