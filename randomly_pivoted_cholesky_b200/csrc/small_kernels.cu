@@ -280,8 +280,12 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rejection_cholesky_kernel(doubl
     const unsigned full = 0xffffffffu;
 
     if (PACKED) {
-        for (int i = warp; i < m; i += NW)
-            for (int l = lane; l <= i; l += 32) T[tri_at<true>(i, l, ld)] = H[(int64_t)i * ldh + l];
+        // flat, coalesced sweep over the m x m block with several independent loads in flight per thread
+#pragma unroll 4
+        for (int q = tid; q < m * m; q += RC_THREADS) {
+            const int i = q / m, l = q - i * m;
+            if (l <= i) T[tri_at<true>(i, l, ld)] = H[(int64_t)i * ldh + l];
+        }
     }
     // trace check (np.trace(H) <= 0 -> RuntimeError): only the sign matters, so the summation order does not
     if (warp == 0) {
@@ -419,6 +423,7 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rejection_cholesky_kernel(doubl
     }
     __syncthreads();
     // L = Lfull[acc, acc] (rpcholesky.py:155-156)
+#pragma unroll 4
     for (int q = tid; q < nacc * nacc; q += RC_THREADS) {
         int r = q / nacc, a = q - r * nacc;
         L[(int64_t)r * ldl + a] = a <= r ? Lfull[(size_t)accpos[r] * m + a] : 0.0;
