@@ -35,6 +35,9 @@ WORKLOADS = {
                text="configs[2]: block_rpcholesky b=200, Laplace sigma=d, N=1e6 d=50 k=2000, fp64"),
     "c2": dict(alg="accelerated", kernel="gaussian", N=100_000, d=20, k=1000, b=120, bw="sqrtd",
                text="configs[1]: accelerated_rpcholesky b=120, Gaussian sigma=sqrt(d), N=1e5 d=20 k=1000, fp64"),
+    "c4": dict(alg="accelerated", kernel="matern", kw={"nu": 2.5}, N=4_000_000, d=3, k=4000, b=400, bw="sqrtd",
+               text="configs[3]: accelerated_rpcholesky b=400, Matern-5/2 sigma=sqrt(d), N=4e6 d=3 k=4000, fp64 "
+                    "(256 GB of factors: needs >= 2 GPUs, meant for 8)"),
     "c5": dict(alg="krr", kernel="laplace", N=100_000, d=750, k=1000, b=100, bw=5120.0, nt=10_000, lamb=1e-8,
                text="configs[4]: KRR_Nystrom (accelerated_rpcholesky b=100 + normal-equation solve + prediction of 1e4 points), "
                     "Laplace sigma=5120, N=1e5 d=750 k=1000, synthetic QM9-shaped features, fp64"),
@@ -71,7 +74,7 @@ def make_points(n, d):
 def run_oracle(w, n_sample):
     from oracle import rpc_oracle as orc
     X = make_points(n_sample, w["d"])
-    A = orc.OracleKernelMatrix(X, kernel=w["kernel"], bandwidth=bandwidth(w))
+    A = orc.OracleKernelMatrix(X, kernel=w["kernel"], bandwidth=bandwidth(w), **w.get("kw", {}))
     rng, legacy = orc.make_streams(SEED)
     if w["alg"] == "krr":
         from oracle import krr_oracle
@@ -263,7 +266,10 @@ def gpu_arm(args, w):
             A_.q = model.queries
             return _KrrResult(model, preds, w_["k"])
     else:
-        A = rpc.KernelMatrix(Xpin, kernel=w["kernel"], bandwidth=bandwidth(w), device=dev, sharded=sharded)
+        need_gb = 16e-9 * w["k"] * n / world
+        if need_gb > 150:
+            raise SystemExit("workload %s needs %.0f GB of factors per GPU at %d GPU(s): run it with more GPUs" % (args.workload, need_gb, world))
+        A = rpc.KernelMatrix(Xpin, kernel=w["kernel"], bandwidth=bandwidth(w), device=dev, sharded=sharded, **w.get("kw", {}))
         step_fn = factorise
 
     def sync_all():
@@ -381,7 +387,7 @@ def gpu_arm(args, w):
             d2h = idx.nbytes + 8 + lra.preds.nbytes + lra.model.sol.nbytes
             del lra
             continue
-        A2 = rpc.KernelMatrix(Xpin, kernel=w["kernel"], bandwidth=bandwidth(w), device=dev, sharded=sharded)
+        A2 = rpc.KernelMatrix(Xpin, kernel=w["kernel"], bandwidth=bandwidth(w), device=dev, sharded=sharded, **w.get("kw", {}))
         lra = step_fn(rpc, A2, w)
         idx = np.asarray(lra.idx)
         err = (n - lra.trace()) / n                      # utils.approximation_error with trace(A) = N
