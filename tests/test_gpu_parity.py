@@ -387,3 +387,81 @@ def test_exact_krr_small(rpc):
     Kx = orc.gaussian_mtx(X, X, bandwidth=1.5)
     want = orc.gaussian_mtx(Xt, X, bandwidth=1.5) @ np.linalg.solve(Kx + 1e-4 * 300 * np.eye(300), y)
     np.testing.assert_allclose(model.predict(Xt), want, rtol=1e-7, atol=1e-8)
+
+
+# ---- edge cases: tiny and ragged problems, exhausted matrices, error behaviour equal to the reference's ----------------
+@pytest.mark.parametrize("n,d,k,b", [(5, 2, 3, 2), (130, 3, 1, 1), (129, 4, 40, 200), (257, 2, 30, 7), (1000, 6, 64, 64)])
+def test_tiny_and_ragged_sizes(rpc, n, d, k, b):
+    X = np.random.default_rng(n).standard_normal((n, d))
+    bw = 1.3
+    for alg in ("accel", "block", "simple"):
+        A = rpc.KernelMatrix(X, kernel="gaussian", bandwidth=bw)
+        A0 = orc.OracleKernelMatrix(X, kernel="gaussian", bandwidth=bw)
+        rng, legacy = orc.make_streams(3)
+        with replay(3):
+            if alg == "accel":
+                lra = rpc.accelerated_rpcholesky(A, k, b=b)
+                ref = orc.accelerated_rpcholesky(A0, k, b, rng, legacy)
+            elif alg == "block":
+                lra = rpc.block_rpcholesky(A, k, b=b)
+                ref = orc.block_rpcholesky(A0, k, b, rng)
+            else:
+                lra = rpc.simple_rpcholesky(A, k)
+                ref = orc.simple_rpcholesky(A0, k, rng)
+        assert [int(i) for i in lra.idx] == [int(i) for i in ref.idx], alg
+        assert lra.G.shape == ref.G.shape
+        assert relerr(lra.rows, ref.rows) <= F_TOL
+        assert relerr(lra.G.T @ lra.G, ref.G.T @ ref.G) <= 1e-9
+        assert relerr(lra.G, ref.G) <= 1e-9
+        assert A.num_queries() == A0.num_queries()
+
+
+def test_exhausted_matrix_raises_like_the_reference(rpc):
+    """20 distinct points repeated 10 times: the kernel matrix has rank 20.  The reference stops early through stoptol
+    (block / accelerated) or runs into Generator.choice's ValueError (simple, stoptol = 0); so must we."""
+    base = np.random.default_rng(5).standard_normal((20, 3))
+    X = np.tile(base, (10, 1))
+    A0 = orc.OracleKernelMatrix(X, kernel="gaussian", bandwidth=1.0)
+    rng, legacy = orc.make_streams(9)
+    ref = orc.accelerated_rpcholesky(A0, 60, 15, rng, legacy)
+    with replay(9):
+        lra = rpc.accelerated_rpcholesky(rpc.KernelMatrix(X, kernel="gaussian", bandwidth=1.0), 60, b=15)
+    assert lra.G.shape == ref.G.shape and lra.G.shape[0] < 60          # early stop at the same round
+    n_ok = 18
+    assert np.array_equal(np.asarray(lra.idx)[:n_ok], ref.idx[:n_ok])
+    # greedy on a dense rank-deficient matrix keeps going on round-off, like the reference; simple 'rp' with an exactly
+    # exhausted diagonal raises ValueError
+    Z = np.zeros((40, 40)); Z[:4, :4] = np.diag([4.0, 9.0, 16.0, 1.0])        # perfect squares: the residual hits exactly 0
+    with pytest.raises(ValueError):
+        rpc.simple_rpcholesky(Z, 8)
+    with pytest.raises(ValueError):
+        orc.simple_rpcholesky(orc.OracleDenseMatrix(Z), 8, np.random.default_rng(0))
+    g = rpc.greedy(Z, 4)
+    assert list(g.idx) == [2, 1, 0, 3]
+
+
+def test_input_forms(rpc):
+    """float32 / non-contiguous / torch inputs, ndarray auto-wrapping, list and slice indexing of the operator."""
+    rng = np.random.default_rng(8)
+    X64 = rng.standard_normal((300, 5))
+    A = rpc.KernelMatrix(np.asfortranarray(X64), kernel="laplace", bandwidth=2.0)
+    B = rpc.KernelMatrix(torch.from_numpy(X64), kernel="laplace", bandwidth=2.0)
+    want = orc.laplace_mtx(X64, X64, bandwidth=2.0)
+    np.testing.assert_allclose(A[:, :], want, rtol=1e-13)
+    np.testing.assert_allclose(B[[3, 5], :], want[[3, 5], :], rtol=1e-13)
+    np.testing.assert_allclose(A[7, 9], want[7, 9], rtol=1e-13)
+    np.testing.assert_allclose(A[np.array([1, 2]), slice(10, 20)], want[1:3, 10:20], rtol=1e-13)
+    np.testing.assert_allclose(A[4, :], want[4, :], rtol=1e-13)
+    with pytest.raises(RuntimeError):
+        A["a", 0]
+    assert A.trace() == 300.0 and isinstance(A.to_matrix(), rpc.PSDMatrix)
+    D = X64 @ X64.T
+    with replay(2):
+        a = rpc.rpcholesky(D.astype(np.float32).astype(np.float64), 4, b=2)
+    assert a.G.shape == (4, 300)
+    # median bandwidths (matrix.py:168-176)
+    from scipy.spatial.distance import cdist
+    M = rpc.KernelMatrix(X64, kernel="gaussian", bandwidth="median")
+    assert abs(M.bandwidth - np.median(cdist(X64, X64))) <= 1e-12
+    M1 = rpc.KernelMatrix(X64, kernel="laplace", bandwidth="approx_median")
+    assert abs(M1.bandwidth - np.median(cdist(X64, X64, "cityblock"))) <= 1e-12
