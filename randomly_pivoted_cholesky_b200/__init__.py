@@ -8,7 +8,7 @@ All numerical work is done by hand-written sm_100a CUDA kernels behind the C ABI
 (librpc_b200.so).  There is no CPU fallback: importing works anywhere, computing needs a B200.
 """
 from .lra import AbstractPSDLowRank, CompactEigenvalueDecomposition, PSDLowRank
-from .matrix import AbstractPSDMatrix, KernelMatrix, PSDMatrix
+from .matrix import AbstractPSDMatrix, KernelMatrix, NonsymmetricKernelMatrix, PSDMatrix
 from .KRR_Nystrom import KRR_Nystrom
 from .rpcholesky import (accelerated_rpcholesky, block_cholesky_helper, block_rpcholesky, cholesky_helper, greedy,
                          rpcholesky, simple_rpcholesky)
@@ -16,6 +16,6 @@ from ._lib import build, load, total_launches
 
 __all__ = [
     "AbstractPSDLowRank", "CompactEigenvalueDecomposition", "PSDLowRank", "AbstractPSDMatrix", "KernelMatrix",
-    "PSDMatrix", "KRR_Nystrom", "accelerated_rpcholesky", "block_cholesky_helper", "block_rpcholesky", "cholesky_helper", "greedy",
+    "PSDMatrix", "NonsymmetricKernelMatrix", "KRR_Nystrom", "accelerated_rpcholesky", "block_cholesky_helper", "block_rpcholesky", "cholesky_helper", "greedy",
     "rpcholesky", "simple_rpcholesky", "build", "load", "total_launches",
 ]

@@ -278,9 +278,8 @@ class KernelMatrix(AbstractPSDMatrix):
         n = self.shape[0]
         X = self._Xd[:n, :self.d]
         if mode == "approx_median":
-            if n > 1000:
-                sel = np.random.choice(n, 1000, replace=False)        # legacy global RNG, as matrix.py:172
-                X = X[torch.as_tensor(sel, device=self.device)]
+            sel = np.random.choice(n, size=min(n, 1000), replace=False)   # legacy global RNG, as matrix.py:172
+            X = X[torch.as_tensor(sel, device=self.device)]
         elif mode != "median":
             raise RuntimeError("Bandwidth {} not recognized".format(mode))
         if X.shape[0] > 30000:
@@ -303,12 +302,14 @@ class KernelMatrix(AbstractPSDMatrix):
             return np.ones(len(list(args[0])))
         return np.ones(self.shape[0])                # *_vec on identical points: exactly 1.0
 
-    def _cross(self, vec_i, vec_j):
-        """kernel_mtx(X[vec_i], X[vec_j]) as a (len(vec_i), len(vec_j)) numpy array."""
+    def _cross(self, vec_i, vec_j, other=None):
+        """kernel_mtx(X[vec_i], Y[vec_j]) as a (len(vec_i), len(vec_j)) numpy array; Y = `other`'s points (default:
+        this operator's own).  The rows X[vec_i] play the pivots of the row evaluator, Y the streamed points."""
         if self.shard_info.world > 1:
             raise NotImplementedError("host-side indexing A[i,j] of a sharded KernelMatrix is not supported; "
                                       "use the factorisation drivers (device protocol) or an unsharded operator")
-        n = self.shape[0]
+        tgt = self if other is None else other
+        n = tgt.shape[0]
         mi, mj = len(vec_i), len(vec_j)
         ti = torch.as_tensor(np.asarray(vec_i, dtype=np.int64), device=self.device)
         piv = _PivotPayload(mi, self.ldx, self.device)
@@ -316,14 +317,14 @@ class KernelMatrix(AbstractPSDMatrix):
         full = (mj == n) and (vec_j == list(range(n)) if mj < 4096 else
                               bool(np.array_equal(np.asarray(vec_j, dtype=np.int64), np.arange(n))))
         if full:
-            Y, ynorm, npad = self._Xd, self._xnorm, self.n_pad
+            Y, ynorm, npad = tgt._Xd, tgt._xnorm, tgt.n_pad
         else:
             tj = torch.as_tensor(np.asarray(vec_j, dtype=np.int64), device=self.device)
             npad = _round_up(mj, COL_ALIGN)
             Y = torch.zeros((npad, self.ldx), dtype=torch.float64, device=self.device)
-            Y[:mj] = self._Xd[tj]
+            Y[:mj] = tgt._Xd[tj]
             ynorm = torch.zeros((npad,), dtype=torch.float64, device=self.device)
-            ynorm[:mj] = self._xnorm[tj]
+            ynorm[:mj] = tgt._xnorm[tj]
         out = torch.empty((mi, npad), dtype=torch.float64, device=self.device)
         check(self._ctx.lib.rpc_kernel_rows(self._ctx.handle, _stream(), C.byref(self._spec), _ptr(Y), _ptr(ynorm), npad,
                                             self.d_pad, self.ldx, _ptr(piv.X), _ptr(piv.norm), mi, self.ldx,
@@ -343,8 +344,15 @@ class KernelMatrix(AbstractPSDMatrix):
             return mtx[:, 0]
         return mtx
 
-    def out_of_sample(self, Xtest):
-        raise NotImplementedError("NonsymmetricKernelMatrix (matrix.py:194-239) is outside the hot path (SURVEY.md section 8f)")
+    def _companion(self, X):
+        """A KernelMatrix over other points with this operator's kernel, bandwidth and device."""
+        return KernelMatrix(X, kernel=self.kernel_name, bandwidth=self.bandwidth, device=self.device, **self.kernel_kwargs)
+
+    def out_of_sample(self, Xtest, vec):
+        """kernel_mtx(Xtest, X[vec]) -> (len(Xtest), len(vec)) array (matrix.py:191-192)."""
+        vec = np.atleast_1d(np.asarray(vec, dtype=np.int64)).ravel().tolist()
+        Kt = self._companion(Xtest)
+        return np.ascontiguousarray(self._cross(vec, list(range(Kt.shape[0])), other=Kt).T)
 
     # -- device protocol ---------------------------------------------------------------------------
     def _dev_diag_into(self, diag):
@@ -375,3 +383,44 @@ class KernelMatrix(AbstractPSDMatrix):
 
     def _simple_step_args(self):
         return self._spec, self._Xd, self._xnorm, self.d_pad, self.ldx, None, 0
+
+
+class NonsymmetricKernelMatrix(object):
+    """K[i, j] = k(X[i], Y[j]) for two point sets (matrix.py:194-239): the cross-kernel operator the reference uses for
+    prediction.  Indexing accepts ints, lists, arrays and slices per axis and returns numpy, like the reference's."""
+
+    def __init__(self, X, Y, kernel="gaussian", bandwidth=1.0, device=None, **kwargs):
+        self.X = X
+        self.Y = Y
+        self.shape = (X.shape[0], Y.shape[0])
+        self._Kx = KernelMatrix(X, kernel=kernel, bandwidth=bandwidth, device=device, **kwargs)
+        self._Ky = self._Kx._companion(Y)
+
+    def _getitem_helper(self, *args):
+        idx = args[0]
+        if len(idx) == 1:
+            idx = [idx, idx]
+        else:
+            idx = list(idx)
+        for j in range(2):
+            if isinstance(idx[j], np.ndarray):
+                idx[j] = idx[j].ravel().tolist()
+            elif isinstance(idx[j], slice):
+                idx[j] = list(range(self.shape[j]))[idx[j]]
+            elif isinstance(idx[j], list):
+                pass
+            elif isinstance(idx[j], numbers.Integral):
+                idx[j] = [idx[j]]
+            else:
+                raise RuntimeError("Indexing not implemented with index of type {}".format(type(idx)))
+        mtx = self._Kx._cross(idx[0], idx[1], other=self._Ky)
+        if len(idx[0]) == 1 and len(idx[1]) == 1:
+            return mtx[0, 0]
+        if len(idx[0]) == 1:
+            return mtx[0, :]
+        if len(idx[1]) == 1:
+            return mtx[:, 0]
+        return mtx
+
+    def __getitem__(self, *args):
+        return self._getitem_helper(*args)

@@ -465,3 +465,20 @@ def test_input_forms(rpc):
     assert abs(M.bandwidth - np.median(cdist(X64, X64))) <= 1e-12
     M1 = rpc.KernelMatrix(X64, kernel="laplace", bandwidth="approx_median")
     assert abs(M1.bandwidth - np.median(cdist(X64, X64, "cityblock"))) <= 1e-12
+
+
+def test_nonsymmetric_kernel_matrix_and_out_of_sample(rpc):
+    """matrix.py:191-239: the cross-kernel operator used for prediction."""
+    rng = np.random.default_rng(21)
+    X = rng.standard_normal((70, 5)); Y = rng.standard_normal((310, 5))
+    for kernel, kw, ref in [("gaussian", {}, orc.gaussian_mtx), ("laplace", {}, orc.laplace_mtx),
+                            ("matern", {"nu": 1.5}, orc.matern_mtx)]:
+        K = rpc.NonsymmetricKernelMatrix(X, Y, kernel=kernel, bandwidth=1.7, **kw)
+        want = ref(X, Y, bandwidth=1.7, **kw)
+        assert K.shape == (70, 310)
+        np.testing.assert_allclose(K[:, :], want, rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(K[[3, 9], :], want[[3, 9], :], rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(K[5, 7], want[5, 7], rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(K[:, np.array([1, 300])], want[:, [1, 300]], rtol=1e-12, atol=1e-14)
+        A = rpc.KernelMatrix(Y, kernel=kernel, bandwidth=1.7, **kw)
+        np.testing.assert_allclose(A.out_of_sample(X, [4, 8, 15]), want[:, [4, 8, 15]], rtol=1e-12, atol=1e-14)
