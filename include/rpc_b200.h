@@ -181,6 +181,14 @@ int rpc_simple_step(rpc_ctx *ctx, void *stream, const rpc_kernel_spec *spec, con
                     int64_t ldx, const double *A, int64_t lda, int64_t n, const int64_t *idx_dev, int i, double *G,
                     int64_t ldg, double *rows, int64_t ldr, double *diag, int64_t n_pad);
 
+/* Steps [i0, i1) of the simple loop (rpcholesky.py:29-43) enqueued by one call: per step rpc_sample_pivots with the
+ * pre-uploaded uniform u_all[i] (greedy != 0: rpc_argmax, rpcholesky.py:35) into idx_all[i], then rpc_simple_step.
+ * stats_all holds 4 doubles per step (the sampler status of that step; for greedy [max, #ties]). */
+int rpc_simple_run(rpc_ctx *ctx, void *stream, int greedy, const rpc_kernel_spec *spec, const double *X, const double *xnorm,
+                   int d, int64_t ldx, const double *A, int64_t lda, int64_t n, const double *u_all, int64_t *idx_all,
+                   double *stats_all, int i0, int i1, double *G, int64_t ldg, double *rows, int64_t ldr, double *diag,
+                   int64_t n_pad);
+
 #ifdef __cplusplus
 }
 #endif

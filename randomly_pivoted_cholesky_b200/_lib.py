@@ -100,6 +100,8 @@ _SIGNATURES = {
     "rpc_fused_update_supported": (_INT, [C.POINTER(KernelSpec), _INT, _I64]),
     "rpc_fused_update": (_INT, [_P, _P, C.POINTER(KernelSpec), _P, _P, _I64, _INT, _I64, _P, _P, _I64, _P, _I64, _INT, _INT, _P,
                                 _I64, _INT, _P, _I64, _P]),
+    "rpc_simple_run": (_INT, [_P, _P, _INT, C.POINTER(KernelSpec), _P, _P, _INT, _I64, _P, _I64, _I64, _P, _P, _P, _INT, _INT, _P,
+                              _I64, _P, _I64, _P, _I64]),
     "rpc_simple_step": (_INT, [_P, _P, C.POINTER(KernelSpec), _P, _P, _INT, _I64, _P, _I64, _I64, _P, _INT, _P, _I64, _P,
                                _I64, _P, _I64]),
 }

@@ -424,3 +424,24 @@ extern "C" int rpc_simple_step(rpc_ctx *ctx, void *stream, const rpc_kernel_spec
     RPC_CUDA(cudaMemcpyAsync(diag, ctx->ws, (size_t)n_pad * sizeof(double), cudaMemcpyDeviceToDevice, st));
     return 0;
 }
+
+// The whole simple-RPCholesky / greedy loop (rpcholesky.py:29-43) enqueued by ONE host call: steps [i0, i1) of
+// sample-or-argmax -> fused step.  The uniforms were uploaded in bulk (the proposal stream is state independent) and
+// nothing is read back, so the k steps run back to back on the stream without any host involvement; stats row i
+// (4 doubles) keeps the sampler status of step i for the caller to inspect afterwards.
+extern "C" int rpc_simple_run(rpc_ctx *ctx, void *stream, int greedy, const rpc_kernel_spec *spec, const double *X,
+                              const double *xnorm, int d, int64_t ldx, const double *A, int64_t lda, int64_t n,
+                              const double *u_all, int64_t *idx_all, double *stats_all, int i0, int i1, double *G,
+                              int64_t ldg, double *rows, int64_t ldr, double *diag, int64_t n_pad) {
+    RPC_CHECK_ARG(ctx && idx_all && stats_all && G && rows && diag, "null pointer");
+    RPC_CHECK_ARG(greedy || u_all, "uniforms required for randomly pivoted steps");
+    RPC_CHECK_ARG(i0 >= 0 && i1 >= i0, "bad step range");
+    for (int i = i0; i < i1; ++i) {
+        int rc = greedy ? rpc_argmax(ctx, stream, diag, n, idx_all + i, stats_all + 4 * (int64_t)i)
+                        : rpc_sample_pivots(ctx, stream, diag, n_pad, u_all + i, 1, idx_all + i, stats_all + 4 * (int64_t)i);
+        if (rc) return rc;
+        rc = rpc_simple_step(ctx, stream, spec, X, xnorm, d, ldx, A, lda, n, idx_all, i, G, ldg, rows, ldr, diag, n_pad);
+        if (rc) return rc;
+    }
+    return 0;
+}

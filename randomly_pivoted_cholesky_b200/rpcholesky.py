@@ -299,7 +299,14 @@ def cholesky_helper(A, k, alg, stoptol=0):
                 cand = torch.nonzero(st.diag[:st.n] == mx).flatten().cpu().numpy()
                 idx_all[i] = int(rng.choice(cand))
 
-    for i in range(k):
+    fast = (not check_every_step) and alg in ("rp", "greedy")
+    if fast:
+        # no stoptol test and no host-side tie break: the whole loop is enqueued by one native call
+        check(lib.rpc_simple_run(ctx.handle, _stream(), 1 if alg == "greedy" else 0, spec_ref, _ptr(X), _ptr(xn), d, ldx,
+                                 _ptr(Ad), lda, st.n, _ptr(u_all), _ptr(idx_all), _ptr(stats_all), 0, k, _ptr(st.G), st.n_pad,
+                                 _ptr(st.rows), st.n_pad, _ptr(st.diag), st.n_pad), "rpc_simple_run")
+        A._count(k * st.n)
+    for i in range(0 if not fast else k, k):
         if alg == "rp":
             sample_into(i, 1)
         else:
