@@ -132,6 +132,19 @@ int rpc_gram_residual(rpc_ctx *ctx, void *stream, const double *P, int c, int m,
 int rpc_rejection_cholesky(rpc_ctx *ctx, void *stream, double *H, int m, int64_t ldh, const double *u, int max_accept,
                            int mode, double shift, double *L, int64_t ldl, int32_t *acc, int32_t *info);
 
+/* RBRP block pivoting: `_greedy_cholesky(H, rtol, atol)` (rpcholesky.py:52-63), i.e. LAPACK dpstrf(lower) -- diagonal
+ * pivoting on the first maximum of the residual diagonal, stop when it falls to m*eps*max(diag H) -- followed, when
+ * use_tol != 0, by rank = argmax(trace - cumsum(norm(L,axis=0)**2) < atol + rtol*trace) + 1.  H (m x m, symmetric) is not
+ * modified.  acc[0:rank] = the pivot positions piv[0:rank]-1 (rpcholesky.py:118), L (ldl >= m) = the rank x rank leading
+ * block of the factor in pivoted order (zeros above the diagonal), info[0] = rank. */
+int rpc_pivoted_cholesky(rpc_ctx *ctx, void *stream, const double *H, int m, int64_t ldh, int use_tol, double rtol,
+                         double atol, double *L, int64_t ldl, int32_t *acc, int32_t *info);
+
+/* Block-greedy pivots: idx[0:b] = the positions of the b largest entries of diag[0:n], i.e. the SET returned by
+ * np.argpartition(diags, -b)[-b:] (rpcholesky.py:94-95), in ascending index order; among entries tied at the threshold
+ * the lowest indices are kept (numpy's choice there is an artefact of its introselect). */
+int rpc_select_largest(rpc_ctx *ctx, void *stream, const double *diag, int64_t n, int b, int64_t *idx);
+
 /* Panel for the fused Schur update.  With Minv = L^{-1} (mode 0) or Minv = T given (mode 1, the
  * eigh fallback of rpcholesky.py:109-114):
  *    At[r, j]     = -sum_i P[r, acc[i]] * Minv[j, i]   r < c       (= -(P_acc Minv^T))

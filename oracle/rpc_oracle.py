@@ -278,8 +278,23 @@ def simple_rpcholesky(A, k, rng, stoptol=0, alg="rp"):
     return OracleResult(G, arr_idx, rows)
 
 
-def block_rpcholesky(A, k, b, rng, stoptol=1e-14):
-    """block_cholesky_helper(A, k, b, 'rp', strategy='regularize') -- rpcholesky.py:65-138."""
+def _greedy_cholesky(H, rtol=None, atol=None):
+    """_greedy_cholesky -- rpcholesky.py:52-63 (LAPACK dpstrf through scipy, like the reference)."""
+    from scipy.linalg import get_lapack_funcs
+    pstrf = get_lapack_funcs("pstrf", dtype=np.float64)
+    trace = np.trace(H)
+    L, piv, rank, info = pstrf(H, lower=True)
+    L = np.tril(L)
+    if not (rtol is None) and not (atol is None):
+        trailing_sums = trace - np.cumsum(np.linalg.norm(L, axis=0) ** 2)
+        rank = np.argmax(trailing_sums < (atol + rtol * trace)) + 1
+    return L, piv, rank
+
+
+def block_rpcholesky(A, k, b, rng, stoptol=1e-14, strategy="regularize", rbrp_atol=0.0, rbrp_rtol="1/b", alg="rp"):
+    """block_cholesky_helper(A, k, b, alg, stoptol, strategy, rbrp_atol, rbrp_rtol) -- rpcholesky.py:65-138.
+    alg 'greedy' takes the block_size largest residuals (:94-95) in ascending index order: numpy's argpartition order
+    (and its choice among ties) is an implementation detail that the device path does not reproduce."""
     A = _as_operator(A)
     diags = A.diag().copy()
     n = A.shape[0]
@@ -287,32 +302,52 @@ def block_rpcholesky(A, k, b, rng, stoptol=1e-14):
     scale = 2 * max(diags)                                                     # :72
     if stoptol is None:
         stoptol = 1e-14
+    if rbrp_rtol == "1/b":
+        rbrp_rtol = 1.0 / b                                                    # :75-76
     G = np.zeros((k, n))
     rows = np.zeros((k, n))
     arr_idx = []
     counter = 0
     while counter < k:
         block_size = min(k - counter, b)
-        idx = sample_pivots(diags, rng.random(2 * block_size))                # :91
-        idx = np.unique(idx)[:block_size]                                      # :92
-        block_size = len(idx)
-        arr_idx.extend(idx)
-        rows[counter:counter + block_size, :] = A.rows(idx)                    # :101
-        G[counter:counter + block_size, :] = (
-            rows[counter:counter + block_size, :] - G[0:counter, idx].T @ G[0:counter, :])  # :102
-        C = G[counter:counter + block_size, idx]                               # :103
-        try:
-            L = np.linalg.cholesky(C + EPS * b * scale * np.identity(block_size))  # :106
-            G[counter:counter + block_size, :] = np.linalg.solve(L, G[counter:counter + block_size, :])  # :107
-        except np.linalg.LinAlgError:                                          # :109-114
-            warnings.warn("Cholesky failed in block partial Cholesky. Falling back to eigendecomposition")
-            evals, evecs = np.linalg.eigh(C)
-            evals[evals > 0] = evals[evals > 0] ** (-0.5)
-            evals[evals < 0] = 0
-            G[counter:counter + block_size, :] = evals[:, np.newaxis] * (evecs.T @ G[counter:counter + block_size, :])
-        diags -= np.sum(G[counter:counter + block_size, :] ** 2, axis=0)       # :128
+        if alg == "rp":
+            idx = sample_pivots(diags, rng.random(2 * block_size))            # :91
+            idx = np.unique(idx)[:block_size]                                  # :92
+            block_size = len(idx)
+        elif alg == "greedy":
+            # the set of np.argpartition(diags, -block_size)[-block_size:], lowest indices among ties at the threshold
+            order = np.lexsort((np.arange(n), -diags))
+            idx = np.sort(order[:block_size])
+        else:
+            raise RuntimeError("Algorithm '{}' not recognized".format(alg))
+        if strategy in ("regularize", "regularized"):
+            arr_idx.extend(idx)
+            rows[counter:counter + block_size, :] = A.rows(idx)                # :101
+            G[counter:counter + block_size, :] = (
+                rows[counter:counter + block_size, :] - G[0:counter, idx].T @ G[0:counter, :])  # :102
+            C = G[counter:counter + block_size, idx]                           # :103
+            try:
+                L = np.linalg.cholesky(C + EPS * b * scale * np.identity(block_size))  # :106
+                G[counter:counter + block_size, :] = np.linalg.solve(L, G[counter:counter + block_size, :])  # :107
+            except np.linalg.LinAlgError:                                      # :109-114
+                warnings.warn("Cholesky failed in block partial Cholesky. Falling back to eigendecomposition")
+                evals, evecs = np.linalg.eigh(C)
+                evals[evals > 0] = evals[evals > 0] ** (-0.5)
+                evals[evals < 0] = 0
+                G[counter:counter + block_size, :] = evals[:, np.newaxis] * (evecs.T @ G[counter:counter + block_size, :])
+        elif strategy in ("rbrp", "pivoting", "pivoted"):                      # :115-123
+            H = A.block(idx) - G[0:counter, idx].T @ G[0:counter, idx]
+            L, piv, rank = _greedy_cholesky(H, rtol=rbrp_rtol, atol=rbrp_atol)
+            idx = idx[piv[0:rank] - 1]
+            arr_idx.extend(idx)
+            rows[counter:counter + len(idx), :] = A.rows(idx)
+            G[counter:counter + len(idx), :] = rows[counter:counter + len(idx), :] - G[0:counter, idx].T @ G[0:counter, :]
+            G[counter:counter + len(idx), :] = np.linalg.solve(L[0:rank, 0:rank], G[counter:counter + len(idx), :])
+        else:
+            raise ValueError("'{}' is not a valid strategy for block RPCholesky".format(strategy))
+        diags -= np.sum(G[counter:counter + len(idx), :] ** 2, axis=0)         # :128
         diags = diags.clip(min=0)                                              # :129
-        counter += block_size
+        counter += len(idx)
         if stoptol > 0 and seq_sum(diags) <= stoptol * orig_trace:            # :133-136
             G = G[:counter, :]
             rows = rows[:counter, :]

@@ -766,3 +766,158 @@ extern "C" int rpc_publish_round(rpc_ctx *ctx, void *stream, const double *stats
     RPC_LAUNCHED(ctx);
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// RBRP: diagonally pivoted Cholesky of the b x b residual block (`_greedy_cholesky`, rpcholesky.py:52-63 = LAPACK
+// dpstrf(lower) + the trailing-sum rank rule).  ONE CTA, left-looking and swap free: step j takes the first maximum
+// of the residual diagonal a_ii - sum_a l_ia^2 (dpstf2's WORK recurrence, sequential in a), stops like dpstrf when it
+// falls to m * eps * max_i a_ii, and forms column j from row p of H and the columns computed so far.  The factor is kept
+// column-major (LfT[a][i]) so a column update reads coalesced rows.
+// ------------------------------------------------------------------------------------------------
+constexpr int PC_THREADS = 512;
+
+__global__ void __launch_bounds__(PC_THREADS, 1) pivoted_cholesky_kernel(const double *__restrict__ H, int m, int64_t ldh,
+                                                                        int use_tol, double rtol, double atol,
+                                                                        double *__restrict__ LfT, double *__restrict__ L,
+                                                                        int64_t ldl, int32_t *__restrict__ acc,
+                                                                        int32_t *__restrict__ info) {
+    extern __shared__ double psh[];
+    double *work = psh;                     // [m] sum_a l_ia^2
+    double *hd = work + m;                  // [m] a_ii
+    double *Lp = hd + m;                    // [m] row p of the factor (first j entries)
+    double *cn = Lp + m;                    // [m] squared column norms
+    int32_t *piv = (int32_t *)(cn + m);     // [m] pivot order
+    int32_t *chosen = piv + m;              // [m]
+    __shared__ double red_v[PC_THREADS / 32];
+    __shared__ int red_i[PC_THREADS / 32];
+    __shared__ double s_ajj, s_stop;
+    __shared__ int s_p, s_rank;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned full = 0xffffffffu;
+    for (int i = tid; i < m; i += PC_THREADS) {
+        work[i] = 0.0;
+        hd[i] = H[(int64_t)i * ldh + i];
+        chosen[i] = 0;
+    }
+    if (tid == 0) s_rank = m;
+    __syncthreads();
+    int rank = m;
+    for (int j = 0; j < m; ++j) {
+        // first maximum of the residual diagonal over the rows not chosen yet (Fortran MAXLOC; NaN never wins a '>')
+        double bv = -1.0 / 0.0;
+        int bi = 0x7fffffff;
+        bool nan_seen = false;
+        for (int i = tid; i < m; i += PC_THREADS) {
+            if (chosen[i]) continue;
+            const double v = hd[i] - work[i];
+            if (v != v) nan_seen = true;
+            if (v > bv || bi == 0x7fffffff) { if (v > bv || bi == 0x7fffffff) { bv = v; bi = i; } }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(full, bv, o);
+            const int oi = __shfl_xor_sync(full, bi, o);
+            if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+        }
+        nan_seen = __any_sync(full, nan_seen);
+        if (lane == 0) { red_v[warp] = nan_seen ? 0.0 / 0.0 : bv; red_i[warp] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            double v = -1.0 / 0.0;
+            int p = 0x7fffffff;
+            bool bad = false;
+            for (int w = 0; w < PC_THREADS / 32; ++w) {
+                if (red_i[w] == 0x7fffffff) continue;
+                if (red_v[w] != red_v[w]) { bad = true; continue; }
+                if (p == 0x7fffffff || red_v[w] > v || (red_v[w] == v && red_i[w] < p)) { v = red_v[w]; p = red_i[w]; }
+            }
+            if (j == 0) s_stop = (double)m * 2.220446049250313e-16 * v;     // dpstrf: DSTOP = N * eps * max diag (tol < 0)
+            // dpstrf tests the first pivot for <= 0 and the later ones against DSTOP
+            const bool stop = bad || p == 0x7fffffff || (j == 0 ? !(v > 0.0) : !(v > s_stop));
+            s_ajj = v;
+            s_p = stop ? -1 : p;
+            if (stop) s_rank = j;
+        }
+        __syncthreads();
+        const int p = s_p;
+        if (p < 0) { rank = j; break; }
+        const double ajj = sqrt(s_ajj);
+        for (int a = tid; a < j; a += PC_THREADS) Lp[a] = LfT[(size_t)a * m + p];
+        __syncthreads();
+        for (int i = tid; i < m; i += PC_THREADS) {
+            if (i == p) {
+                LfT[(size_t)j * m + i] = ajj;
+            } else if (!chosen[i]) {
+                // dgemv then dscal: column j = (H[:, p] - sum_a L[:, a] L[p, a]) * (1 / ajj)
+                double v = H[(int64_t)p * ldh + i];
+                for (int a = 0; a < j; ++a) v = fma(-LfT[(size_t)a * m + i], Lp[a], v);
+                const double l = v * (1.0 / ajj);
+                LfT[(size_t)j * m + i] = l;
+                work[i] += l * l;
+            } else {
+                LfT[(size_t)j * m + i] = 0.0;
+            }
+        }
+        if (tid == 0) { piv[j] = p; chosen[p] = 1; }
+        __syncthreads();
+    }
+    __syncthreads();
+    rank = s_rank;
+    if (use_tol && rank > 0) {
+        // rank = argmax(trace - cumsum(norm(L, axis=0)**2) < atol + rtol * trace) + 1   (rpcholesky.py:59-62); the column
+        // sums run over the rows in pivot order, like numpy's reduction along axis 0
+        for (int a = tid; a < rank; a += PC_THREADS) {
+            double s = 0.0;
+            for (int r = a; r < m; ++r) {
+                int row = -1;
+                if (r < rank) row = piv[r];
+                if (row >= 0) { const double x = LfT[(size_t)a * m + row]; s += x * x; }
+            }
+            // rows never chosen (rank < m) still carry their entries of the computed columns
+            if (rank < m)
+                for (int i = 0; i < m; ++i)
+                    if (!chosen[i]) { const double x = LfT[(size_t)a * m + i]; s += x * x; }
+            const double nrm = sqrt(s);
+            cn[a] = nrm * nrm;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double tr = 0.0;
+            for (int i = 0; i < m; ++i) tr += hd[i];
+            const double thr = atol + rtol * tr;
+            double cs = 0.0;
+            int newrank = 1;                     // np.argmax of an all-False array is 0
+            for (int a = 0; a < rank; ++a) {
+                cs += cn[a];
+                if (tr - cs < thr) { newrank = a + 1; break; }
+            }
+            s_rank = newrank;
+        }
+        __syncthreads();
+        rank = s_rank;
+    }
+    for (int q = tid; q < rank * rank; q += PC_THREADS) {
+        const int r = q / rank, a = q - r * rank;
+        L[(int64_t)r * ldl + a] = a <= r ? LfT[(size_t)a * m + piv[r]] : 0.0;
+    }
+    for (int q = tid; q < rank; q += PC_THREADS) acc[q] = piv[q];
+    if (tid == 0) { info[0] = rank; info[1] = 0; info[2] = 0; }
+}
+
+extern "C" int rpc_pivoted_cholesky(rpc_ctx *ctx, void *stream, const double *H, int m, int64_t ldh, int use_tol, double rtol,
+                                    double atol, double *L, int64_t ldl, int32_t *acc, int32_t *info) {
+    RPC_CHECK_ARG(ctx && H && L && acc && info, "null pointer");
+    RPC_CHECK_ARG(m >= 1 && m <= 4096 && ldh >= m && ldl >= m, "bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = rpc_ws_reserve(ctx, (size_t)m * m * sizeof(double));
+    if (rc) return rc;
+    const size_t shm = (size_t)m * (4 * sizeof(double) + 2 * sizeof(int32_t));
+    static size_t configured = 48 * 1024;
+    if (shm > configured) {
+        RPC_CUDA(cudaFuncSetAttribute(pivoted_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = 200 * 1024;
+    }
+    pivoted_cholesky_kernel<<<1, PC_THREADS, shm, st>>>(H, m, ldh, use_tol, rtol, atol, ctx->ws, L, ldl, acc, info);
+    RPC_LAUNCHED(ctx);
+    return 0;
+}

@@ -106,3 +106,33 @@ def schur_update(G, c, rows_new, P, L, diag, device=None):
     check(ctx.lib.rpc_schur_update(ctx.handle, _stream(), _ptr(G), G.stride(0), c, s, _ptr(At), ldat, k_pad, _ptr(rows_new),
                                    rows_new.stride(0), _ptr(diag), n_pad), "rpc_schur_update")
     return At
+
+
+def pivoted_cholesky(H, rtol=None, atol=None, device=None):
+    """`_greedy_cholesky(H, rtol, atol)` of rpcholesky.py:52-63 (dpstrf + trailing-sum rank rule).
+    Returns (L (rank x rank, pivoted order) tensor, pivot positions int64 numpy (0-based), rank)."""
+    dev = _cuda_device(device)
+    ctx = _ctx(dev)
+    Hd = _dev_f64(H, dev)
+    if Hd.ndim != 2 or Hd.shape[0] != Hd.shape[1]:
+        raise RuntimeError("pivoted_cholesky requires a square matrix")
+    m = Hd.shape[0]
+    L = torch.zeros((m, m), dtype=torch.float64, device=dev)
+    acc = torch.zeros((m,), dtype=torch.int32, device=dev)
+    info = torch.zeros((4,), dtype=torch.int32, device=dev)
+    use_tol = rtol is not None and atol is not None
+    check(ctx.lib.rpc_pivoted_cholesky(ctx.handle, _stream(), _ptr(Hd), m, m, 1 if use_tol else 0,
+                                       float(rtol) if use_tol else 0.0, float(atol) if use_tol else 0.0, _ptr(L), m,
+                                       _ptr(acc), _ptr(info)), "rpc_pivoted_cholesky")
+    rank = int(info[0])
+    return L[:rank, :rank], acc[:rank].cpu().numpy().astype(np.int64), rank
+
+
+def select_largest(diag, b, device=None):
+    """The set np.argpartition(diag, -b)[-b:] in ascending index order (lowest indices among ties at the threshold)."""
+    dev = _cuda_device(device)
+    ctx = _ctx(dev)
+    d = _dev_f64(diag, dev)
+    idx = torch.empty((b,), dtype=torch.int64, device=dev)
+    check(ctx.lib.rpc_select_largest(ctx.handle, _stream(), _ptr(d), d.numel(), int(b), _ptr(idx)), "rpc_select_largest")
+    return idx

@@ -347,19 +347,23 @@ def cholesky_helper(A, k, alg, stoptol=0):
 # block RPCholesky: block_cholesky_helper(A, k, b, 'rp', strategy='regularize') -- rpcholesky.py:65-138
 # --------------------------------------------------------------------------------------------------
 def block_cholesky_helper(A, k, b, alg, stoptol=1e-14, strategy="regularize", rbrp_atol=0.0, rbrp_rtol="1/b"):
-    if alg != "rp":
-        if alg == "greedy":
-            raise NotImplementedError("block greedy pivoting is outside the round-1 hot path")
+    if alg not in ("rp", "greedy"):
         raise RuntimeError("Algorithm '{}' not recognized".format(alg))
-    if strategy not in ("regularize", "rbrp"):
-        raise ValueError("Strategy '{}' not recognized".format(strategy))
-    if strategy == "rbrp":
-        raise NotImplementedError("strategy='rbrp' (LAPACK pstrf pivoting) is a SURVEY.md section 8(f) row")
+    if strategy in ("regularize", "regularized"):
+        rbrp = False
+    elif strategy in ("rbrp", "pivoting", "pivoted"):
+        rbrp = True
+    else:
+        raise ValueError("'{}' is not a valid strategy for block RPCholesky".format(strategy))
     A = _as_operator(A)
     if stoptol is None:
         stoptol = 1e-14
     b = int(b)
+    if rbrp_rtol == "1/b":                                                    # rpcholesky.py:75-76
+        rbrp_rtol = 1.0 / b
+    use_tol = rbrp_rtol is not None and rbrp_atol is not None                 # rpcholesky.py:56
     st = _State(A, k, 2 * min(b, k))
+    lib, ctx = st.lib, st.ctx
     scale = 2.0 * float(torch.max(rdist.gather_diag(st.info, st.diag, st.diag_full)))   # rpcholesky.py:72
     rng = np.random.default_rng()
     arr_idx = []
@@ -368,18 +372,45 @@ def block_cholesky_helper(A, k, b, alg, stoptol=1e-14, strategy="regularize", rb
     count = k
     while counter < k:
         block_size = min(k - counter, b)
-        up = rng.random(2 * block_size)                        # rng.choice(..., size=2*block_size) (:91)
-        st.upload_uniforms(up)
-        st.sample(2 * block_size)
-        stats_host, _, _, drawn = st.readback(2 * block_size, with_chol=False)                     # one sync
-        _raise_if_invalid(stats_host)
+        if alg == "rp":
+            up = rng.random(2 * block_size)                    # rng.choice(..., size=2*block_size) (:91)
+            st.upload_uniforms(up)
+            st.sample(2 * block_size)
+        else:
+            # np.argpartition(diags, -block_size)[-block_size:] (:94-95): the set of the block_size largest residuals
+            st.sample(0)                                       # python sum(diags) for the stoptol test
+            full = st.diag_full if st.info.world > 1 else st.diag   # gathered by st.sample
+            check(lib.rpc_select_largest(ctx.handle, _stream(), _ptr(full), st.n, block_size, _ptr(st.idx_dev)),
+                  "rpc_select_largest")
+        ndraw = 2 * block_size if alg == "rp" else block_size
+        stats_host, _, _, drawn = st.readback(ndraw, with_chol=False)                              # one sync
+        if alg == "rp":
+            _raise_if_invalid(stats_host)
         if orig_trace is None:
             orig_trace = float(stats_host[0])
         elif stoptol > 0 and float(stats_host[0]) <= stoptol * orig_trace:     # :133-136, checked after the previous block
             count = counter
             break
-        idx = np.unique(drawn)[:block_size]                                   # :92
+        idx = np.unique(drawn)[:block_size] if alg == "rp" else drawn          # :92
         block_size = len(idx)
+        if rbrp:
+            # :115-123: H = A[idx,idx] - G[:c,idx]^T G[:c,idx]; pivoted Cholesky; keep idx[piv[:rank]-1]
+            st.sel_host[:block_size] = torch.from_numpy(idx)
+            st.idx_dev[:block_size].copy_(st.sel_host[:block_size], non_blocking=True)
+            st.gather(st.idx_dev, block_size, counter)
+            st.residual_block(st.idx_dev, block_size, counter, count=True)
+            check(lib.rpc_pivoted_cholesky(ctx.handle, _stream(), _ptr(st.H), block_size, st.m_max, 1 if use_tol else 0,
+                                           float(rbrp_rtol) if use_tol else 0.0, float(rbrp_atol) if use_tol else 0.0,
+                                           _ptr(st.L), st.m_max, _ptr(st.acc), _ptr(st.info_dev)), "rpc_pivoted_cholesky")
+            _, info, acc_host, _ = st.readback(block_size)
+            rank = int(info[0])
+            if rank < 1:
+                raise RuntimeError("pivoted Cholesky of the residual block found no positive pivot")
+            idx = idx[acc_host[:rank]]
+            arr_idx.extend(idx)
+            st.update(counter, rank, st.acc, st.idx_dev)
+            counter += rank
+            continue
         arr_idx.extend(idx)
         st.sel_host[:block_size] = torch.from_numpy(idx)
         st.sel_dev[:block_size].copy_(st.sel_host[:block_size], non_blocking=True)
@@ -506,6 +537,13 @@ def greedy(A, k, randomized_tiebreaking=False, b=1, **kwargs):
     """rpcholesky.py:245-251.  b == 1: greedy / randomized-greedy pivoting through the simple loop."""
     if b == 1:
         return cholesky_helper(A, k, "rgreedy" if randomized_tiebreaking else "greedy", **kwargs)
-    # np.argpartition's order inside the selected block is an implementation detail of numpy's introselect, so the
-    # reference's block-greedy factor cannot be reproduced row for row; not built
-    raise NotImplementedError("block greedy pivoting (rpcholesky.py:94-95) is not built")
+    if randomized_tiebreaking:
+        warn("Randomized tiebreaking not implemented for block greedy method")
+    # np.argpartition's order inside the selected block (and its choice among entries tied at the threshold) is an
+    # implementation detail of numpy's introselect: the device returns the same SET in ascending index order
+    return block_cholesky_helper(A, k, b, "greedy", **kwargs)
+
+
+def block_greedy(A, k, b=100, stoptol=None):
+    """rpcholesky.py:259-260 (the reference's version raises NameError on an undefined `kwargs`; this is its intent)."""
+    return block_cholesky_helper(A, k, b, "greedy", stoptol=stoptol)

@@ -38,6 +38,16 @@ CASES = {
     "greedy_gauss":     dict(alg="greedy", N=450, d=5, kernel="gaussian", bw="sqrtd", k=28, seed=27),
     "greedy_dense":     dict(alg="greedy", N=130, dense_rank=50, k=24, seed=28),
     "rgreedy_laplace":  dict(alg="rgreedy", N=380, d=6, kernel="laplace", bw="d", k=22, seed=29),
+    # block strategies / block greedy (rpcholesky.py:94-95, 115-123): RBRP = pivoted Cholesky of the residual block
+    "rbrp_gauss":       dict(alg="block", N=700, d=6, kernel="gaussian", bw="sqrtd", k=60, b=20, seed=30,
+                             blockkw=dict(strategy="rbrp")),
+    "rbrp_laplace":     dict(alg="block", N=500, d=5, kernel="laplace", bw="d", k=45, b=16, seed=31,
+                             blockkw=dict(strategy="pivoting", rbrp_rtol=1e-3)),
+    "rbrp_matern_wide": dict(alg="block", N=900, d=3, kernel="matern", nu=1.5, bw="sqrtd", k=150, b=70, seed=32,
+                             blockkw=dict(strategy="rbrp", rbrp_rtol=1e-6, rbrp_atol=1e-9)),
+    "rbrp_lowrank":     dict(alg="block", N=200, dense_rank=12, k=40, b=10, seed=33, blockkw=dict(strategy="rbrp")),
+    "bgreedy_dense":    dict(alg="bgreedy", N=150, dense_rank=60, k=30, b=8, seed=34),
+    "bgreedy_rbrp":     dict(alg="bgreedy", N=160, dense_rank=70, k=36, b=12, seed=35, blockkw=dict(strategy="rbrp")),
 }
 
 KERNEL_CASES = {
@@ -99,7 +109,9 @@ def main():
             elif spec["alg"] == "simple":
                 lra = ref.simple_rpcholesky(A, spec["k"], **kw)
             elif spec["alg"] == "block":
-                lra = ref.block_rpcholesky(A, spec["k"], b=spec["b"], **kw)
+                lra = ref.block_rpcholesky(A, spec["k"], b=spec["b"], **kw, **spec.get("blockkw", {}))
+            elif spec["alg"] == "bgreedy":
+                lra = ref.greedy(A, spec["k"], b=spec["b"], **kw, **spec.get("blockkw", {}))
             else:
                 lra = ref.accelerated_rpcholesky(A, spec["k"], b=spec["b"], **kw)
         out = {"idx": np.asarray(lra.idx, dtype=np.int64), "G": lra.G, "rows": lra.rows, "trace": np.float64(lra.trace())}
