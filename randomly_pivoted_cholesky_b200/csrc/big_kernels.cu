@@ -394,20 +394,18 @@ __global__ void __launch_bounds__(SS_THREADS) simple_step_kernel(int has_spec, K
     }
 }
 
-extern "C" int rpc_simple_step(rpc_ctx *ctx, void *stream, const rpc_kernel_spec *spec, const double *X,
-                               const double *xnorm, int d, int64_t ldx, const double *A, int64_t lda, int64_t n,
-                               const int64_t *idx_dev, int i, double *G, int64_t ldg, double *rows, int64_t ldr,
-                               double *diag, int64_t n_pad) {
-    RPC_CHECK_ARG(ctx && idx_dev && G && rows && diag, "null pointer");
+// one step reading the residual diagonal from diag_in and writing the updated one to diag_out (the step reads
+// diag_in[piv] while other CTAs write the new diagonal, so the two must not alias)
+static int simple_step_launch(rpc_ctx *ctx, cudaStream_t st, const rpc_kernel_spec *spec, const double *X, const double *xnorm,
+                              int d, int64_t ldx, const double *A, int64_t lda, int64_t n, const int64_t *idx_dev, int i,
+                              double *G, int64_t ldg, double *rows, int64_t ldr, double *diag_in, double *diag_out,
+                              int64_t n_pad) {
+    RPC_CHECK_ARG(ctx && idx_dev && G && rows && diag_in && diag_out, "null pointer");
     RPC_CHECK_ARG((spec && X) || A, "either a kernel spec with X or a dense A is required");
     RPC_CHECK_ARG(i >= 0 && n_pad > 0 && n_pad % 2 == 0 && ldg % 2 == 0 && ldr % 2 == 0, "i >= 0, even n_pad / ldg / ldr");
     RPC_CHECK_ARG(!spec || d <= SS_MAXD, "d too large for the fused simple step");
-    cudaStream_t st = (cudaStream_t)stream;
     KernParams kp{};
     if (spec) kp = make_kern_params(spec);
-    // the step reads diag[piv] while other CTAs overwrite diag: double-buffer through the workspace
-    int rc = rpc_ws_reserve(ctx, (size_t)n_pad * sizeof(double));
-    if (rc) return rc;
     int grid = (int)((n_pad / 2 + SS_THREADS - 1) / SS_THREADS);
     int cap = ctx->sm_count * 8;
     if (grid > cap) grid = cap;
@@ -419,8 +417,22 @@ extern "C" int rpc_simple_step(rpc_ctx *ctx, void *stream, const rpc_kernel_spec
     }
     RPC_CHECK_ARG(shm <= 200 * 1024, "rank too large for the fused simple step");
     simple_step_kernel<<<grid, SS_THREADS, shm, st>>>(spec ? 1 : 0, kp, X, xnorm, d, ldx, A, lda, n, idx_dev, i, G, ldg,
-                                                      rows, ldr, diag, ctx->ws, n_pad);
+                                                      rows, ldr, diag_in, diag_out, n_pad);
     RPC_LAUNCHED(ctx);
+    return 0;
+}
+
+extern "C" int rpc_simple_step(rpc_ctx *ctx, void *stream, const rpc_kernel_spec *spec, const double *X,
+                               const double *xnorm, int d, int64_t ldx, const double *A, int64_t lda, int64_t n,
+                               const int64_t *idx_dev, int i, double *G, int64_t ldg, double *rows, int64_t ldr,
+                               double *diag, int64_t n_pad) {
+    RPC_CHECK_ARG(ctx && diag && n_pad > 0, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    // in-place semantics for the caller: double-buffer through the workspace
+    int rc = rpc_ws_reserve(ctx, (size_t)n_pad * sizeof(double));
+    if (rc) return rc;
+    rc = simple_step_launch(ctx, st, spec, X, xnorm, d, ldx, A, lda, n, idx_dev, i, G, ldg, rows, ldr, diag, ctx->ws, n_pad);
+    if (rc) return rc;
     RPC_CUDA(cudaMemcpyAsync(diag, ctx->ws, (size_t)n_pad * sizeof(double), cudaMemcpyDeviceToDevice, st));
     return 0;
 }
@@ -428,20 +440,31 @@ extern "C" int rpc_simple_step(rpc_ctx *ctx, void *stream, const rpc_kernel_spec
 // The whole simple-RPCholesky / greedy loop (rpcholesky.py:29-43) enqueued by ONE host call: steps [i0, i1) of
 // sample-or-argmax -> fused step.  The uniforms were uploaded in bulk (the proposal stream is state independent) and
 // nothing is read back, so the k steps run back to back on the stream without any host involvement; stats row i
-// (4 doubles) keeps the sampler status of step i for the caller to inspect afterwards.
+// (4 doubles) keeps the sampler status of step i for the caller to inspect afterwards.  The residual diagonal
+// ping-pongs between `diag` and a second buffer at the end of the workspace (no per-step copy).
 extern "C" int rpc_simple_run(rpc_ctx *ctx, void *stream, int greedy, const rpc_kernel_spec *spec, const double *X,
                               const double *xnorm, int d, int64_t ldx, const double *A, int64_t lda, int64_t n,
                               const double *u_all, int64_t *idx_all, double *stats_all, int i0, int i1, double *G,
                               int64_t ldg, double *rows, int64_t ldr, double *diag, int64_t n_pad) {
     RPC_CHECK_ARG(ctx && idx_all && stats_all && G && rows && diag, "null pointer");
     RPC_CHECK_ARG(greedy || u_all, "uniforms required for randomly pivoted steps");
-    RPC_CHECK_ARG(i0 >= 0 && i1 >= i0, "bad step range");
+    RPC_CHECK_ARG(i0 >= 0 && i1 >= i0 && n_pad > 0, "bad step range");
+    cudaStream_t st = (cudaStream_t)stream;
+    // the sampler / argmax scratch lives at the front of the workspace (never more than n_pad/8 + 4096 doubles); reserving
+    // the whole range first keeps ctx->ws fixed for the duration of the loop
+    const size_t front = ((size_t)n_pad / 8 + 4096 + 255) & ~(size_t)255;
+    int rc = rpc_ws_reserve(ctx, (front + (size_t)n_pad) * sizeof(double));
+    if (rc) return rc;
+    double *other = ctx->ws + front;
+    double *cur = diag, *nxt = other;
     for (int i = i0; i < i1; ++i) {
-        int rc = greedy ? rpc_argmax(ctx, stream, diag, n, idx_all + i, stats_all + 4 * (int64_t)i)
-                        : rpc_sample_pivots(ctx, stream, diag, n_pad, u_all + i, 1, idx_all + i, stats_all + 4 * (int64_t)i);
+        rc = greedy ? rpc_argmax(ctx, stream, cur, n, idx_all + i, stats_all + 4 * (int64_t)i)
+                    : rpc_sample_pivots(ctx, stream, cur, n_pad, u_all + i, 1, idx_all + i, stats_all + 4 * (int64_t)i);
         if (rc) return rc;
-        rc = rpc_simple_step(ctx, stream, spec, X, xnorm, d, ldx, A, lda, n, idx_all, i, G, ldg, rows, ldr, diag, n_pad);
+        rc = simple_step_launch(ctx, st, spec, X, xnorm, d, ldx, A, lda, n, idx_all, i, G, ldg, rows, ldr, cur, nxt, n_pad);
         if (rc) return rc;
+        double *t = cur; cur = nxt; nxt = t;
     }
+    if (cur != diag) RPC_CUDA(cudaMemcpyAsync(diag, cur, (size_t)n_pad * sizeof(double), cudaMemcpyDeviceToDevice, st));
     return 0;
 }

@@ -34,10 +34,8 @@ __device__ __forceinline__ double elem(const double *__restrict__ d, int64_t j, 
 
 // 1. approximate chunk sums (+ validity: NaN or negative entries make numpy raise ValueError)
 template <bool DIV>
-__global__ void __launch_bounds__(SC_WARPS * 32) sc_chunk_sums(const double *__restrict__ d, int64_t n, const double *Sptr,
-                                                                double *__restrict__ csum, int32_t *__restrict__ bad) {
-    const int lane = threadIdx.x & 31;
-    const int64_t k = (int64_t)blockIdx.x * SC_WARPS + (threadIdx.x >> 5);
+__device__ __forceinline__ void chunk_sums_body(const double *__restrict__ d, int64_t n, const double *Sptr,
+                                                double *__restrict__ csum, int32_t *__restrict__ bad, int64_t k, int lane) {
     const int64_t base = k * SC_CH;
     if (base >= n) return;
     const double S = DIV ? *Sptr : 1.0;
@@ -56,8 +54,14 @@ __global__ void __launch_bounds__(SC_WARPS * 32) sc_chunk_sums(const double *__r
     if (lane == 0) csum[k] = s;
 }
 
+template <bool DIV>
+__global__ void __launch_bounds__(SC_WARPS * 32) sc_chunk_sums(const double *__restrict__ d, int64_t n, const double *Sptr,
+                                                                double *__restrict__ csum, int32_t *__restrict__ bad) {
+    chunk_sums_body<DIV>(d, n, Sptr, csum, bad, (int64_t)blockIdx.x * SC_WARPS + (threadIdx.x >> 5), threadIdx.x & 31);
+}
+
 // 2. exclusive scan of the chunk sums, one CTA
-__global__ void __launch_bounds__(1024) sc_scan_chunks(double *__restrict__ csum, int nch) {
+__device__ __forceinline__ void scan_chunks_body(double *__restrict__ csum, int nch) {
     __shared__ double part[1024];
     const int tid = threadIdx.x;
     const int per = (nch + 1023) / 1024;
@@ -80,13 +84,13 @@ __global__ void __launch_bounds__(1024) sc_scan_chunks(double *__restrict__ csum
     if (tid == 1023) csum[nch] = part[1023];
 }
 
+__global__ void __launch_bounds__(1024) sc_scan_chunks(double *__restrict__ csum, int nch) { scan_chunks_body(csum, nch); }
+
 // 3. classify each chunk and compute the exact contribution of the regular ones
 template <bool DIV>
-__global__ void __launch_bounds__(SC_WARPS * 32) sc_classify(const double *__restrict__ d, int64_t n, const double *Sptr,
-                                                             const double *__restrict__ P, double delta,
-                                                             double *__restrict__ D, int32_t *__restrict__ cls) {
-    const int lane = threadIdx.x & 31;
-    const int64_t k = (int64_t)blockIdx.x * SC_WARPS + (threadIdx.x >> 5);
+__device__ __forceinline__ void classify_body(const double *__restrict__ d, int64_t n, const double *Sptr,
+                                              const double *__restrict__ P, double delta, double *__restrict__ D,
+                                              int32_t *__restrict__ cls, int64_t k, int lane) {
     const int64_t base = k * SC_CH;
     if (base >= n) return;
     const double S = DIV ? *Sptr : 1.0;
@@ -121,6 +125,13 @@ __global__ void __launch_bounds__(SC_WARPS * 32) sc_classify(const double *__res
         cls[k] = regular ? e : INT_MIN;
         D[k] = regular ? A * pow2d(e - 52) : 0.0;    // exact: integer times a power of two
     }
+}
+
+template <bool DIV>
+__global__ void __launch_bounds__(SC_WARPS * 32) sc_classify(const double *__restrict__ d, int64_t n, const double *Sptr,
+                                                             const double *__restrict__ P, double delta,
+                                                             double *__restrict__ D, int32_t *__restrict__ cls) {
+    classify_body<DIV>(d, n, Sptr, P, delta, D, cls, (int64_t)blockIdx.x * SC_WARPS + (threadIdx.x >> 5), threadIdx.x & 31);
 }
 
 // 4. the walk: exact running sum before every chunk.  One CTA.
@@ -229,17 +240,17 @@ __device__ __forceinline__ double walk_dirty_tile(const double *__restrict__ d, 
 constexpr int SW_SLOTS = 64;      // replay chunks staged in shared memory (64 x 2 KB); more fall back to global loads
 
 template <bool DIV>
-__global__ void __launch_bounds__(SW_THREADS) sc_walk(const double *__restrict__ d, int64_t n, const double *Sptr,
-                                                      double *__restrict__ D, const int32_t *__restrict__ cls, int nch,
-                                                      double *__restrict__ cstart, double *__restrict__ tile_tot,
-                                                      double *__restrict__ tile_carry, int32_t *__restrict__ tile_e,
-                                                      int32_t *__restrict__ bad, double *__restrict__ stats) {
+__device__ __forceinline__ void walk_body(const double *__restrict__ d, int64_t n, const double *Sptr,
+                                          double *__restrict__ D, const int32_t *__restrict__ cls, int nch,
+                                          double *__restrict__ cstart, double *__restrict__ tile_tot,
+                                          double *__restrict__ tile_carry, int32_t *__restrict__ tile_e,
+                                          int32_t *__restrict__ bad, double *__restrict__ stats, double *xs) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned full = 0xffffffffu;
     const double S = DIV ? *Sptr : 1.0;
     const int ntile = (nch + 31) / 32;
     constexpr int NW = SW_THREADS / 32;
-    extern __shared__ double xs[];                               // [SW_SLOTS][SC_CH], element (lane*8+t) at [t*32+lane]
+    // xs: [SW_SLOTS][SC_CH], element (lane*8+t) at [t*32+lane]
     __shared__ int nslots;
     if (threadIdx.x == 0) nslots = 0;
     __syncthreads();
@@ -325,6 +336,16 @@ __global__ void __launch_bounds__(SW_THREADS) sc_walk(const double *__restrict__
     }
 }
 
+template <bool DIV>
+__global__ void __launch_bounds__(SW_THREADS) sc_walk(const double *__restrict__ d, int64_t n, const double *Sptr,
+                                                      double *__restrict__ D, const int32_t *__restrict__ cls, int nch,
+                                                      double *__restrict__ cstart, double *__restrict__ tile_tot,
+                                                      double *__restrict__ tile_carry, int32_t *__restrict__ tile_e,
+                                                      int32_t *__restrict__ bad, double *__restrict__ stats) {
+    extern __shared__ double xs_dyn[];
+    walk_body<DIV>(d, n, Sptr, D, cls, nch, cstart, tile_tot, tile_carry, tile_e, bad, stats, xs_dyn);
+}
+
 // 5. locate the draws: idx = #{ j : fl(c_j / c_last) <= u }.  Division by c_last > 0 is monotone, so the predicate
 // equals c_j <= t with t the LARGEST double whose quotient rounds to <= u; t is found once per draw and the
 // per-element division disappears from the sequential replay.
@@ -339,14 +360,12 @@ __device__ __forceinline__ double quotient_threshold(double u, double clast) {
     return t;
 }
 
-__global__ void __launch_bounds__(32) sc_locate(const double *__restrict__ d, int64_t n, const double *Sptr,
-                                                const double *__restrict__ cstart, int nch, const double *__restrict__ u,
-                                                int64_t *__restrict__ idx) {
-    __shared__ double xs[SC_CH];
-    const int lane = threadIdx.x;
+__device__ __forceinline__ void locate_body(const double *__restrict__ d, int64_t n, const double *Sptr,
+                                            const double *__restrict__ cstart, int nch, double uq, int64_t *__restrict__ out,
+                                            int lane, double *xs) {
     const double S = *Sptr;
     const double clast = cstart[nch];
-    const double thr = quotient_threshold(u[blockIdx.x], clast);
+    const double thr = quotient_threshold(uq, clast);
     // first chunk whose END value exceeds the threshold: cdf is non-decreasing, cstart[k+1] is the value at chunk k's end
     int lo = 0, hi = nch - 1;
     while (lo < hi) {
@@ -368,8 +387,47 @@ __global__ void __launch_bounds__(32) sc_locate(const double *__restrict__ d, in
             if (c <= thr) ++cnt; else break;
         }
         int64_t r = base + cnt;
-        idx[blockIdx.x] = r < n ? r : n - 1;
+        *out = r < n ? r : n - 1;
     }
+}
+
+__global__ void __launch_bounds__(32) sc_locate(const double *__restrict__ d, int64_t n, const double *Sptr,
+                                                const double *__restrict__ cstart, int nch, const double *__restrict__ u,
+                                                int64_t *__restrict__ idx) {
+    __shared__ double xs[SC_CH];
+    locate_body(d, n, Sptr, cstart, nch, u[blockIdx.x], idx + blockIdx.x, threadIdx.x, xs);
+}
+
+// Small problems (n_pad <= SC_FUSED_MAX): all seven phases in ONE CTA separated by CTA barriers -- the multi-kernel
+// pipeline above is a chain of latency-bound launches there (simple RPCholesky samples once per step).
+constexpr int64_t SC_FUSED_MAX = 65536;
+
+__global__ void __launch_bounds__(SW_THREADS) sc_fused_small(const double *__restrict__ d, int64_t n, const double *__restrict__ u,
+                                                             int m, int64_t *__restrict__ idx, double *__restrict__ stats,
+                                                             double *__restrict__ csum, double *__restrict__ D,
+                                                             double *__restrict__ cA, double *__restrict__ cB,
+                                                             double *__restrict__ tile_tot, double *__restrict__ tile_carry,
+                                                             int32_t *__restrict__ cls, int32_t *__restrict__ bad,
+                                                             int32_t *__restrict__ tile_e, int nch, double delta, double delta_b) {
+    extern __shared__ double xs_dyn[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = SW_THREADS / 32;
+    const double *Sptr = cA + nch;
+    if (threadIdx.x < 2) bad[threadIdx.x] = 0;
+    __syncthreads();
+    for (int k = warp; k < nch; k += NW) chunk_sums_body<false>(d, n, nullptr, csum, bad, k, lane);
+    __syncthreads();
+    scan_chunks_body(csum, nch);
+    __syncthreads();
+    for (int k = warp; k < nch; k += NW) classify_body<false>(d, n, nullptr, csum, delta, D, cls, k, lane);
+    __syncthreads();
+    walk_body<false>(d, n, nullptr, D, cls, nch, cA, tile_tot, tile_carry, tile_e, bad, nullptr, xs_dyn);
+    __syncthreads();
+    for (int k = warp; k < nch; k += NW) classify_body<true>(d, n, Sptr, cA, delta_b, D, cls, k, lane);
+    __syncthreads();
+    walk_body<true>(d, n, Sptr, D, cls, nch, cB, tile_tot, tile_carry, tile_e, bad, stats, xs_dyn);
+    __syncthreads();
+    for (int q = warp; q < m; q += NW) locate_body(d, n, Sptr, cB, nch, u[q], idx + q, lane, xs_dyn + warp * SC_CH);
 }
 
 extern "C" int rpc_sample_pivots(rpc_ctx *ctx, void *stream, const double *diag, int64_t n_pad, const double *u, int m,
@@ -390,14 +448,23 @@ extern "C" int rpc_sample_pivots(rpc_ctx *ctx, void *stream, const double *diag,
     double *csum = ctx->ws, *D = csum + (nch + 2), *cA = D + (nch + 2), *cB = cA + (nch + 2);
     double *tile_tot = cB + (nch + 2), *tile_carry = tile_tot + (ntile + 2);
     int32_t *cls = ctx->flags, *bad = ctx->flags + nch, *tile_e = ctx->flags + nch + 8;
-    RPC_CUDA(cudaMemsetAsync(bad, 0, 2 * sizeof(int32_t), st));
     static bool configured = false;
     if (!configured) {
         RPC_CUDA(cudaFuncSetAttribute(sc_walk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SLOTS * SC_CH * 8));
         RPC_CUDA(cudaFuncSetAttribute(sc_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SLOTS * SC_CH * 8));
+        RPC_CUDA(cudaFuncSetAttribute(sc_fused_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SLOTS * SC_CH * 8));
         configured = true;
     }
     const double delta = ((double)n_pad + 256.0) * 1.1102230246251565e-16 * 1.01;
+    if (n_pad <= SC_FUSED_MAX) {
+        const double delta_b = (2.0 * (double)n_pad + 512.0) * 1.1102230246251565e-16 * 1.01;
+        sc_fused_small<<<1, SW_THREADS, SW_SLOTS * SC_CH * sizeof(double), st>>>(diag, n_pad, u, m, idx, stats, csum, D, cA, cB,
+                                                                                 tile_tot, tile_carry, cls, bad, tile_e, nch,
+                                                                                 delta, delta_b);
+        RPC_LAUNCHED(ctx);
+        return 0;
+    }
+    RPC_CUDA(cudaMemsetAsync(bad, 0, 2 * sizeof(int32_t), st));
     const unsigned grid = (unsigned)((nch + SC_WARPS - 1) / SC_WARPS);
     const double *Sptr = cA + nch;     // exact python sum(diags)
 
