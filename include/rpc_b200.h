@@ -202,6 +202,41 @@ int rpc_simple_run(rpc_ctx *ctx, void *stream, int greedy, const rpc_kernel_spec
                    double *stats_all, int i0, int i1, double *G, int64_t ldg, double *rows, int64_t ldr, double *diag,
                    int64_t n_pad);
 
+/* ---- peer-memory exchange for row-sharded runs (one process per GPU of one NVSwitch box) --------------------------
+ * The two per-round exchanges of the sharded factorisation (the residual-diagonal all-gather and
+ * the pivot-payload exchange) are done by the producing kernels themselves: they store their results straight into every
+ * rank's buffers through NVLink peer mappings and publish a monotone epoch in a flag word; the consumer side waits on
+ * its local flag words.  No NCCL call is left inside a round. */
+#define RPC_MAX_PEERS 8
+typedef struct rpc_peers {
+    int32_t world, rank;
+    int64_t shard;                                  /* points per rank (dist.ShardInfo.shard) */
+    double *diag_full[RPC_MAX_PEERS];               /* rank r's copy of the full residual diagonal (world * shard) */
+    double *payload[RPC_MAX_PEERS];                 /* rank r's pivot payload [X[idx] | |x|^2 | G[:c, idx]] */
+    unsigned long long *flags[RPC_MAX_PEERS];       /* rank r's flag words: [src] diag epochs, [RPC_MAX_PEERS + src] payload */
+} rpc_peers;
+
+/* A zero-initialised device buffer that other processes of the box can map: handle = its 64-byte cudaIpcMemHandle_t. */
+int rpc_peer_alloc(rpc_ctx *ctx, int64_t bytes, void **ptr, unsigned char handle[64]);
+int rpc_peer_free(rpc_ctx *ctx, void *ptr);
+/* Map / unmap a buffer exported by another process (cudaIpcOpenMemHandle with lazy peer access). */
+int rpc_peer_open(rpc_ctx *ctx, const unsigned char handle[64], void **ptr);
+int rpc_peer_close(rpc_ctx *ctx, void *ptr);
+/* Enqueue a wait until flags[i] >= epoch for all i < count (a one-warp kernel spinning on local memory).  If that does not
+ * happen within timeout_ms the kernel gives up and sets *status (device int32) to 1. */
+int rpc_peer_wait(rpc_ctx *ctx, void *stream, const unsigned long long *flags, int count, unsigned long long epoch,
+                  int timeout_ms, int32_t *status);
+/* rpc_schur_update that also stores the updated residual diagonal into every rank's diag_full and publishes `epoch` in
+ * flags[r][rank] of every rank r (the fused diag all-gather). */
+int rpc_schur_update_peers(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At, int64_t ldat,
+                           int k_pad, const double *rows_new, int64_t ldr, double *diag, int64_t n_pad, const rpc_peers *peers,
+                           unsigned long long epoch);
+/* rpc_gather_pivots whose owners store their entries into EVERY rank's payload (offsets in doubles: Xpiv at 0 with row
+ * stride ldp, |x|^2 at off_norm, P at off_P with row stride ldP) and publish `epoch` in flags[r][RPC_MAX_PEERS + rank]. */
+int rpc_gather_pivots_peers(rpc_ctx *ctx, void *stream, const int64_t *idx, int m, const double *X, const double *xnorm, int d,
+                            int64_t ldx, int64_t ldp, int64_t off_norm, const double *G, int64_t ldg, int c, int64_t off_P,
+                            int64_t ldP, int64_t lo, int64_t hi, const rpc_peers *peers, unsigned long long epoch);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,15 @@ KT = 16
 KERN_GAUSSIAN, KERN_LAPLACE, KERN_MATERN = 0, 1, 2
 
 
+MAX_PEERS = 8
+
+
+class Peers(C.Structure):
+    """rpc_peers of include/rpc_b200.h: per-rank base pointers of the peer-memory windows."""
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("shard", C.c_int64),
+                ("diag_full", C.c_void_p * MAX_PEERS), ("payload", C.c_void_p * MAX_PEERS), ("flags", C.c_void_p * MAX_PEERS)]
+
+
 class KernelSpec(C.Structure):
     _fields_ = [("kind", C.c_int32), ("nu2", C.c_int32), ("extra_stability", C.c_int32), ("reserved", C.c_int32),
                 ("bandwidth", C.c_double)]
@@ -102,6 +111,15 @@ _SIGNATURES = {
     "rpc_fused_update_supported": (_INT, [C.POINTER(KernelSpec), _INT, _I64]),
     "rpc_fused_update": (_INT, [_P, _P, C.POINTER(KernelSpec), _P, _P, _I64, _INT, _I64, _P, _P, _I64, _P, _I64, _INT, _INT, _P,
                                 _I64, _INT, _P, _I64, _P]),
+    "rpc_peer_alloc": (_INT, [_P, _I64, C.POINTER(_P), _P]),
+    "rpc_peer_free": (_INT, [_P, _P]),
+    "rpc_peer_open": (_INT, [_P, _P, C.POINTER(_P)]),
+    "rpc_peer_close": (_INT, [_P, _P]),
+    "rpc_peer_wait": (_INT, [_P, _P, _P, _INT, C.c_uint64, _INT, _P]),
+    "rpc_schur_update_peers": (_INT, [_P, _P, _P, _I64, _INT, _INT, _P, _I64, _INT, _P, _I64, _P, _I64, C.POINTER(Peers),
+                                      C.c_uint64]),
+    "rpc_gather_pivots_peers": (_INT, [_P, _P, _P, _INT, _P, _P, _INT, _I64, _I64, _I64, _P, _I64, _INT, _I64, _I64, _I64, _I64,
+                                       C.POINTER(Peers), C.c_uint64]),
     "rpc_simple_run": (_INT, [_P, _P, _INT, C.POINTER(KernelSpec), _P, _P, _INT, _I64, _P, _I64, _I64, _P, _P, _P, _INT, _INT, _P,
                               _I64, _P, _I64, _P, _I64]),
     "rpc_simple_step": (_INT, [_P, _P, C.POINTER(KernelSpec), _P, _P, _INT, _I64, _P, _I64, _I64, _P, _INT, _P, _I64, _P,

@@ -118,14 +118,21 @@ static bool fused_fits(int m, int64_t ldx) {
     return need <= SMEM_LIMIT;
 }
 
-extern "C" int rpc_schur_update(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At,
-                                int64_t ldat, int k_pad, const double *rows_new, int64_t ldr, double *diag,
-                                int64_t n_pad) {
+static int schur_update_impl(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At, int64_t ldat,
+                             int k_pad, const double *rows_new, int64_t ldr, double *diag, int64_t n_pad, const rpc_peers *peers,
+                             unsigned long long epoch) {
     RPC_CHECK_ARG(ctx && G && At && rows_new && diag, "null pointer");
     RPC_CHECK_ARG(s >= 1 && c >= 0, "s >= 1, c >= 0");
     RPC_CHECK_ARG(n_pad > 0 && n_pad % RPC_COL_ALIGN == 0, "n_pad must be a positive multiple of RPC_COL_ALIGN");
     RPC_CHECK_ARG(k_pad % RPC_KT == 0 && k_pad >= c + s, "k_pad must be a multiple of RPC_KT and >= c+s");
     RPC_CHECK_ARG(ldg % 2 == 0 && ldr % 2 == 0 && ldat % 2 == 0, "leading dimensions must be even (16-byte rows)");
+    if (peers) {
+        RPC_CHECK_ARG(peers->world >= 1 && peers->world <= RPC_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world,
+                      "bad peer table");
+        RPC_CHECK_ARG(n_pad <= peers->shard, "the local shard is wider than the peers' slot for it");
+        int rc = rpc_sync_reserve(ctx);
+        if (rc) return rc;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     for (int m0 = 0; m0 < s; m0 += 256) {
         int m = s - m0 < 256 ? s - m0 : 256;
@@ -134,10 +141,34 @@ extern "C" int rpc_schur_update(rpc_ctx *ctx, void *stream, double *G, int64_t l
         p.At = At + m0; p.ldat = ldat; p.k_pad = k_pad; p.m_valid = m;
         p.G = G; p.ldg = ldg; p.c = c; p.R = rows_new; p.ldr = ldr; p.K = c + s;
         p.Cout = G + (int64_t)(c + m0) * ldg; p.ldc = ldg; p.diag = diag;
+        if (peers && m0 + 256 >= s) {
+            // the last row chunk leaves the final diagonal: it stores it into every rank's copy and publishes the epoch
+            p.npeers = peers->world;
+            for (int r = 0; r < peers->world; ++r) {
+                RPC_CHECK_ARG(peers->diag_full[r] && peers->flags[r], "peer table has null entries");
+                p.peer_diag[r] = peers->diag_full[r] + (int64_t)peers->rank * peers->shard;
+                p.peer_flag[r] = peers->flags[r] + peers->rank;
+            }
+            p.epoch = epoch;
+            p.done_counter = ctx->sync_counter;
+        }
         int rc = dispatch_gemm<MODE_SCHUR>(ctx, st, p, m, n_pad);
         if (rc) return rc;
     }
     return 0;
+}
+
+extern "C" int rpc_schur_update(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At,
+                                int64_t ldat, int k_pad, const double *rows_new, int64_t ldr, double *diag,
+                                int64_t n_pad) {
+    return schur_update_impl(ctx, stream, G, ldg, c, s, At, ldat, k_pad, rows_new, ldr, diag, n_pad, nullptr, 0);
+}
+
+extern "C" int rpc_schur_update_peers(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At,
+                                      int64_t ldat, int k_pad, const double *rows_new, int64_t ldr, double *diag, int64_t n_pad,
+                                      const rpc_peers *peers, unsigned long long epoch) {
+    RPC_CHECK_ARG(peers != nullptr, "peer table required");
+    return schur_update_impl(ctx, stream, G, ldg, c, s, At, ldat, k_pad, rows_new, ldr, diag, n_pad, peers, epoch);
 }
 
 extern "C" int rpc_fused_update_supported(const rpc_kernel_spec *spec, int s, int64_t ldx) {

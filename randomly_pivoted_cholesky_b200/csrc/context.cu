@@ -41,6 +41,7 @@ extern "C" int rpc_ctx_destroy(rpc_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->flags) cudaFree(ctx->flags);
+    if (ctx->sync_counter) cudaFree(ctx->sync_counter);
     delete ctx;
     return 0;
 }
@@ -56,6 +57,13 @@ int rpc_ws_reserve(rpc_ctx *ctx, size_t bytes) {
     ctx->ws_bytes = 0;
     RPC_CUDA(cudaMalloc((void **)&ctx->ws, want));
     ctx->ws_bytes = want;
+    return 0;
+}
+
+int rpc_sync_reserve(rpc_ctx *ctx) {
+    if (ctx->sync_counter) return 0;
+    RPC_CUDA(cudaMalloc((void **)&ctx->sync_counter, 16 * sizeof(unsigned int)));
+    RPC_CUDA(cudaMemset(ctx->sync_counter, 0, 16 * sizeof(unsigned int)));
     return 0;
 }
 

@@ -84,6 +84,14 @@ struct Params {
     int64_t ldat_e;
     int ke_pad;
     int ntiles;            // column tiles (n_pad / N_TILE); the kernel is persistent over them
+    // MODE_SCHUR, row-sharded runs: the updated residual diagonal of this rank's columns is ALSO stored straight into
+    // every rank's copy of the full diagonal (peer memory over NVLink; entry r already points at this rank's block),
+    // and the last CTA to finish publishes `epoch` in each rank's flag word for this source (csrc/peers.cu)
+    int npeers;
+    double *peer_diag[RPC_MAX_PEERS];
+    unsigned long long *peer_flag[RPC_MAX_PEERS];
+    unsigned long long epoch;
+    unsigned int *done_counter;
 };
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
@@ -454,10 +462,27 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
 #pragma unroll
                 for (int w = 0; w < C::WM; ++w) sres += red[w * C::N_TILE + n];
                 double dv = p.diag[col0 + n] - sres;
-                p.diag[col0 + n] = dv > 0.0 ? dv : 0.0;    // .clip(min=0)
+                dv = dv > 0.0 ? dv : 0.0;                  // .clip(min=0)
+                p.diag[col0 + n] = dv;
+                if (MODE == MODE_SCHUR)
+                    for (int r = 0; r < p.npeers; ++r) p.peer_diag[r][col0 + n] = dv;   // the diag "all-gather", tile by tile
             }
         } else {
             eval_epilogue<C>(p, acc, p.Cout, p.ldc, col0, m0, n0, lr, lk, mi_cnt);
+        }
+    }
+    if (MODE == MODE_SCHUR && p.npeers > 0) {
+        // release pattern: this CTA's peer stores -> system fence -> CTA counter; the last CTA publishes the epoch
+        consumer_bar_sync(C::CONSUMERS * 32);
+        if (tid == 0) {
+            __threadfence_system();
+            const unsigned int prev = atomicAdd(p.done_counter, 1u);
+            if (prev == gridDim.x - 1) {
+                __threadfence_system();
+                *p.done_counter = 0;                                   // every CTA has arrived: re-arm for the next launch
+                for (int r = 0; r < p.npeers; ++r)
+                    asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p.peer_flag[r]), "l"(p.epoch) : "memory");
+            }
         }
     }
 }

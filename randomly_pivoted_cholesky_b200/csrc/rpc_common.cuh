@@ -14,11 +14,13 @@ struct rpc_ctx {
     size_t ws_bytes;
     int32_t *flags;    // small int workspace (sampler flags etc.)
     size_t flags_bytes;
+    unsigned int *sync_counter;   // [0] Schur, [1] gather: CTA arrival counters of the peer-publishing kernels (self re-arming)
 };
 
 void rpc_set_error(const char *fmt, ...);
 int rpc_ws_reserve(rpc_ctx *ctx, size_t bytes);
 int rpc_flags_reserve(rpc_ctx *ctx, size_t bytes);
+int rpc_sync_reserve(rpc_ctx *ctx);
 // out (k_pad x ldo) = zero-padded transpose of in (m x d)
 int rpc_transpose_pad(rpc_ctx *ctx, cudaStream_t st, const double *in, int64_t ldi, int m, int d, double *out, int64_t ldo,
                       int k_pad);

@@ -94,3 +94,82 @@ def current_shard_info(n: int, group=None) -> ShardInfo:
     if dist.is_available() and dist.is_initialized():
         return make_shard_info(n, dist.get_world_size(group), dist.get_rank(group), group)
     return make_shard_info(n, 1, 0, None)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Peer-memory exchange (CUDA only): the two per-round exchanges done by the producing kernels themselves
+# ----------------------------------------------------------------------------------------------------------------
+class _DevMem:
+    """Wraps a raw device allocation so that torch can view it (torch.as_tensor via __cuda_array_interface__)."""
+
+    def __init__(self, ptr, nbytes, typestr, shape):
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": shape, "typestr": typestr, "version": 2}
+        self.nbytes = nbytes
+
+
+class PeerWindow:
+    """One buffer per rank, [diag_full (world*shard) | payload (payload_len) | flag words (2*8 u64)], mapped into every
+    process of the box over CUDA IPC (include/rpc_b200.h, rpc_peers).  The Schur kernel stores its updated diagonal
+    block into every rank's diag_full, the pivot gather stores the owners' entries into every rank's payload; each
+    publishes a monotone epoch in the flag words, and `wait_*` enqueues the matching wait on the local stream.
+    Windows are cached per (group, sizes): mapping a peer allocation costs milliseconds."""
+
+    _cache = {}
+
+    @classmethod
+    def get(cls, info: ShardInfo, ctx, device, payload_len: int):
+        key = (id(info.group), info.world, info.rank, info.shard, device.index)
+        w = cls._cache.get(key)
+        if w is not None and w.payload_len >= payload_len:
+            return w
+        # the payload is sized generously so that one window serves every factorisation of this operator
+        w = cls(info, ctx, device, payload_len)
+        cls._cache[key] = w
+        return w
+
+    def __init__(self, info: ShardInfo, ctx, device, payload_len: int):
+        import ctypes as C
+        from . import _lib
+        self.info, self.ctx, self.device = info, ctx, device
+        self.payload_len = int(payload_len)
+        self.n_total = info.n_total_pad
+        ndbl = self.n_total + self.payload_len
+        self.nbytes = 8 * ndbl + 8 * 2 * _lib.MAX_PEERS
+        base = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        _lib.check(ctx.lib.rpc_peer_alloc(ctx.handle, self.nbytes, C.byref(base), handle), "rpc_peer_alloc")
+        self.base = int(base.value)
+        mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=device)
+        allh = torch.empty((info.world, 64), dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(allh, mine, group=info.group)
+        allh = allh.cpu().numpy()
+        self.bases = []
+        self._opened = []
+        for r in range(info.world):
+            if r == info.rank:
+                self.bases.append(self.base)
+                continue
+            p = C.c_void_p()
+            hb = (C.c_ubyte * 64).from_buffer_copy(bytes(allh[r].tobytes()))
+            _lib.check(ctx.lib.rpc_peer_open(ctx.handle, hb, C.byref(p)), "rpc_peer_open")
+            self.bases.append(int(p.value))
+            self._opened.append(int(p.value))
+        peers = _lib.Peers()
+        peers.world, peers.rank, peers.shard = info.world, info.rank, info.shard
+        for r in range(info.world):
+            peers.diag_full[r] = self.bases[r]
+            peers.payload[r] = self.bases[r] + 8 * self.n_total
+            peers.flags[r] = self.bases[r] + 8 * ndbl
+        self.peers = peers
+        self.flags_ptr = self.base + 8 * ndbl
+        self.diag_full = torch.as_tensor(_DevMem(self.base, 8 * self.n_total, "<f8", (self.n_total,)), device=device)
+        self.payload = torch.as_tensor(_DevMem(self.base + 8 * self.n_total, 8 * self.payload_len, "<f8", (self.payload_len,)),
+                                       device=device)
+        self.status = torch.zeros((1,), dtype=torch.int32, device=device)
+        self.epoch_diag = 0
+        self.epoch_payload = 0
+        dist.barrier(group=info.group)            # every rank has mapped every window before anyone stores into one
+
+    def check_status(self):
+        if int(self.status.item()) != 0:
+            raise RuntimeError("peer-memory exchange timed out waiting for another rank's epoch")

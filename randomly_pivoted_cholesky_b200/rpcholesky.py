@@ -33,6 +33,9 @@ AT_LD_ALIGN = 256          # panel leading dimension granularity (widest row til
 # rpc_kernel_rows + rpc_schur_update on B200 (profiles/): opt-in only
 import os as _os
 USE_FUSED = _os.environ.get("RPC_B200_FUSED", "0") == "1"
+# Row-sharded runs exchange the residual diagonal and the pivot payload through NVLink peer memory, stored by the
+# producing kernels themselves (dist.PeerWindow); RPC_B200_PEER=0 falls back to the two NCCL collectives per round
+USE_PEER = _os.environ.get("RPC_B200_PEER", "1") != "0"
 
 # bench.py sets this to a list to collect (start_event, end_event, flops, bytes, phase) per timed launch
 KERNEL_TIMERS = None
@@ -90,7 +93,6 @@ class _State:
         self.G = torch.empty((k, self.n_pad), **f64)
         self.rows = torch.empty((k, self.n_pad), **f64)
         self.diag = torch.empty((self.n_pad,), **f64)
-        self.diag_full = torch.empty((self.info.n_total_pad,), **f64) if self.info.world > 1 else self.diag
         self.m_max = m_max
         self.u_dev = torch.empty((2 * m_max,), **f64)
         self.idx_dev = torch.empty((m_max,), dtype=torch.int64, device=self.dev)
@@ -99,7 +101,16 @@ class _State:
         # payload: [Xpiv (m_max x ldx) | pnorm (m_max) | P (k x m_max)] -- the used prefix is one contiguous range
         self.ldx = getattr(A, "ldx", 0)
         nx = m_max * self.ldx
-        self.payload = torch.zeros((nx + (m_max if self.ldx else 0) + max(k, 1) * m_max,), **f64)
+        payload_len = nx + (m_max if self.ldx else 0) + max(k, 1) * m_max
+        self.peer = None
+        self.diag_pending = False              # True: the last Schur update published the new diagonal into diag_full
+        if self.info.world > 1 and USE_PEER and not USE_FUSED and self.dev.type == "cuda" and self.ldx:
+            self.peer = rdist.PeerWindow.get(self.info, self.ctx, self.dev, payload_len)
+            self.payload = self.peer.payload[:payload_len]
+            self.diag_full = self.peer.diag_full
+        else:
+            self.payload = torch.zeros((payload_len,), **f64)
+            self.diag_full = torch.empty((self.info.n_total_pad,), **f64) if self.info.world > 1 else self.diag
         if self.ldx:
             self.piv = _Payload(self.payload[:nx].view(m_max, self.ldx), self.payload[nx:nx + m_max])
             self.sel = _Payload(torch.zeros((m_max, self.ldx), **f64), torch.zeros((m_max,), **f64))
@@ -159,7 +170,14 @@ class _State:
 
     def sample(self, m, u_off=0):
         """Every rank samples on the FULL residual diagonal (all-gathered when sharded): identical pivots everywhere."""
-        full = rdist.gather_diag(self.info, self.diag, self.diag_full)
+        if self.peer is not None and self.diag_pending:
+            # every rank's Schur kernel stored its block of the new diagonal here and published the epoch
+            check(self.lib.rpc_peer_wait(self.ctx.handle, _stream(), C.c_void_p(self.peer.flags_ptr), self.info.world,
+                                         self.peer.epoch_diag, 0, _ptr(self.peer.status)), "rpc_peer_wait")
+            self.diag_pending = False
+            full = self.diag_full
+        else:
+            full = rdist.gather_diag(self.info, self.diag, self.diag_full)
         u = C.c_void_p(self.u_dev.data_ptr() + 8 * u_off)
         check(self.lib.rpc_sample_pivots(self.ctx.handle, _stream(), _ptr(full), full.numel(), u, m, _ptr(self.idx_dev),
                                          _ptr(self.stats)), "rpc_sample_pivots")
@@ -171,6 +189,17 @@ class _State:
         xn = getattr(A, "_xnorm", None)
         d = getattr(A, "d_pad", 0)
         piv = self.piv
+        if self.peer is not None:
+            # owners store their entries into EVERY rank's payload through peer memory, then all wait for all epochs
+            pw = self.peer
+            pw.epoch_payload += 1
+            check(self.lib.rpc_gather_pivots_peers(self.ctx.handle, _stream(), _ptr(idx_dev), m, _ptr(X), _ptr(xn), d, self.ldx,
+                                                   self.ldx, self.m_max * self.ldx, _ptr(self.G) if c > 0 else None,
+                                                   self.n_pad, c, self.p_off, self.m_max, self.info.lo, self.info.hi,
+                                                   C.byref(pw.peers), pw.epoch_payload), "rpc_gather_pivots_peers")
+            check(self.lib.rpc_peer_wait(self.ctx.handle, _stream(), C.c_void_p(pw.flags_ptr + 8 * _lib.MAX_PEERS),
+                                         self.info.world, pw.epoch_payload, 0, _ptr(pw.status)), "rpc_peer_wait")
+            return
         check(self.lib.rpc_gather_pivots(self.ctx.handle, _stream(), _ptr(idx_dev), m, _ptr(X), _ptr(xn), d, self.ldx,
                                          _ptr(piv.X) if piv is not None else None,
                                          _ptr(piv.norm) if piv is not None else None, self.ldx,
@@ -234,13 +263,23 @@ class _State:
         A._count(s * self.n)
         # algorithmic work of the Schur update: 2 s (c+s) N flops; reads G[:c] and rows_new, writes G_new
         with _timed("schur", 2.0 * s * (c + s) * n, 8.0 * n * (c + 2 * s + 2)):
-            check(self.lib.rpc_schur_update(self.ctx.handle, _stream(), _ptr(self.G), self.n_pad, c, s, _ptr(self.At),
-                                            ldat, k_pad, rows_ptr, self.n_pad, _ptr(self.diag), self.n_pad),
-                  "rpc_schur_update")
+            if self.peer is not None:
+                self.peer.epoch_diag += 1
+                check(self.lib.rpc_schur_update_peers(self.ctx.handle, _stream(), _ptr(self.G), self.n_pad, c, s, _ptr(self.At),
+                                                      ldat, k_pad, rows_ptr, self.n_pad, _ptr(self.diag), self.n_pad,
+                                                      C.byref(self.peer.peers), self.peer.epoch_diag),
+                      "rpc_schur_update_peers")
+                self.diag_pending = True
+            else:
+                check(self.lib.rpc_schur_update(self.ctx.handle, _stream(), _ptr(self.G), self.n_pad, c, s, _ptr(self.At),
+                                                ldat, k_pad, rows_ptr, self.n_pad, _ptr(self.diag), self.n_pad),
+                      "rpc_schur_update")
 
     def result(self, count, arr_idx):
         # sharded: keep the whole padded shard (equal widths on all ranks, so `.G` can all-gather); else cut to N
         nl = self.n_pad if self.info.world > 1 else self.n_loc
+        if self.peer is not None:
+            self.peer.check_status()
         return PSDLowRank(self.G[:count, :nl], n=self.n, idx=arr_idx, rows=self.rows[:count, :nl], shard_info=self.info)
 
 

@@ -18,15 +18,27 @@ def rel(a, b): return np.linalg.norm(a - b) / np.linalg.norm(b)
 ok = True
 for (alg, kernel, n, d, k, b, bw, kw) in [("accel", "gaussian", 20000, 20, 600, 120, np.sqrt(20), {}),
                                            ("block", "laplace", 15000, 50, 400, 100, 50.0, {}),
-                                           ("accel", "matern", 30011, 3, 500, 64, np.sqrt(3), {"nu": 2.5})]:
+                                           ("accel", "matern", 30011, 3, 500, 64, np.sqrt(3), {"nu": 2.5}),
+                                           ("rbrp", "gaussian", 12000, 8, 300, 60, np.sqrt(8), {}),
+                                           ("bgreedy", "laplace", 9000, 6, 200, 50, 6.0, {}),
+                                           ("accel", "gaussian", 20000, 20, 600, 120, np.sqrt(20), {})]:
     X = np.random.default_rng(3).standard_normal((n, d))
     A = rpc.KernelMatrix(X, kernel=kernel, bandwidth=float(bw), sharded=True, **kw)
     with replay(77):
-        lra = rpc.accelerated_rpcholesky(A, k, b=b) if alg == "accel" else rpc.block_rpcholesky(A, k, b=b)
+        if alg == "accel":
+            lra = rpc.accelerated_rpcholesky(A, k, b=b)
+        elif alg == "bgreedy":
+            lra = rpc.greedy(A, k, b=b)
+        else:
+            lra = rpc.block_rpcholesky(A, k, b=b, **({"strategy": "rbrp"} if alg == "rbrp" else {}))
     G = lra.G; rows = lra.rows; tr = lra.trace()
     rng, legacy = orc.make_streams(77)
     A0 = orc.OracleKernelMatrix(X, kernel=kernel, bandwidth=float(bw), **kw)
-    ref = orc.accelerated_rpcholesky(A0, k, b, rng, legacy) if alg == "accel" else orc.block_rpcholesky(A0, k, b, rng)
+    if alg == "accel":
+        ref = orc.accelerated_rpcholesky(A0, k, b, rng, legacy)
+    else:
+        ref = orc.block_rpcholesky(A0, k, b, rng, alg="greedy" if alg == "bgreedy" else "rp",
+                                   strategy="rbrp" if alg == "rbrp" else "regularize")
     same = [int(i) for i in lra.idx] == [int(i) for i in ref.idx]
     eg, er = rel(G, ref.G), rel(rows, ref.rows)
     good = same and eg <= 1e-10 and er <= 1e-10 and abs(tr - ref.trace()) <= 1e-9 * ref.trace() and A.num_queries() == A0.num_queries()
