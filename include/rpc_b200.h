@@ -202,6 +202,14 @@ int rpc_simple_run(rpc_ctx *ctx, void *stream, int greedy, const rpc_kernel_spec
                    double *stats_all, int i0, int i1, double *G, int64_t ldg, double *rows, int64_t ldr, double *diag,
                    int64_t n_pad);
 
+/* rpc_build_panel (mode 0) followed by rpc_compact_selected, with the row count s read on the device from *s_dev
+ * (0 <= *s_dev <= s_max): both can be enqueued before the host knows s (accelerated RPCholesky: right behind
+ * rpc_rejection_cholesky, whose info[0] is s_dev).  The panel is laid out with ldat = rpc_panel_ld(*s_dev) and
+ * k_pad = (c + *s_dev) rounded up to 16, exactly what the host then passes to rpc_schur_update. */
+int rpc_build_panel_dev(rpc_ctx *ctx, void *stream, const double *P, int64_t ldP, int c, const int32_t *acc,
+                        const int32_t *s_dev, int s_max, const double *L, int64_t ldl, double *At, const int64_t *idx,
+                        const double *Xpiv, const double *pnorm, int64_t ldp, int64_t *sel_idx, double *Xsel, double *nsel);
+
 /* ---- peer-memory exchange for row-sharded runs (one process per GPU of one NVSwitch box) --------------------------
  * The two per-round exchanges of the sharded factorisation (the residual-diagonal all-gather and
  * the pivot-payload exchange) are done by the producing kernels themselves: they store their results straight into every

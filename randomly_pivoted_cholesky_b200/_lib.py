@@ -106,6 +106,7 @@ _SIGNATURES = {
     "rpc_pivoted_cholesky": (_INT, [_P, _P, _P, _INT, _I64, _INT, _DBL, _DBL, _P, _I64, _P, _P]),
     "rpc_select_largest": (_INT, [_P, _P, _P, _I64, _INT, _P]),
     "rpc_build_panel": (_INT, [_P, _P, _P, _I64, _INT, _P, _INT, _P, _I64, _INT, _P, _I64, _INT]),
+    "rpc_build_panel_dev": (_INT, [_P, _P, _P, _I64, _INT, _P, _P, _INT, _P, _I64, _P, _P, _P, _P, _I64, _P, _P, _P]),
     "rpc_panel_ld": (_INT, [_INT]),
     "rpc_schur_update": (_INT, [_P, _P, _P, _I64, _INT, _INT, _P, _I64, _INT, _P, _I64, _P, _I64]),
     "rpc_fused_update_supported": (_INT, [C.POINTER(KernelSpec), _INT, _I64]),

@@ -42,6 +42,7 @@ extern "C" int rpc_ctx_destroy(rpc_ctx *ctx) {
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->flags) cudaFree(ctx->flags);
     if (ctx->sync_counter) cudaFree(ctx->sync_counter);
+    if (ctx->panel_ld_table) cudaFree(ctx->panel_ld_table);
     delete ctx;
     return 0;
 }

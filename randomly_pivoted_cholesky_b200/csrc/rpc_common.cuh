@@ -14,6 +14,7 @@ struct rpc_ctx {
     size_t ws_bytes;
     int32_t *flags;    // small int workspace (sampler flags etc.)
     size_t flags_bytes;
+    int32_t *panel_ld_table;      // rpc_panel_ld(s) for s <= 256, for the kernels that read s on the device
     unsigned int *sync_counter;   // [0] Schur, [1] gather: CTA arrival counters of the peer-publishing kernels (self re-arming)
 };
 

@@ -27,6 +27,10 @@ __device__ __forceinline__ double pow2d(int e) {   // 2^e for e in [-1022, 1023]
     return __longlong_as_double((long long)(e + 1023) << 52);
 }
 
+// exponent of a positive NORMAL double from its bit pattern (the serial walk cannot afford ilogb's special-case handling);
+// zero / subnormal give -1023 and inf / NaN give 1024, both outside the range the callers accept
+__device__ __forceinline__ int fast_ilogb(double c) { return (int)((__double_as_longlong(c) >> 52) & 0x7ff) - 1023; }
+
 template <bool DIV>
 __device__ __forceinline__ double elem(const double *__restrict__ d, int64_t j, double S) {
     return DIV ? d[j] / S : d[j];
@@ -175,7 +179,7 @@ __device__ __forceinline__ double walk_dirty_tile(const double *__restrict__ d, 
             if (lane == 0) cstart[k0 + pos] = carry;
             int lpos = 0;
             while (lpos < 32) {
-                const int eb = carry > 0.0 ? ilogb(carry) : INT_MIN;
+                const int eb = carry > 0.0 ? fast_ilogb(carry) : INT_MIN;
                 int f = lpos;                                  // first lane that needs the sequential treatment
                 if (eb >= -960 && eb <= 1000) {
                     const double scale = pow2d(52 - eb), q = pow2d(eb - 52), top = pow2d(eb + 1);
@@ -230,7 +234,7 @@ __device__ __forceinline__ double walk_dirty_tile(const double *__restrict__ d, 
         }
         const double total = __shfl_sync(full, v, 31);
         if (in_run) cstart[k] = carry + (v - Dk);                  // exclusive prefix, exact
-        if (ilogb(carry) != e0 || !(carry + total <= pow2d(e0 + 1))) violated = 1;
+        if (fast_ilogb(carry) != e0 || !(carry + total <= pow2d(e0 + 1))) violated = 1;
         carry += total;                                            // exact
         pos = end;
     }
@@ -298,19 +302,38 @@ __device__ __forceinline__ void walk_body(const double *__restrict__ d, int64_t 
             const int te = tl < ntile ? tile_e[tl] : INT_MIN;
             const double tt = tl < ntile ? tile_tot[tl] : 0.0;
             const int tend = min(32, ntile - t0);
-            for (int q = 0; q < tend; ++q) {
+            int q = 0;
+            while (q < tend) {
                 const int e0 = __shfl_sync(full, te, q);
-                const double tot = __shfl_sync(full, tt, q);
-                if (lane == 0) tile_carry[t0 + q] = carry;
-                if (e0 != INT_MIN) {
-                    if (ilogb(carry) != e0 || !(carry + tot <= pow2d(e0 + 1))) violated = 1;
-                    carry += tot;                                // exact
-                } else {
+                if (e0 == INT_MIN) {
+                    if (lane == 0) tile_carry[t0 + q] = carry;
                     const int k0 = (t0 + q) * 32, k = k0 + lane;
                     const bool live = k < nch;
                     carry = walk_dirty_tile<DIV>(d, n, S, k0, nch, live ? cls[k] : INT_MIN + 1, live ? D[k] : 0.0, carry, cstart,
                                                  lane, violated, xs);
+                    ++q;
+                    continue;
                 }
+                // maximal run [q, end) of clean tiles of binade e0: their totals are multiples of one ulp and add up
+                // exactly in any order, so the carries of the whole run come from one warp scan (lanes past ntile
+                // hold INT_MIN and never match)
+                const unsigned same = __ballot_sync(full, te == e0);
+                const unsigned from = same >> q;
+                const int len = (~from == 0u) ? 32 - q : __ffs(~from) - 1;
+                const int end = q + len;
+                const bool in_run = lane >= q && lane < end;
+                double v = in_run ? tt : 0.0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double t2 = __shfl_up_sync(full, v, o);
+                    if (lane >= o) v += t2;
+                }
+                const double total = __shfl_sync(full, v, 31);
+                if (in_run) tile_carry[t0 + lane] = carry + (v - tt);          // exact
+                // non-negative terms: the running sum stays in the binade iff it starts and ends in it
+                if (!(carry > 0.0) || fast_ilogb(carry) != e0 || !(carry + total <= pow2d(e0 + 1))) violated = 1;
+                carry += total;                                                // exact
+                q = end;
             }
         }
         if (lane == 0) {

@@ -480,9 +480,17 @@ template <bool LSMEM>
 __global__ void __launch_bounds__(TS_WARPS * 32) panel_trsm_kernel(const double *__restrict__ P, int64_t ldP, int c,
                                                                    const int32_t *__restrict__ acc, int s,
                                                                    const double *__restrict__ L, int64_t ldl,
-                                                                   double *__restrict__ At, int64_t ldat, int k_pad) {
+                                                                   double *__restrict__ At, int64_t ldat, int k_pad,
+                                                                   const int32_t *__restrict__ s_dev,
+                                                                   const int32_t *__restrict__ ld_table) {
     extern __shared__ double zs[];                  // [TS_WARPS][TS_RW][s] | inv[s] | Lt packed (when LSMEM)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (s_dev) {
+        // the row count is still on the device (the host has not read the round back yet): derive the panel shape here
+        s = *s_dev;
+        ldat = s <= 256 ? ld_table[s] : (s + 255) / 256 * 256;
+        k_pad = (c + s + RPC_KT - 1) / RPC_KT * RPC_KT;
+    }
     const int r0 = (blockIdx.x * TS_WARPS + warp) * TS_RW;
     double *inv = zs + (size_t)TS_WARPS * TS_RW * s;
     double *Lt = inv + s;
@@ -616,30 +624,64 @@ __global__ void __launch_bounds__(256) panel_kernel(const double *__restrict__ P
     }
 }
 
+__global__ void compact_selected_kernel(const int32_t *__restrict__ acc, int s, const int64_t *__restrict__ idx,
+                                        const double *__restrict__ Xpiv, const double *__restrict__ pnorm, int64_t ldp,
+                                        int64_t *__restrict__ sel_idx, double *__restrict__ Xsel, double *__restrict__ nsel,
+                                        const int32_t *__restrict__ s_dev);
+
+static int launch_panel_trsm(rpc_ctx *ctx, cudaStream_t st, const double *P, int64_t ldP, int c, const int32_t *acc, int s,
+                             const double *L, int64_t ldl, double *At, int64_t ldat, int k_pad, const int32_t *s_dev,
+                             const int32_t *ld_table) {
+    // s is the row count, or its upper bound when the count is read on the device (s_dev)
+    size_t shm = ((size_t)TS_WARPS * TS_RW * s + s) * sizeof(double);
+    size_t shm_l = shm + (size_t)s * (s + 1) / 2 * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        RPC_CUDA(cudaFuncSetAttribute(panel_trsm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        RPC_CUDA(cudaFuncSetAttribute(panel_trsm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    int rows_per_cta = TS_WARPS * TS_RW;
+    int blocks = (k_pad + rows_per_cta - 1) / rows_per_cta;
+    if (shm_l <= 227 * 1024)
+        panel_trsm_kernel<true><<<blocks, TS_WARPS * 32, shm_l, st>>>(P, ldP, c, acc, s, L, ldl, At, ldat, k_pad, s_dev, ld_table);
+    else
+        panel_trsm_kernel<false><<<blocks, TS_WARPS * 32, shm, st>>>(P, ldP, c, acc, s, L, ldl, At, ldat, k_pad, s_dev, ld_table);
+    RPC_LAUNCHED(ctx);
+    return 0;
+}
+
+// rpc_build_panel (mode 0) + rpc_compact_selected with the accepted count read ON THE DEVICE from *s_dev (<= s_max): both
+// can be enqueued right behind the rejection kernel, before the host has read the round back, so the host's wake-up and
+// launch latency hides behind them.  The panel uses ldat = rpc_panel_ld(*s_dev) and k_pad = (c + *s_dev) rounded up to 16.
+extern "C" int rpc_build_panel_dev(rpc_ctx *ctx, void *stream, const double *P, int64_t ldP, int c, const int32_t *acc,
+                                   const int32_t *s_dev, int s_max, const double *L, int64_t ldl, double *At,
+                                   const int64_t *idx, const double *Xpiv, const double *pnorm, int64_t ldp, int64_t *sel_idx,
+                                   double *Xsel, double *nsel) {
+    RPC_CHECK_ARG(ctx && L && At && acc && s_dev && idx && sel_idx, "null pointer");
+    RPC_CHECK_ARG(s_max >= 1 && s_max <= 768 && c >= 0 && (c == 0 || P), "bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!ctx->panel_ld_table) {
+        int32_t host[257];
+        for (int q = 0; q <= 256; ++q) host[q] = q == 0 ? rpc_panel_ld(1) : rpc_panel_ld(q);
+        RPC_CUDA(cudaMalloc((void **)&ctx->panel_ld_table, sizeof(host)));
+        RPC_CUDA(cudaMemcpy(ctx->panel_ld_table, host, sizeof(host), cudaMemcpyHostToDevice));
+    }
+    const int k_pad_max = (c + s_max + RPC_KT - 1) / RPC_KT * RPC_KT;
+    int rc = launch_panel_trsm(ctx, st, P, ldP, c, acc, s_max, L, ldl, At, 0, k_pad_max, s_dev, ctx->panel_ld_table);
+    if (rc) return rc;
+    compact_selected_kernel<<<s_max, 64, 0, st>>>(acc, s_max, idx, Xpiv, pnorm, ldp, sel_idx, Xsel, nsel, s_dev);
+    RPC_LAUNCHED(ctx);
+    return 0;
+}
+
 extern "C" int rpc_build_panel(rpc_ctx *ctx, void *stream, const double *P, int64_t ldP, int c, const int32_t *acc, int s,
                                const double *L, int64_t ldl, int mode, double *At, int64_t ldat, int k_pad) {
     RPC_CHECK_ARG(ctx && L && At, "null pointer");
     RPC_CHECK_ARG(s >= 1 && s <= 768 && c >= 0 && (c == 0 || P), "bad sizes");
     RPC_CHECK_ARG(k_pad >= c + s && ldat >= s, "k_pad >= c+s and ldat >= s required");
     cudaStream_t st = (cudaStream_t)stream;
-    if (mode == 0) {
-        size_t shm = ((size_t)TS_WARPS * TS_RW * s + s) * sizeof(double);
-        size_t shm_l = shm + (size_t)s * (s + 1) / 2 * sizeof(double);
-        static bool configured = false;
-        if (!configured) {
-            RPC_CUDA(cudaFuncSetAttribute(panel_trsm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-            RPC_CUDA(cudaFuncSetAttribute(panel_trsm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            configured = true;
-        }
-        int rows_per_cta = TS_WARPS * TS_RW;
-        int blocks = (k_pad + rows_per_cta - 1) / rows_per_cta;
-        if (shm_l <= 227 * 1024)
-            panel_trsm_kernel<true><<<blocks, TS_WARPS * 32, shm_l, st>>>(P, ldP, c, acc, s, L, ldl, At, ldat, k_pad);
-        else
-            panel_trsm_kernel<false><<<blocks, TS_WARPS * 32, shm, st>>>(P, ldP, c, acc, s, L, ldl, At, ldat, k_pad);
-        RPC_LAUNCHED(ctx);
-        return 0;
-    }
+    if (mode == 0) return launch_panel_trsm(ctx, st, P, ldP, c, acc, s, L, ldl, At, ldat, k_pad, nullptr, nullptr);
     // Minv given in L (dense s x s): MiT[i][j] = L[j][i]
     const int lds = (s + 7) & ~7;
     int rc = rpc_ws_reserve(ctx, (size_t)s * lds * sizeof(double));
@@ -659,8 +701,10 @@ extern "C" int rpc_build_panel(rpc_ctx *ctx, void *stream, const double *P, int6
 // ------------------------------------------------------------------------------------------------
 __global__ void compact_selected_kernel(const int32_t *__restrict__ acc, int s, const int64_t *__restrict__ idx,
                                         const double *__restrict__ Xpiv, const double *__restrict__ pnorm, int64_t ldp,
-                                        int64_t *__restrict__ sel_idx, double *__restrict__ Xsel, double *__restrict__ nsel) {
+                                        int64_t *__restrict__ sel_idx, double *__restrict__ Xsel, double *__restrict__ nsel,
+                                        const int32_t *__restrict__ s_dev) {
     const int j = blockIdx.x;
+    if (s_dev && j >= *s_dev) return;
     const int src = acc ? acc[j] : j;
     if (threadIdx.x == 0) {
         sel_idx[j] = idx[src];
@@ -674,7 +718,7 @@ extern "C" int rpc_compact_selected(rpc_ctx *ctx, void *stream, const int32_t *a
                                     const double *Xpiv, const double *pnorm, int64_t ldp, int64_t *sel_idx, double *Xsel,
                                     double *nsel) {
     RPC_CHECK_ARG(ctx && idx && sel_idx && s >= 1, "null pointer or bad sizes");
-    compact_selected_kernel<<<s, 64, 0, (cudaStream_t)stream>>>(acc, s, idx, Xpiv, pnorm, ldp, sel_idx, Xsel, nsel);
+    compact_selected_kernel<<<s, 64, 0, (cudaStream_t)stream>>>(acc, s, idx, Xpiv, pnorm, ldp, sel_idx, Xsel, nsel, nullptr);
     RPC_LAUNCHED(ctx);
     return 0;
 }

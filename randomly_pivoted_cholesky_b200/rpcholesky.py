@@ -133,7 +133,11 @@ class _State:
         A._count(self.n)                                       # A.diag() counts N queries (matrix.py:33-39)
 
     def readback(self, m, with_chol=True):
-        """The round's host sync.  A tiny kernel writes [seq | stats | info | acc[:m] | idx[:m]] straight into pinned
+        self.publish(m, with_chol)
+        return self.collect(m)
+
+    def publish(self, m, with_chol=True):
+        """The round's host sync, device half.  A tiny kernel writes [seq | stats | info | acc[:m] | idx[:m]] straight into pinned
         host memory and the host spins on the sequence word: no stream synchronisation (~100 us of wake-up latency
         on this box), no staging copies.  Returns (stats[4], info[4], acc[m], idx[m]) as numpy arrays."""
         need = 9 + 2 * m
@@ -146,6 +150,11 @@ class _State:
         check(self.lib.rpc_publish_round(self.ctx.handle, _stream(), _ptr(self.stats), _ptr(self.info_dev) if with_chol else None,
                                          _ptr(self.acc) if with_chol else None, _ptr(self.idx_dev), m,
                                          C.c_void_p(self.rb_host.data_ptr()), seq), "rpc_publish_round")
+
+    def collect(self, m):
+        """Host half of the round's sync: spin on the sequence word of the last publish()."""
+        need = 9 + 2 * m
+        seq = float(self.rb_seq)
         buf = self.rb_np
         spins = 0
         while buf[0] != seq:
@@ -224,19 +233,34 @@ class _State:
                                               float(shift), _ptr(self.L), self.m_max, _ptr(self.acc), _ptr(self.info_dev)),
               "rpc_rejection_cholesky")
 
-    def update(self, c, s, acc_dev, idx_dev, panel_mode=0, Lmat=None):
+    def prelaunch_panel(self, c, s_max):
+        """Panel solve + compaction of the accepted pivots with the accepted count read on the device (info_dev[0]):
+        enqueued behind the rejection kernel BEFORE the host reads the round back, so the host's wake-up and launch
+        latency hides behind them.  update(..., panel_done=True) then only evaluates the rows and runs the Schur update."""
+        piv = self.piv
+        check(self.lib.rpc_build_panel_dev(self.ctx.handle, _stream(), _ptr(self.P), self.m_max, c, _ptr(self.acc),
+                                           _ptr(self.info_dev), s_max, _ptr(self.L), self.L.stride(0), _ptr(self.At),
+                                           _ptr(self.idx_dev), _ptr(piv.X) if piv is not None else None,
+                                           _ptr(piv.norm) if piv is not None else None, self.ldx, _ptr(self.sel_dev),
+                                           _ptr(self.sel.X) if piv is not None else None,
+                                           _ptr(self.sel.norm) if piv is not None else None), "rpc_build_panel_dev")
+
+    def update(self, c, s, acc_dev, idx_dev, panel_mode=0, Lmat=None, panel_done=False):
         """rows[c:c+s] = A[S,:]; G[c:c+s] = L^{-1}(rows - P^T G[:c]); diag update (rpcholesky.py:101-107,128-129 /
         205-209) on this rank's columns.  S = idx[acc] (acc None: all of idx); the selected pivot points are
         compacted out of the (already exchanged) payload, so no further communication is needed."""
         k_pad = _round_up(c + s, KT)
         ldat = int(self.lib.rpc_panel_ld(s))          # stride that lets the kernel fetch a panel stage in one bulk copy
         Lm = self.L if Lmat is None else Lmat
-        with _timed("panel", 1.0 * s * s * c + s ** 3 / 3.0, 8.0 * c * s):
-            check(self.lib.rpc_build_panel(self.ctx.handle, _stream(), _ptr(self.P), self.m_max, c, _ptr(acc_dev), s,
-                                           _ptr(Lm), Lm.stride(0), panel_mode, _ptr(self.At), ldat, k_pad),
-                  "rpc_build_panel")
+        if not panel_done:
+            with _timed("panel", 1.0 * s * s * c + s ** 3 / 3.0, 8.0 * c * s):
+                check(self.lib.rpc_build_panel(self.ctx.handle, _stream(), _ptr(self.P), self.m_max, c, _ptr(acc_dev), s,
+                                               _ptr(Lm), Lm.stride(0), panel_mode, _ptr(self.At), ldat, k_pad),
+                      "rpc_build_panel")
         A = self.A
-        if acc_dev is not None:
+        if panel_done:
+            sel_idx, sel_piv = self.sel_dev, self.sel
+        elif acc_dev is not None:
             piv = self.piv
             check(self.lib.rpc_compact_selected(self.ctx.handle, _stream(), _ptr(acc_dev), s, _ptr(idx_dev),
                                                 _ptr(piv.X) if piv is not None else None,
@@ -511,7 +535,10 @@ def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
             st.residual_block(st.idx_dev, b, counter)              # :189
         with _timed("reject", b ** 3 / 3.0, 8.0 * b * b):
             st.cholesky(b, 0, k - counter, 0.0, b)                 # :190 + truncation :193-196
-        stats_host, info, acc_host, idx_host = st.readback(b)                       # the round's only sync
+        st.publish(b)
+        with _timed("panel", 1.0 * b * b * counter, 8.0 * counter * b):
+            st.prelaunch_panel(counter, b)                         # runs while the host wakes up
+        stats_host, info, acc_host, idx_host = st.collect(b)                        # the round's only sync
         _raise_if_invalid(stats_host)
         if orig_trace is None:
             orig_trace = float(stats_host[0])
@@ -528,7 +555,7 @@ def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
         arr_idx[counter:counter + num_sel] = idx
         t1 = time.perf_counter()
         if num_sel > 0:
-            st.update(counter, num_sel, st.acc, st.idx_dev)
+            st.update(counter, num_sel, st.acc, st.idx_dev, panel_done=True)
         counter += num_sel
         rounds.append(num_sel)
         if auto_b:                                             # :211-220, on device-synchronised wall time
