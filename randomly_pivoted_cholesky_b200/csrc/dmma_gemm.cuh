@@ -249,14 +249,26 @@ __device__ __forceinline__ void eval_epilogue(const Params &p, double (&acc)[C::
         if (i < mi_cnt && row < p.m_valid) {
             const double pn = p.pnorm[row];
             double *dst = out + (int64_t)row * ldo + col0 + n0 + 2 * lk;
+            // sklearn: D2 = ((-2 * X.Y^T) + XX) + YY, clamped at 0
+            double dd[C::NI][2];
 #pragma unroll
-            for (int j = 0; j < C::NI; ++j) {
-                // sklearn: D2 = ((-2 * X.Y^T) + XX) + YY, clamped at 0
-                double d0 = (-2.0 * acc[i][j][0] + pn) + xn[j][0];
-                double d1 = (-2.0 * acc[i][j][1] + pn) + xn[j][1];
-                d0 = d0 > 0.0 ? d0 : 0.0;
-                d1 = d1 > 0.0 ? d1 : 0.0;
-                *reinterpret_cast<double2 *>(dst + j * 8) = kern_from_d2_pair(p.kp, d0, d1);
+            for (int j = 0; j < C::NI; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const double v = (-2.0 * acc[i][j][e] + pn) + xn[j][e];
+                    dd[j][e] = v > 0.0 ? v : 0.0;
+                }
+            if (p.kp.kind == RPC_KERN_GAUSSIAN && (C::NI == 4 || C::NI == 2)) {
+                // the whole fragment row in one out-of-line call: 2*NI interleaved exp chains
+                if (C::NI == 4)
+                    gauss_store8(p.kp.gscale, dst, dd[0][0], dd[0][1], dd[1][0], dd[1][1], dd[2 % C::NI][0], dd[2 % C::NI][1],
+                                 dd[3 % C::NI][0], dd[3 % C::NI][1]);
+                else
+                    gauss_store4(p.kp.gscale, dst, dd[0][0], dd[0][1], dd[1][0], dd[1][1]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < C::NI; ++j)
+                    *reinterpret_cast<double2 *>(dst + j * 8) = kern_from_d2_pair(p.kp, dd[j][0], dd[j][1]);
             }
         }
     }

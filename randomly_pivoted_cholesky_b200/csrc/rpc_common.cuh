@@ -97,6 +97,55 @@ static __device__ __noinline__ double2 kern_from_d2_pair(const KernParams kp, do
     return make_double2(kern_from_d2(kp, d0), kern_from_d2(kp, d1));
 }
 
+// Gaussian epilogue of the DMMA evaluator: exp(x) for x = d2 * gscale <= 0, N values at a time so that the N polynomial
+// chains interleave (the pair version above leaves the FP64 pipe waiting on two dependent Horner chains).  Cody-Waite
+// reduction x = n ln2 + r, |r| <= ln2/2, degree-13 Taylor polynomial (remainder 4e-18 relative), scaling by 2^n through the
+// exponent bits.  No special cases are needed on this domain: x <= 0, and below -708 (value < 3.3e-308, where CUDA's exp
+// returns denormals) the result is flushed to 0.  <= 2 ulp from the correctly rounded value.
+template <int N>
+__device__ __forceinline__ void exp_neg_batch(double (&x)[N]) {
+    double nf[N], r[N], pl[N];
+    int ni[N];
+#pragma unroll
+    for (int t = 0; t < N; ++t) {
+        const double xc = x[t] > -708.0 ? x[t] : -708.0;
+        const double tm = fma(xc, 1.4426950408889634, 6755399441055744.0);      // round(x log2 e) in the low mantissa bits
+        ni[t] = __double2loint(tm);
+        nf[t] = tm - 6755399441055744.0;
+        r[t] = fma(nf[t], -6.93147180369123816490e-01, xc);
+        r[t] = fma(nf[t], -1.90821492927058770002e-10, r[t]);
+        pl[t] = 1.6059043836821613e-10;                                           // 1/13!
+    }
+    const double cf[12] = {2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, 2.7557319223985893e-06,
+                           2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03, 8.333333333333333e-03,
+                           4.1666666666666664e-02, 1.6666666666666666e-01, 0.5, 1.0};
+#pragma unroll
+    for (int c = 0; c < 12; ++c)
+#pragma unroll
+        for (int t = 0; t < N; ++t) pl[t] = fma(pl[t], r[t], cf[c]);
+#pragma unroll
+    for (int t = 0; t < N; ++t) {
+        pl[t] = fma(pl[t], r[t], 1.0);
+        const double sc = __hiloint2double((ni[t] + 1023) << 20, 0);              // 2^n, n in [-1022, 0]
+        x[t] = x[t] > -708.0 ? pl[t] * sc : 0.0;
+    }
+}
+
+// one row of a warp's C fragment block: 2 * NI squared distances -> Gaussian kernel values, stored as NI double2
+static __device__ __noinline__ void gauss_store8(double gscale, double *dst, double d0, double d1, double d2, double d3,
+                                                 double d4, double d5, double d6, double d7) {
+    double x[8] = {d0 * gscale, d1 * gscale, d2 * gscale, d3 * gscale, d4 * gscale, d5 * gscale, d6 * gscale, d7 * gscale};
+    exp_neg_batch<8>(x);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) *reinterpret_cast<double2 *>(dst + j * 8) = make_double2(x[2 * j], x[2 * j + 1]);
+}
+static __device__ __noinline__ void gauss_store4(double gscale, double *dst, double d0, double d1, double d2, double d3) {
+    double x[4] = {d0 * gscale, d1 * gscale, d2 * gscale, d3 * gscale};
+    exp_neg_batch<4>(x);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) *reinterpret_cast<double2 *>(dst + j * 8) = make_double2(x[2 * j], x[2 * j + 1]);
+}
+
 __device__ __forceinline__ double kern_from_l1(const KernParams &kp, double l1) { return exp(-l1 / kp.bw); }
 static __device__ __noinline__ double2 kern_from_l1_pair(const KernParams kp, double a, double b) {
     return make_double2(exp(-a / kp.bw), exp(-b / kp.bw));
