@@ -10,12 +10,13 @@ All numerical work is done by hand-written sm_100a CUDA kernels behind the C ABI
 from .lra import AbstractPSDLowRank, CompactEigenvalueDecomposition, PSDLowRank
 from .matrix import AbstractPSDMatrix, KernelMatrix, NonsymmetricKernelMatrix, PSDMatrix
 from .KRR_Nystrom import KRR_Nystrom
-from .rpcholesky import (accelerated_rpcholesky, block_cholesky_helper, block_rpcholesky, cholesky_helper, greedy,
-                         rpcholesky, simple_rpcholesky)
+from .rpcholesky import (accelerated_rpcholesky, block_cholesky_helper, block_greedy, block_rpcholesky, cholesky_helper,
+                         greedy, rpcholesky, simple_rpcholesky)
+from .rpqr import accelerated_rpqr, rpqr
 from ._lib import build, load, total_launches
 
 __all__ = [
     "AbstractPSDLowRank", "CompactEigenvalueDecomposition", "PSDLowRank", "AbstractPSDMatrix", "KernelMatrix",
-    "PSDMatrix", "NonsymmetricKernelMatrix", "KRR_Nystrom", "accelerated_rpcholesky", "block_cholesky_helper", "block_rpcholesky", "cholesky_helper", "greedy",
+    "PSDMatrix", "NonsymmetricKernelMatrix", "KRR_Nystrom", "accelerated_rpcholesky", "block_cholesky_helper", "block_rpcholesky", "cholesky_helper", "greedy", "block_greedy", "accelerated_rpqr", "rpqr",
     "rpcholesky", "simple_rpcholesky", "build", "load", "total_launches",
 ]

@@ -531,3 +531,78 @@ def test_nonsymmetric_kernel_matrix_and_out_of_sample(rpc):
         np.testing.assert_allclose(K[:, np.array([1, 300])], want[:, [1, 300]], rtol=1e-12, atol=1e-14)
         A = rpc.KernelMatrix(Y, kernel=kernel, bandwidth=1.7, **kw)
         np.testing.assert_allclose(A.out_of_sample(X, [4, 8, 15]), want[:, [4, 8, 15]], rtol=1e-12, atol=1e-14)
+
+
+# ---- accelerated RPQR: sampler + rejection Cholesky reused, QR / GEMM from the libraries ------
+from make_golden_rpqr import RPQR_CASES, rpqr_inputs  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(RPQR_CASES))
+def test_rpqr_matches_reference(rpc, name):
+    from randomly_pivoted_cholesky_b200.rpqr import accelerated_rpqr, rpqr
+    spec = RPQR_CASES[name]
+    gold = load(name)
+    B = rpqr_inputs(spec)
+    with replay(spec["seed"]):
+        Q, F, idx = accelerated_rpqr(B, spec["k"], b=spec["b"])
+    assert np.array_equal(np.asarray(idx, dtype=np.int64), gold["idx"]), "pivots must be bit-exact"
+    assert relerr(Q, gold["Q"]) <= 1e-9 and relerr(F, gold["F"]) <= 1e-9
+    np.testing.assert_allclose(Q.T @ Q, np.eye(spec["k"]), atol=1e-12)
+    # auto b (wall-clock dependent, like the reference): structural properties only
+    Q2, F2, idx2 = rpqr(B, spec["k"])
+    np.testing.assert_allclose(Q2.T @ Q2, np.eye(spec["k"]), atol=1e-12)
+    np.testing.assert_allclose(F2, B.T @ Q2, rtol=1e-10, atol=1e-12)
+    assert len(set(int(i) for i in idx2)) == spec["k"]
+
+
+def test_rpqr_large_against_oracle(rpc):
+    from oracle import rpqr_oracle
+    from randomly_pivoted_cholesky_b200.rpqr import accelerated_rpqr
+    rng0 = np.random.default_rng(9)
+    m, n, k, b = 300, 20000, 120, 40
+    B = rng0.standard_normal((m, 60)) @ rng0.standard_normal((60, n)) + 0.05 * rng0.standard_normal((m, n))
+    with replay(5):
+        Q, F, idx = accelerated_rpqr(B, k, b=b)
+    rng, legacy = orc.make_streams(5)
+    Qw, Fw, idxw, _ = rpqr_oracle.accelerated_rpqr(B, k, b, rng, legacy)
+    assert np.array_equal(np.asarray(idx, dtype=np.int64), np.asarray(idxw, dtype=np.int64))
+    assert relerr(Q, Qw) <= 1e-8 and relerr(F, Fw) <= 1e-8
+
+
+# ---- Nystrom-preconditioned CG --------------------------------------------------------
+@pytest.mark.parametrize("kernel,kw,bw", [("gaussian", {}, 2.0), ("laplace", {}, 6.0), ("matern", {"nu": 1.5}, 2.5)])
+def test_nystrom_pcg_matches_oracle(rpc, kernel, kw, bw):
+    from make_golden_pcg import pcg_precond_inputs
+    from oracle import pcg_oracle
+    from randomly_pivoted_cholesky_b200.pcg import NystromPreconditioner, kernel_matvec, pcg
+    import torch
+    rng0 = np.random.default_rng(21)
+    n, d, k, b, mu = 1500, 5, 300, 50, 0.05
+    X = rng0.standard_normal((n, d))
+    y = np.sin(X[:, 0]) + 0.1 * rng0.standard_normal(n)
+    A = rpc.KernelMatrix(X, kernel=kernel, bandwidth=bw, **kw)
+    with replay(31):
+        lra = rpc.accelerated_rpcholesky(A, k, b=b)
+    A0 = orc.OracleKernelMatrix(X, kernel=kernel, bandwidth=bw, **kw)
+    K = A0.rows(np.arange(n))
+    # the blocked device mat-vec against the dense product
+    p = rng0.standard_normal(n)
+    got = kernel_matvec(A, torch.from_numpy(p).to(A.device), block_rows=200).cpu().numpy()
+    assert relerr(got, K @ p) <= 1e-12
+    # preconditioner: the reference's eigen-form solve (lra.py:78-80) on the fixture, and the oracle on this factor
+    Gf, vf, muf = pcg_precond_inputs()
+    pre_f = NystromPreconditioner(torch.from_numpy(Gf).to(A.device), muf)
+    assert relerr(pre_f(torch.from_numpy(vf).to(A.device)).cpu().numpy(), load("pcg_precond")["out"]) <= 1e-9
+    pre = NystromPreconditioner(lra, mu)
+    v = rng0.standard_normal(n)
+    assert relerr(pre(torch.from_numpy(v).to(A.device)).cpu().numpy(), pcg_oracle.nystrom_preconditioner(lra.G, mu)(v)) <= 1e-9
+    # the solve, iterate for iterate
+    x, resid = pcg(A, y, mu, pre, tol=1e-10, max_iters=80, block_rows=256)
+    xw, residw = pcg_oracle.pcg(K, y, mu, pcg_oracle.nystrom_preconditioner(lra.G, mu), tol=1e-10, max_iters=80)
+    assert resid[-1] < 1e-10 and abs(len(resid) - len(residw)) <= 1
+    q = min(8, len(resid), len(residw))
+    np.testing.assert_allclose(resid[:q], residw[:q], rtol=1e-6)          # CG amplifies round-off later on
+    exact = np.linalg.solve(K + mu * np.eye(n), y)
+    assert relerr(x, exact) <= 1e-8 and relerr(xw, exact) <= 1e-8
+    x0, resid0 = pcg(A, y, mu, None, tol=1e-10, max_iters=80)
+    assert len(resid) < len(resid0) or resid[-1] < resid0[-1]              # the preconditioner pays

@@ -161,3 +161,46 @@ def test_krr_oracle_matches_reference(name):
     np.testing.assert_allclose(sol, gold["sol"], rtol=1e-7, atol=1e-9)
     preds = krr_oracle.predict_nystrom(Xts, Xtr, idx, sol, spec["kernel"], spec["bw"])
     np.testing.assert_allclose(preds, gold["preds"], rtol=1e-8, atol=1e-10)
+
+
+# ---- accelerated RPQR -----------------------------------------------------------------
+from make_golden_rpqr import RPQR_CASES, rpqr_inputs  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(RPQR_CASES))
+def test_rpqr_oracle_matches_reference(name):
+    from oracle import rpqr_oracle
+    spec = RPQR_CASES[name]
+    gold = load(name)
+    B = rpqr_inputs(spec)
+    rng, legacy = orc.make_streams(spec["seed"])
+    Q, F, idx, _ = rpqr_oracle.accelerated_rpqr(B, spec["k"], spec["b"], rng, legacy)
+    assert np.array_equal(np.asarray(idx, dtype=np.int64), gold["idx"])
+    assert relerr(Q, gold["Q"]) <= 1e-12 and relerr(F, gold["F"]) <= 1e-12
+
+
+# ---- Nystrom-preconditioned CG ---------------------------------------------------------
+def test_pcg_oracle_preconditioner_matches_reference_krr():
+    from make_golden_pcg import pcg_precond_inputs
+    from oracle import pcg_oracle
+    G, v, mu = pcg_precond_inputs()
+    out = pcg_oracle.nystrom_preconditioner(G, mu)(v)
+    assert relerr(out, load("pcg_precond")["out"]) <= 1e-10
+    # it is the inverse of G^T G + mu I
+    np.testing.assert_allclose((G.T @ G + mu * np.eye(G.shape[1])) @ out, v, rtol=1e-8, atol=1e-8)
+
+
+def test_pcg_oracle_solves_the_system():
+    from oracle import pcg_oracle
+    rng = np.random.default_rng(8)
+    X = rng.standard_normal((200, 4))
+    A = orc.OracleKernelMatrix(X, kernel="gaussian", bandwidth=2.0)
+    K = A.rows(np.arange(200))
+    y = rng.standard_normal(200)
+    mu = 1e-2
+    rs, lg = orc.make_streams(3)
+    res = orc.accelerated_rpcholesky(orc.OracleKernelMatrix(X, kernel="gaussian", bandwidth=2.0), 40, 10, rs, lg)
+    x, resid = pcg_oracle.pcg(K, y, mu, pcg_oracle.nystrom_preconditioner(res.G, mu), tol=1e-10, max_iters=200)
+    np.testing.assert_allclose(x, np.linalg.solve(K + mu * np.eye(200), y), rtol=1e-6, atol=1e-8)
+    x0, resid0 = pcg_oracle.pcg(K, y, mu, None, tol=1e-10, max_iters=200)
+    assert len(resid) < len(resid0)            # the preconditioner pays
