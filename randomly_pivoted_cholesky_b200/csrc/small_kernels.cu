@@ -280,11 +280,14 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rejection_cholesky_kernel(doubl
     const unsigned full = 0xffffffffu;
 
     if (PACKED) {
-        // flat, coalesced sweep over the m x m block with several independent loads in flight per thread
-#pragma unroll 4
-        for (int q = tid; q < m * m; q += RC_THREADS) {
-            const int i = q / m, l = q - i * m;
-            if (l <= i) T[tri_at<true>(i, l, ld)] = H[(int64_t)i * ldh + l];
+        // lower triangle only, a warp per row (coalesced, no index division), four rows in flight per warp
+        for (int i0 = warp * 4; i0 < m; i0 += NW * 4) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const int i = i0 + w;
+                if (i < m)
+                    for (int l = lane; l <= i; l += 32) T[tri_at<true>(i, l, ld)] = H[(int64_t)i * ldh + l];
+            }
         }
     }
     // trace check (np.trace(H) <= 0 -> RuntimeError): only the sign matters, so the summation order does not
@@ -389,8 +392,41 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rejection_cholesky_kernel(doubl
                 }
             }
             __syncthreads();
-            // ---- step 3: trailing lower triangle T[i,l] -= sum_a L[i,a] L[l,a], j0+nb <= l <= i; a warp takes two
-            // rows at a time (two independent FMA chains per L[l,a] load)
+            // ---- step 3: trailing lower triangle T[i,l] -= sum_a L[i,a] L[l,a], j0+nb <= l <= i.
+            if (PACKED && nb == RB) {
+                // FP64 tensor cores: the rank-8 update of an 8 x 8 tile is two DMMA.8x8x4 (A = -L[i-block, 0:8],
+                // B = L[l-block, 0:8]^T), i.e. 14 instructions per 64 entries instead of ~70.  A warp owns whole
+                // block rows ("strips", A fragments loaded once per strip); strips are dealt longest-first in snake
+                // order so every warp gets about the same number of tiles.
+                const int t0 = (j0 + RB) >> 3, mt = (m + 7) >> 3, nst = mt - t0;
+                const int r = lane >> 2, kq = lane & 3;
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int si = pass == 0 ? warp : 2 * NW - 1 - warp;          // strip rank by length (0 = longest)
+                    if (si >= nst) continue;
+                    const int I = mt - 1 - si, i0 = I << 3, i = i0 + r;
+                    const bool iok = i < m;
+                    const double a0 = (iok && kq < na) ? -Lb[kq * m + i] : 0.0;
+                    const double a1 = (iok && 4 + kq < na) ? -Lb[(4 + kq) * m + i] : 0.0;
+                    const size_t rowbase = (size_t)i * (i + 1) / 2;
+                    for (int J = t0; J <= I; ++J) {
+                        const int l0 = J << 3, lb = l0 + r, l = l0 + 2 * kq;
+                        const bool lok = lb < m;
+                        const double b0 = (lok && kq < na) ? Lb[kq * m + lb] : 0.0;
+                        const double b1 = (lok && 4 + kq < na) ? Lb[(4 + kq) * m + lb] : 0.0;
+                        const bool v0 = iok && l <= i, v1 = iok && l + 1 <= i;
+                        double cfrag[2];
+                        cfrag[0] = v0 ? T[rowbase + l] : 0.0;
+                        cfrag[1] = v1 ? T[rowbase + l + 1] : 0.0;
+                        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                            : "+d"(cfrag[0]), "+d"(cfrag[1]) : "d"(a0), "d"(b0));
+                        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                            : "+d"(cfrag[0]), "+d"(cfrag[1]) : "d"(a1), "d"(b1));
+                        if (v0) T[rowbase + l] = cfrag[0];
+                        if (v1) T[rowbase + l + 1] = cfrag[1];
+                    }
+                }
+            } else
+            // a warp takes two rows at a time (two independent FMA chains per L[l,a] load)
             for (int i = j0 + nb + 2 * warp; i < m; i += 2 * NW) {
                 const bool two = i + 1 < m;
                 double li0[RB], li1[RB];
@@ -423,10 +459,9 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rejection_cholesky_kernel(doubl
     }
     __syncthreads();
     // L = Lfull[acc, acc] (rpcholesky.py:155-156)
-#pragma unroll 4
-    for (int q = tid; q < nacc * nacc; q += RC_THREADS) {
-        int r = q / nacc, a = q - r * nacc;
-        L[(int64_t)r * ldl + a] = a <= r ? Lfull[(size_t)accpos[r] * m + a] : 0.0;
+    for (int r = warp; r < nacc; r += NW) {                      // a warp per row: no index division, no loads above the diagonal
+        const double *src = Lfull + (size_t)accpos[r] * m;
+        for (int a = lane; a < nacc; a += 32) L[(int64_t)r * ldl + a] = a <= r ? src[a] : 0.0;
     }
     for (int q = tid; q < nacc; q += RC_THREADS) acc[q] = accpos[q];
     if (tid == 0) info[0] = nacc;
