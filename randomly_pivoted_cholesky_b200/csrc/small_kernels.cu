@@ -282,11 +282,13 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rejection_cholesky_kernel(doubl
     if (PACKED) {
         // lower triangle only, a warp per row (coalesced, no index division), four rows in flight per warp
         for (int i0 = warp * 4; i0 < m; i0 += NW * 4) {
+            for (int l = lane; l <= i0 + 3; l += 32) {
+                double v[4];
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                const int i = i0 + w;
-                if (i < m)
-                    for (int l = lane; l <= i; l += 32) T[tri_at<true>(i, l, ld)] = H[(int64_t)i * ldh + l];
+                for (int w = 0; w < 4; ++w) v[w] = (i0 + w < m && l <= i0 + w) ? H[(int64_t)(i0 + w) * ldh + l] : 0.0;
+#pragma unroll
+                for (int w = 0; w < 4; ++w)
+                    if (i0 + w < m && l <= i0 + w) T[tri_at<true>(i0 + w, l, ld)] = v[w];
             }
         }
     }
@@ -321,7 +323,9 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rejection_cholesky_kernel(doubl
                 lrow[cc] = 0.0;
             }
             int na = 0, stop = 0, cols[RB];
-            double rinvs[RB];
+            double rinvs[RB], thr8[RB];
+#pragma unroll
+            for (int jj = 0; jj < RB; ++jj) thr8[jj] = jj < nb ? thr[j0 + jj] : 0.0;    // off the serial chain
 #pragma unroll
             for (int jj = 0; jj < RB; ++jj) {
                 if (jj < nb && !stop) {                                   // warp-uniform
@@ -335,7 +339,7 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rejection_cholesky_kernel(doubl
                             accept = false;
                         }
                     } else {
-                        accept = thr[j0 + jj] < hjj;                      // rpcholesky.py:151
+                        accept = thr8[jj] < hjj;                          // rpcholesky.py:151
                     }
                     if (accept && nacc + na == max_accept) { stop = 1; accept = false; }   // truncation, :193-196
                     if (accept) {
@@ -408,6 +412,7 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rejection_cholesky_kernel(doubl
                     const double a0 = (iok && kq < na) ? -Lb[kq * m + i] : 0.0;
                     const double a1 = (iok && 4 + kq < na) ? -Lb[(4 + kq) * m + i] : 0.0;
                     const size_t rowbase = (size_t)i * (i + 1) / 2;
+#pragma unroll 4
                     for (int J = t0; J <= I; ++J) {
                         const int l0 = J << 3, lb = l0 + r, l = l0 + 2 * kq;
                         const bool lok = lb < m;
@@ -459,9 +464,19 @@ __global__ void __launch_bounds__(RC_THREADS, 1) rejection_cholesky_kernel(doubl
     }
     __syncthreads();
     // L = Lfull[acc, acc] (rpcholesky.py:155-156)
-    for (int r = warp; r < nacc; r += NW) {                      // a warp per row: no index division, no loads above the diagonal
-        const double *src = Lfull + (size_t)accpos[r] * m;
-        for (int a = lane; a < nacc; a += 32) L[(int64_t)r * ldl + a] = a <= r ? src[a] : 0.0;
+    // a warp per four rows (four independent loads in flight): no index division, no loads above the diagonal
+    for (int r0 = warp * 4; r0 < nacc; r0 += NW * 4) {
+        const double *src[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) src[w] = Lfull + (size_t)accpos[r0 + w < nacc ? r0 + w : r0] * m;
+        for (int a = lane; a < nacc; a += 32) {
+            double v[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) v[w] = (r0 + w < nacc && a <= r0 + w) ? src[w][a] : 0.0;
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+                if (r0 + w < nacc) L[(int64_t)(r0 + w) * ldl + a] = v[w];
+        }
     }
     for (int q = tid; q < nacc; q += RC_THREADS) acc[q] = accpos[q];
     if (tid == 0) info[0] = nacc;
