@@ -210,6 +210,22 @@ int rpc_build_panel_dev(rpc_ctx *ctx, void *stream, const double *P, int64_t ldP
                         const int32_t *s_dev, int s_max, const double *L, int64_t ldl, double *At, const int64_t *idx,
                         const double *Xpiv, const double *pnorm, int64_t ldp, int64_t *sel_idx, double *Xsel, double *nsel);
 
+struct rpc_peers;
+/* Persistent kernels launched after this call use (SM count - count) CTAs: room for a single-CTA kernel (the rejection
+ * Cholesky) to run beside them on another stream.  count = 0 restores the default. */
+int rpc_ctx_reserve_sms(rpc_ctx *ctx, int count);
+
+/* dst[i, :] = src[rowmap[i], :] for i < *count_dev (<= max_rows), n_pad columns: the accepted rows of a speculatively
+ * evaluated proposal block, compacted into rows[c:c+s] = A[S,:] (rpcholesky.py:199).  The count is read on the device. */
+int rpc_gather_rows(rpc_ctx *ctx, void *stream, const double *src, int64_t lds, const int32_t *rowmap,
+                    const int32_t *count_dev, int max_rows, double *dst, int64_t ldd, int64_t n_pad);
+
+/* rpc_schur_update with the new rows taken from rows_src through a row map (new row i = rows_src[rowmap[i], :]; rowmap
+ * may be NULL) and, when peers != NULL, the fused diagonal exchange of rpc_schur_update_peers. */
+int rpc_schur_update_ex(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At, int64_t ldat,
+                        int k_pad, const double *rows_src, int64_t ldr, const int32_t *rowmap, double *diag, int64_t n_pad,
+                        const struct rpc_peers *peers, unsigned long long epoch);
+
 /* ---- peer-memory exchange for row-sharded runs (one process per GPU of one NVSwitch box) --------------------------
  * The two per-round exchanges of the sharded factorisation (the residual-diagonal all-gather and
  * the pivot-payload exchange) are done by the producing kernels themselves: they store their results straight into every

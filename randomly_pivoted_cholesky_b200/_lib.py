@@ -112,6 +112,10 @@ _SIGNATURES = {
     "rpc_fused_update_supported": (_INT, [C.POINTER(KernelSpec), _INT, _I64]),
     "rpc_fused_update": (_INT, [_P, _P, C.POINTER(KernelSpec), _P, _P, _I64, _INT, _I64, _P, _P, _I64, _P, _I64, _INT, _INT, _P,
                                 _I64, _INT, _P, _I64, _P]),
+    "rpc_ctx_reserve_sms": (_INT, [_P, _INT]),
+    "rpc_gather_rows": (_INT, [_P, _P, _P, _I64, _P, _P, _INT, _P, _I64, _I64]),
+    "rpc_schur_update_ex": (_INT, [_P, _P, _P, _I64, _INT, _INT, _P, _I64, _INT, _P, _I64, _P, _P, _I64, C.POINTER(Peers),
+                                   C.c_uint64]),
     "rpc_peer_alloc": (_INT, [_P, _I64, C.POINTER(_P), _P]),
     "rpc_peer_free": (_INT, [_P, _P]),
     "rpc_peer_open": (_INT, [_P, _P, C.POINTER(_P)]),
@@ -166,6 +170,7 @@ class Context:
     """One rpc_ctx per CUDA device (scratch + launch counter)."""
 
     _by_device = {}
+    _extra = []
 
     def __init__(self, device_index: int):
         self.lib = load()
@@ -182,9 +187,16 @@ class Context:
             cls._by_device[device_index] = ctx
         return ctx
 
+    @classmethod
+    def extra(cls, device_index: int) -> "Context":
+        """A further context on the device (own scratch) for work enqueued on a second stream."""
+        ctx = cls(device_index)
+        cls._extra.append(ctx)
+        return ctx
+
     def launch_count(self) -> int:
         return int(self.lib.rpc_ctx_launch_count(self.handle))
 
 
 def total_launches() -> int:
-    return sum(c.launch_count() for c in Context._by_device.values())
+    return sum(c.launch_count() for c in list(Context._by_device.values()) + Context._extra)

@@ -24,7 +24,8 @@ static int launch_gemm(rpc_ctx *ctx, cudaStream_t st, const Params &p, int64_t n
     // persistent: one CTA per SM walks the column tiles; the producer warp prefetches across tile boundaries
     Params q = p;
     q.ntiles = (int)(n_pad / C::N_TILE);
-    unsigned grid = (unsigned)(q.ntiles < ctx->sm_count ? q.ntiles : ctx->sm_count);
+    const int ctas = rpc_persistent_ctas(ctx);
+    unsigned grid = (unsigned)(q.ntiles < ctas ? q.ntiles : ctas);
     gemm_kernel<C, MODE><<<grid, C::THREADS, shm, st>>>(q);
     RPC_LAUNCHED(ctx);
     return 0;
@@ -119,8 +120,8 @@ static bool fused_fits(int m, int64_t ldx) {
 }
 
 static int schur_update_impl(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At, int64_t ldat,
-                             int k_pad, const double *rows_new, int64_t ldr, double *diag, int64_t n_pad, const rpc_peers *peers,
-                             unsigned long long epoch) {
+                             int k_pad, const double *rows_new, int64_t ldr, const int32_t *rowmap, double *diag, int64_t n_pad,
+                             const rpc_peers *peers, unsigned long long epoch) {
     RPC_CHECK_ARG(ctx && G && At && rows_new && diag, "null pointer");
     RPC_CHECK_ARG(s >= 1 && c >= 0, "s >= 1, c >= 0");
     RPC_CHECK_ARG(n_pad > 0 && n_pad % RPC_COL_ALIGN == 0, "n_pad must be a positive multiple of RPC_COL_ALIGN");
@@ -139,7 +140,7 @@ static int schur_update_impl(rpc_ctx *ctx, void *stream, double *G, int64_t ldg,
         RPC_CHECK_ARG(ldat >= m0 + tile_rows_for(m, true), "ldat too small for the zero-padded row tile");
         Params p{};
         p.At = At + m0; p.ldat = ldat; p.k_pad = k_pad; p.m_valid = m;
-        p.G = G; p.ldg = ldg; p.c = c; p.R = rows_new; p.ldr = ldr; p.K = c + s;
+        p.G = G; p.ldg = ldg; p.c = c; p.R = rows_new; p.ldr = ldr; p.K = c + s; p.rowmap = rowmap;
         p.Cout = G + (int64_t)(c + m0) * ldg; p.ldc = ldg; p.diag = diag;
         if (peers && m0 + 256 >= s) {
             // the last row chunk leaves the final diagonal: it stores it into every rank's copy and publishes the epoch
@@ -161,14 +162,20 @@ static int schur_update_impl(rpc_ctx *ctx, void *stream, double *G, int64_t ldg,
 extern "C" int rpc_schur_update(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At,
                                 int64_t ldat, int k_pad, const double *rows_new, int64_t ldr, double *diag,
                                 int64_t n_pad) {
-    return schur_update_impl(ctx, stream, G, ldg, c, s, At, ldat, k_pad, rows_new, ldr, diag, n_pad, nullptr, 0);
+    return schur_update_impl(ctx, stream, G, ldg, c, s, At, ldat, k_pad, rows_new, ldr, nullptr, diag, n_pad, nullptr, 0);
+}
+
+extern "C" int rpc_schur_update_ex(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At,
+                                   int64_t ldat, int k_pad, const double *rows_src, int64_t ldr, const int32_t *rowmap,
+                                   double *diag, int64_t n_pad, const rpc_peers *peers, unsigned long long epoch) {
+    return schur_update_impl(ctx, stream, G, ldg, c, s, At, ldat, k_pad, rows_src, ldr, rowmap, diag, n_pad, peers, epoch);
 }
 
 extern "C" int rpc_schur_update_peers(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At,
                                       int64_t ldat, int k_pad, const double *rows_new, int64_t ldr, double *diag, int64_t n_pad,
                                       const rpc_peers *peers, unsigned long long epoch) {
     RPC_CHECK_ARG(peers != nullptr, "peer table required");
-    return schur_update_impl(ctx, stream, G, ldg, c, s, At, ldat, k_pad, rows_new, ldr, diag, n_pad, peers, epoch);
+    return schur_update_impl(ctx, stream, G, ldg, c, s, At, ldat, k_pad, rows_new, ldr, nullptr, diag, n_pad, peers, epoch);
 }
 
 extern "C" int rpc_fused_update_supported(const rpc_kernel_spec *spec, int s, int64_t ldx) {

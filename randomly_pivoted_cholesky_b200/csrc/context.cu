@@ -47,6 +47,12 @@ extern "C" int rpc_ctx_destroy(rpc_ctx *ctx) {
     return 0;
 }
 
+extern "C" int rpc_ctx_reserve_sms(rpc_ctx *ctx, int count) {
+    RPC_CHECK_ARG(ctx && count >= 0 && count < ctx->sm_count, "count must be in [0, SM count)");
+    ctx->sm_reserved = count;
+    return 0;
+}
+
 extern "C" int64_t rpc_ctx_launch_count(const rpc_ctx *ctx) { return ctx ? ctx->launches : -1; }
 
 // cudaFree synchronises the device, so growing a buffer that in-flight kernels still read is safe.

@@ -104,7 +104,8 @@ static int launch_direct(rpc_ctx *ctx, cudaStream_t st, const KernParams &kp, co
         configured = true;
     }
     const int ntiles = (int)(n_pad / DE_TN);
-    const int grid = ntiles < ctx->sm_count ? ntiles : ctx->sm_count;
+    const int ctas = rpc_persistent_ctas(ctx);
+    const int grid = ntiles < ctas ? ntiles : ctas;
     direct_rows_tma<L1, PI><<<grid, DE_THREADS, shm, st>>>(kp, X, ldx, d, Pt, ldpt, s, out, ldo, ntiles);
     RPC_LAUNCHED(ctx);
     return 0;

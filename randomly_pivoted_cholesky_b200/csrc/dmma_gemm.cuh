@@ -67,6 +67,7 @@ struct Params {
     int c;
     const double *R;
     int64_t ldr;
+    const int32_t *rowmap;   // optional: new row i is row rowmap[i] of R (rows evaluated speculatively for ALL proposals)
     int K;
     double *Cout;
     int64_t ldc;
@@ -176,7 +177,7 @@ __device__ __forceinline__ void produce_stage(const Params &p, double *As, doubl
             const int kk = k0 + r;
             const double *src;
             if (kk < p.c) src = p.G + (int64_t)kk * p.ldg;
-            else if (kk < p.K) src = p.R + (int64_t)(kk - p.c) * p.ldr;
+            else if (kk < p.K) src = p.R + (int64_t)(p.rowmap ? p.rowmap[kk - p.c] : kk - p.c) * p.ldr;
             else src = p.R;                       // padded k: At is zero there, any finite row will do
             bulk_g2s(Bs + r * C::LDB, src + col0, C::N_TILE * 8, full);
         }

@@ -8,6 +8,7 @@
 struct rpc_ctx {
     int device;
     int sm_count;
+    int sm_reserved;   // SMs the persistent kernels leave free (rpc_ctx_reserve_sms): room for a concurrent single-CTA kernel
     int64_t launches;
     // scratch owned by the context (grown on demand, never shrunk)
     double *ws;        // general double workspace
@@ -17,6 +18,11 @@ struct rpc_ctx {
     int32_t *panel_ld_table;      // rpc_panel_ld(s) for s <= 256, for the kernels that read s on the device
     unsigned int *sync_counter;   // [0] Schur, [1] gather: CTA arrival counters of the peer-publishing kernels (self re-arming)
 };
+
+static inline int rpc_persistent_ctas(const rpc_ctx *ctx) {
+    int n = ctx->sm_count - ctx->sm_reserved;
+    return n < 1 ? 1 : n;
+}
 
 void rpc_set_error(const char *fmt, ...);
 int rpc_ws_reserve(rpc_ctx *ctx, size_t bytes);

@@ -1015,3 +1015,31 @@ extern "C" int rpc_pivoted_cholesky(rpc_ctx *ctx, void *stream, const double *H,
     RPC_LAUNCHED(ctx);
     return 0;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// dst[i, :] = src[rowmap[i], :] for i < *count: compaction of the speculatively evaluated kernel rows of the accepted
+// proposals into rows[c:c+s] (= A[S,:]).  The count is read on the device, so the copy can be enqueued before the host has
+// read the round back; it is HBM bound and runs beside the compute-bound Schur update.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_rows_kernel(const double *__restrict__ src, int64_t lds, const int32_t *__restrict__ rowmap,
+                                                          const int32_t *__restrict__ count, double *__restrict__ dst, int64_t ldd,
+                                                          int64_t n_pad) {
+    const int i = blockIdx.y;
+    if (i >= *count) return;
+    const double2 *s2 = reinterpret_cast<const double2 *>(src + (int64_t)rowmap[i] * lds);
+    double2 *d2 = reinterpret_cast<double2 *>(dst + (int64_t)i * ldd);
+    for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < n_pad / 2; q += (int64_t)gridDim.x * 256) d2[q] = s2[q];
+}
+
+extern "C" int rpc_gather_rows(rpc_ctx *ctx, void *stream, const double *src, int64_t lds, const int32_t *rowmap,
+                               const int32_t *count_dev, int max_rows, double *dst, int64_t ldd, int64_t n_pad) {
+    RPC_CHECK_ARG(ctx && src && rowmap && count_dev && dst, "null pointer");
+    RPC_CHECK_ARG(max_rows >= 1 && n_pad > 0 && n_pad % 2 == 0 && lds % 2 == 0 && ldd % 2 == 0, "bad sizes");
+    int gx = (int)((n_pad / 2 + 256 * 8 - 1) / (256 * 8));
+    if (gx < 1) gx = 1;
+    if (gx > 64) gx = 64;
+    gather_rows_kernel<<<dim3(gx, max_rows), 256, 0, (cudaStream_t)stream>>>(src, lds, rowmap, count_dev, dst, ldd, n_pad);
+    RPC_LAUNCHED(ctx);
+    return 0;
+}

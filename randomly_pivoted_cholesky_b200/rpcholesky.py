@@ -36,6 +36,11 @@ USE_FUSED = _os.environ.get("RPC_B200_FUSED", "0") == "1"
 # Row-sharded runs exchange the residual diagonal and the pivot payload through NVLink peer memory, stored by the
 # producing kernels themselves (dist.PeerWindow); RPC_B200_PEER=0 falls back to the two NCCL collectives per round
 USE_PEER = _os.environ.get("RPC_B200_PEER", "1") != "0"
+# Accelerated RPCholesky on a sharded operator evaluates the kernel rows of ALL b proposals on a second stream while the
+# single-CTA rejection Cholesky runs (147 of 148 SMs would idle otherwise); the Schur update then reads the accepted rows
+# through a row map.  Worth it once the evaluation is short compared with the serial chain, i.e. when sharded:
+# RPC_B200_SPEC = "auto" (sharded only) | "1" (always) | "0" (never)
+USE_SPEC = _os.environ.get("RPC_B200_SPEC", "auto")
 
 # bench.py sets this to a list to collect (start_event, end_event, flops, bytes, phase) per timed launch
 KERNEL_TIMERS = None
@@ -129,6 +134,7 @@ class _State:
         self.u_host = torch.empty((2 * m_max,), dtype=torch.float64).pin_memory()
         self.sel_host = torch.empty((m_max,), dtype=torch.int64).pin_memory()
         self.rb_host = None
+        self.spec = False
         A._dev_diag_into(self.diag)
         A._count(self.n)                                       # A.diag() counts N queries (matrix.py:33-39)
 
@@ -233,6 +239,51 @@ class _State:
                                               float(shift), _ptr(self.L), self.m_max, _ptr(self.acc), _ptr(self.info_dev)),
               "rpc_rejection_cholesky")
 
+    # ---- speculative evaluation of all proposals beside the rejection Cholesky (accelerated, sharded) ---------------------
+    def enable_speculation(self):
+        A = self.A
+        # break-even is where evaluating b rows takes about as long as the rejection kernel: N/world <~ 3e5 points at d = 50
+        if not (hasattr(A, "_spec") and self.ldx) or USE_SPEC == "0" or (USE_SPEC == "auto" and self.info.world < 4) or USE_FUSED:
+            return
+        self.spec = True
+        self.rows_all = torch.empty((self.m_max, self.n_pad), dtype=torch.float64, device=self.dev)
+        if getattr(self.ctx, "_side", None) is None:          # cached per device: a second rpc_ctx (own scratch: the side
+            self.ctx._side = (_lib.Context.extra(self.dev.index), torch.cuda.Stream(device=self.dev))   # stream must not
+        self.ctx2, self.side = self.ctx._side                 # share the main workspace) and the side stream
+        self.ev_fork, self.ev_eval = torch.cuda.Event(), torch.cuda.Event()
+        self.ev_rej, self.ev_copy = torch.cuda.Event(), None
+
+    def launch_eval_all(self, m):
+        """rows_all[:m] = A[idx, :] on the side stream, one SM left free for the rejection kernel."""
+        A = self.A
+        main = torch.cuda.current_stream()
+        self.ev_fork.record(main)
+        self.side.wait_event(self.ev_fork)
+        with torch.cuda.stream(self.side):
+            with _timed("eval", 2.0 * m * self.n_loc * A.d, 8.0 * self.n_loc * (m + A.d)):
+                check(self.lib.rpc_ctx_reserve_sms(self.ctx2.handle, 1), "rpc_ctx_reserve_sms")
+                check(self.lib.rpc_kernel_rows(self.ctx2.handle, _stream(), C.byref(A._spec), _ptr(A._Xd), _ptr(A._xnorm),
+                                               self.n_pad, A.d_pad, A.ldx, _ptr(self.piv.X), _ptr(self.piv.norm), m, A.ldx,
+                                               _ptr(self.rows_all), self.n_pad), "rpc_kernel_rows")
+            self.ev_eval.record(self.side)
+
+    def launch_row_gather(self, c, m):
+        """rows[c:c+s] = rows_all[acc[:s]] on the side stream (s read on the device), beside the panel solve / Schur update."""
+        main = torch.cuda.current_stream()
+        self.ev_rej.record(main)
+        self.side.wait_event(self.ev_rej)
+        with torch.cuda.stream(self.side):
+            check(self.lib.rpc_gather_rows(self.ctx2.handle, _stream(), _ptr(self.rows_all), self.n_pad, _ptr(self.acc),
+                                           _ptr(self.info_dev), m, C.c_void_p(self.rows.data_ptr() + 8 * c * self.n_pad),
+                                           self.n_pad, self.n_pad), "rpc_gather_rows")
+            self.ev_copy = torch.cuda.Event()
+            self.ev_copy.record(self.side)
+
+    def wait_row_gather(self):
+        if self.spec and self.ev_copy is not None:
+            torch.cuda.current_stream().wait_event(self.ev_copy)
+            self.ev_copy = None
+
     def prelaunch_panel(self, c, s_max):
         """Panel solve + compaction of the accepted pivots with the accepted count read on the device (info_dev[0]):
         enqueued behind the rejection kernel BEFORE the host reads the round back, so the host's wake-up and launch
@@ -245,7 +296,7 @@ class _State:
                                            _ptr(self.sel.X) if piv is not None else None,
                                            _ptr(self.sel.norm) if piv is not None else None), "rpc_build_panel_dev")
 
-    def update(self, c, s, acc_dev, idx_dev, panel_mode=0, Lmat=None, panel_done=False):
+    def update(self, c, s, acc_dev, idx_dev, panel_mode=0, Lmat=None, panel_done=False, spec_rows=False):
         """rows[c:c+s] = A[S,:]; G[c:c+s] = L^{-1}(rows - P^T G[:c]); diag update (rpcholesky.py:101-107,128-129 /
         205-209) on this rank's columns.  S = idx[acc] (acc None: all of idx); the selected pivot points are
         compacted out of the (already exchanged) payload, so no further communication is needed."""
@@ -272,6 +323,19 @@ class _State:
             sel_idx, sel_piv = idx_dev, self.piv
         rows_ptr = C.c_void_p(self.rows.data_ptr() + 8 * c * self.n_pad)
         n, d = self.n_loc, getattr(A, "d", 0)
+        if spec_rows:
+            # the rows of all proposals were evaluated on the side stream; the accepted ones are read through acc
+            torch.cuda.current_stream().wait_event(self.ev_eval)
+            A._count(s * self.n)
+            with _timed("schur", 2.0 * s * (c + s) * n, 8.0 * n * (c + 2 * s + 2)):
+                if self.peer is not None:
+                    self.peer.epoch_diag += 1
+                check(self.lib.rpc_schur_update_ex(self.ctx.handle, _stream(), _ptr(self.G), self.n_pad, c, s, _ptr(self.At),
+                                                   ldat, k_pad, _ptr(self.rows_all), self.n_pad, _ptr(self.acc), _ptr(self.diag),
+                                                   self.n_pad, C.byref(self.peer.peers) if self.peer is not None else None,
+                                                   self.peer.epoch_diag if self.peer is not None else 0), "rpc_schur_update_ex")
+                self.diag_pending = self.peer is not None
+            return
         spec = getattr(A, "_spec", None)
         if USE_FUSED and spec is not None and self.lib.rpc_fused_update_supported(C.byref(spec), s, A.ldx):
             # kernel rows evaluated and consumed in ONE pass over the column tile (fused update)
@@ -302,6 +366,7 @@ class _State:
     def result(self, count, arr_idx):
         # sharded: keep the whole padded shard (equal widths on all ranks, so `.G` can all-gather); else cut to N
         nl = self.n_pad if self.info.world > 1 else self.n_loc
+        self.wait_row_gather()
         if self.peer is not None:
             self.peer.check_status()
         return PSDLowRank(self.G[:count, :nl], n=self.n, idx=arr_idx, rows=self.rows[:count, :nl], shard_info=self.info)
@@ -516,6 +581,7 @@ def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
     b = int(b)
     b_cap = max(b, int(math.ceil(k / 3)), 10) if auto_b else b
     st = _State(A, k, b_cap)
+    st.enable_speculation()
     rng = np.random.default_rng()
     arr_idx = np.zeros(k, dtype=int)
     counter = 0
@@ -533,9 +599,16 @@ def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
         with _timed("gram", 2.0 * b * b * counter, 8.0 * counter * b):
             st.gather(st.idx_dev, b, counter)
             st.residual_block(st.idx_dev, b, counter)              # :189
+        if st.spec:
+            # side stream, forked behind the (many-CTA) Gram kernels: the 147-CTA evaluation then runs beside the
+            # single-CTA rejection kernel only
+            st.launch_eval_all(b)
+        st.wait_row_gather()                                       # the previous round's row compaction still reads acc
         with _timed("reject", b ** 3 / 3.0, 8.0 * b * b):
             st.cholesky(b, 0, k - counter, 0.0, b)                 # :190 + truncation :193-196
         st.publish(b)
+        if st.spec:
+            st.launch_row_gather(counter, b)
         with _timed("panel", 1.0 * b * b * counter, 8.0 * counter * b):
             st.prelaunch_panel(counter, b)                         # runs while the host wakes up
         stats_host, info, acc_host, idx_host = st.collect(b)                        # the round's only sync
@@ -555,7 +628,7 @@ def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
         arr_idx[counter:counter + num_sel] = idx
         t1 = time.perf_counter()
         if num_sel > 0:
-            st.update(counter, num_sel, st.acc, st.idx_dev, panel_done=True)
+            st.update(counter, num_sel, st.acc, st.idx_dev, panel_done=True, spec_rows=st.spec)
         counter += num_sel
         rounds.append(num_sel)
         if auto_b:                                             # :211-220, on device-synchronised wall time
