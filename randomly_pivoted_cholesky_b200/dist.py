@@ -99,6 +99,10 @@ def current_shard_info(n: int, group=None) -> ShardInfo:
 # ----------------------------------------------------------------------------------------------------------------
 # Peer-memory exchange (CUDA only): the two per-round exchanges done by the producing kernels themselves
 # ----------------------------------------------------------------------------------------------------------------
+class PeerUnavailable(RuntimeError):
+    """CUDA IPC / peer access is not available between the GPUs of this job."""
+
+
 class _DevMem:
     """Wraps a raw device allocation so that torch can view it (torch.as_tensor via __cuda_array_interface__)."""
 
@@ -118,12 +122,20 @@ class PeerWindow:
 
     @classmethod
     def get(cls, info: ShardInfo, ctx, device, payload_len: int):
+        """The cached window of this (group, shard, device), or None when peer mapping is unavailable on this box (decided
+        collectively, so every rank takes the same path; the drivers then use the NCCL collectives)."""
         key = (id(info.group), info.world, info.rank, info.shard, device.index)
-        w = cls._cache.get(key)
-        if w is not None and w.payload_len >= payload_len:
-            return w
-        # the payload is sized generously so that one window serves every factorisation of this operator
-        w = cls(info, ctx, device, payload_len)
+        if key in cls._cache:
+            w = cls._cache[key]
+            if w is None or w.payload_len >= payload_len:
+                return w
+        try:
+            # the payload is sized generously so that one window serves every factorisation of this operator
+            w = cls(info, ctx, device, max(payload_len, 1 << 20))
+        except PeerUnavailable as exc:
+            import warnings
+            warnings.warn("peer-memory exchange unavailable (%s): using the NCCL collectives" % exc)
+            w = None
         cls._cache[key] = w
         return w
 
@@ -135,10 +147,14 @@ class PeerWindow:
         self.n_total = info.n_total_pad
         ndbl = self.n_total + self.payload_len
         self.nbytes = 8 * ndbl + 8 * 2 * _lib.MAX_PEERS
+        # every step below is executed by every rank even after a local failure, and the outcome is agreed on with one
+        # MIN all-reduce: a rank must never leave the others waiting inside a collective
+        ok, why = 1, ""
         base = C.c_void_p()
         handle = (C.c_ubyte * 64)()
-        _lib.check(ctx.lib.rpc_peer_alloc(ctx.handle, self.nbytes, C.byref(base), handle), "rpc_peer_alloc")
-        self.base = int(base.value)
+        if ctx.lib.rpc_peer_alloc(ctx.handle, self.nbytes, C.byref(base), handle) != 0:
+            ok, why = 0, ctx.lib.rpc_last_error().decode()
+        self.base = int(base.value or 0)
         mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=device)
         allh = torch.empty((info.world, 64), dtype=torch.uint8, device=device)
         dist.all_gather_into_tensor(allh, mine, group=info.group)
@@ -151,9 +167,19 @@ class PeerWindow:
                 continue
             p = C.c_void_p()
             hb = (C.c_ubyte * 64).from_buffer_copy(bytes(allh[r].tobytes()))
-            _lib.check(ctx.lib.rpc_peer_open(ctx.handle, hb, C.byref(p)), "rpc_peer_open")
-            self.bases.append(int(p.value))
-            self._opened.append(int(p.value))
+            if ok and ctx.lib.rpc_peer_open(ctx.handle, hb, C.byref(p)) != 0:
+                ok, why = 0, ctx.lib.rpc_last_error().decode()
+            self.bases.append(int(p.value or 0))
+            if p.value:
+                self._opened.append(int(p.value))
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=info.group)
+        if int(flag.item()) == 0:
+            for q in self._opened:
+                ctx.lib.rpc_peer_close(ctx.handle, C.c_void_p(q))
+            if self.base:
+                ctx.lib.rpc_peer_free(ctx.handle, C.c_void_p(self.base))
+            raise PeerUnavailable(why or "another rank could not map the peer windows")
         peers = _lib.Peers()
         peers.world, peers.rank, peers.shard = info.world, info.rank, info.shard
         for r in range(info.world):

@@ -110,7 +110,8 @@ class _State:
         self.peer = None
         self.diag_pending = False              # True: the last Schur update published the new diagonal into diag_full
         if self.info.world > 1 and USE_PEER and not USE_FUSED and self.dev.type == "cuda" and self.ldx:
-            self.peer = rdist.PeerWindow.get(self.info, self.ctx, self.dev, payload_len)
+            self.peer = rdist.PeerWindow.get(self.info, self.ctx, self.dev, payload_len)     # None: no peer access here
+        if self.peer is not None:
             self.payload = self.peer.payload[:payload_len]
             self.diag_full = self.peer.diag_full
         else:
@@ -327,14 +328,7 @@ class _State:
             # the rows of all proposals were evaluated on the side stream; the accepted ones are read through acc
             torch.cuda.current_stream().wait_event(self.ev_eval)
             A._count(s * self.n)
-            with _timed("schur", 2.0 * s * (c + s) * n, 8.0 * n * (c + 2 * s + 2)):
-                if self.peer is not None:
-                    self.peer.epoch_diag += 1
-                check(self.lib.rpc_schur_update_ex(self.ctx.handle, _stream(), _ptr(self.G), self.n_pad, c, s, _ptr(self.At),
-                                                   ldat, k_pad, _ptr(self.rows_all), self.n_pad, _ptr(self.acc), _ptr(self.diag),
-                                                   self.n_pad, C.byref(self.peer.peers) if self.peer is not None else None,
-                                                   self.peer.epoch_diag if self.peer is not None else 0), "rpc_schur_update_ex")
-                self.diag_pending = self.peer is not None
+            self._schur(c, s, ldat, k_pad, _ptr(self.rows_all), _ptr(self.acc))
             return
         spec = getattr(A, "_spec", None)
         if USE_FUSED and spec is not None and self.lib.rpc_fused_update_supported(C.byref(spec), s, A.ldx):
@@ -349,19 +343,22 @@ class _State:
         with _timed("eval", 2.0 * s * n * d, 8.0 * n * (s + d)):
             A._dev_rows_into(sel_idx, s, sel_piv, rows_ptr, self.n_pad)
         A._count(s * self.n)
-        # algorithmic work of the Schur update: 2 s (c+s) N flops; reads G[:c] and rows_new, writes G_new
+        self._schur(c, s, ldat, k_pad, rows_ptr, None)
+
+    def _schur(self, c, s, ldat, k_pad, rows_src, rowmap):
+        """G[c:c+s] = At^T [G[:c]; rows_new], diag update; new row i is rows_src[rowmap[i]] (rowmap None: rows_src[i]).
+        Sharded with peer windows: the kernel also stores the new diagonal into every rank's copy and publishes the epoch.
+        Algorithmic work: 2 s (c+s) N flops; reads G[:c] and rows_new, writes G_new."""
+        n = self.n_loc
+        peers, epoch = None, 0
+        if self.peer is not None:
+            self.peer.epoch_diag += 1
+            peers, epoch = C.byref(self.peer.peers), self.peer.epoch_diag
         with _timed("schur", 2.0 * s * (c + s) * n, 8.0 * n * (c + 2 * s + 2)):
-            if self.peer is not None:
-                self.peer.epoch_diag += 1
-                check(self.lib.rpc_schur_update_peers(self.ctx.handle, _stream(), _ptr(self.G), self.n_pad, c, s, _ptr(self.At),
-                                                      ldat, k_pad, rows_ptr, self.n_pad, _ptr(self.diag), self.n_pad,
-                                                      C.byref(self.peer.peers), self.peer.epoch_diag),
-                      "rpc_schur_update_peers")
-                self.diag_pending = True
-            else:
-                check(self.lib.rpc_schur_update(self.ctx.handle, _stream(), _ptr(self.G), self.n_pad, c, s, _ptr(self.At),
-                                                ldat, k_pad, rows_ptr, self.n_pad, _ptr(self.diag), self.n_pad),
-                      "rpc_schur_update")
+            check(self.lib.rpc_schur_update_ex(self.ctx.handle, _stream(), _ptr(self.G), self.n_pad, c, s, _ptr(self.At), ldat,
+                                               k_pad, rows_src, self.n_pad, rowmap, _ptr(self.diag), self.n_pad, peers, epoch),
+                  "rpc_schur_update_ex")
+        self.diag_pending = self.peer is not None
 
     def result(self, count, arr_idx):
         # sharded: keep the whole padded shard (equal widths on all ranks, so `.G` can all-gather); else cut to N
