@@ -21,7 +21,6 @@
 
 constexpr int SC_CH = 256;            // elements per chunk (one warp, 8 per lane)
 constexpr int SC_WARPS = 8;           // chunks per CTA in the parallel passes
-constexpr int SC_NO_CAND = -100000;   // "no candidate binade" marker of an irregular chunk
 
 
 __device__ __forceinline__ double pow2d(int e) {   // 2^e for e in [-1022, 1023]
@@ -128,9 +127,7 @@ __device__ __forceinline__ void classify_body(const double *__restrict__ d, int6
     }
     if (lane == 0) {
         cls[k] = regular ? e : INT_MIN;
-        // irregular chunk: park the binade of the lower bound (the walk pre-classifies the chunk for it and the next one)
-        const double cand = (lo > 0.0 && isfinite(lo)) ? (double)ilogb(lo) : (double)SC_NO_CAND;
-        D[k] = regular ? A * pow2d(e - 52) : cand;   // exact: integer times a power of two
+        D[k] = regular ? A * pow2d(e - 52) : 0.0;    // exact: integer times a power of two
     }
 }
 
@@ -153,35 +150,10 @@ __global__ void __launch_bounds__(SC_WARPS * 32) sc_classify(const double *__res
 //   phase C (all warps): cstart = tile carry + within-tile prefix for the clean tiles.
 constexpr int SW_THREADS = 1024;
 
-constexpr int SW_SLOTS = 64;      // replay chunks staged in shared memory (64 x 2 KB); more fall back to global loads
-// dynamic shared memory of the walk: xs[SW_SLOTS][SC_CH] | Apre[SW_SLOTS][2][32] | tiemask[SW_SLOTS][2] | ecand[SW_SLOTS]
-constexpr size_t SW_SMEM_BYTES = (size_t)SW_SLOTS * SC_CH * 8 + (size_t)SW_SLOTS * 2 * 32 * 8 + (size_t)SW_SLOTS * 3 * 4;
-
-struct WalkPre {            // per staged chunk: the lanes' integer sums sum_t rne(x_t / q) for the binades ecand and ecand + 1
-    const double *A;        // [SW_SLOTS][2][32]
-    const unsigned *tie;    // [SW_SLOTS][2]  lanes that hold a rounding tie
-    const int *ecand;       // [SW_SLOTS]
-};
-
-// lane-local classification of 8 elements for the binade e: A = sum_t rne(x_t * 2^(52-e)), tie = some x_t sits on .5
-__device__ __forceinline__ void classify8(const double (&x)[8], int e, double &A, bool &tie) {
-    const double scale = pow2d(52 - e);
-    A = 0.0;
-    tie = false;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const double v = x[t] * scale;
-        const double kf = floor(v);
-        const double fr = v - kf;
-        tie |= (fr == 0.5);
-        A += kf + (fr > 0.5 ? 1.0 : 0.0);
-    }
-}
-
 template <bool DIV>
 __device__ __forceinline__ double walk_dirty_tile(const double *__restrict__ d, int64_t n, double S, int k0, int nch, int e,
                                                   double Dk, double carry, double *__restrict__ cstart, int lane,
-                                                  int &violated, const double *xs, const WalkPre pre_tab) {
+                                                  int &violated, const double *xs) {
     const unsigned full = 0xffffffffu;
     const int k = k0 + lane;
     int pos = 0;
@@ -210,18 +182,18 @@ __device__ __forceinline__ double walk_dirty_tile(const double *__restrict__ d, 
                 const int eb = carry > 0.0 ? fast_ilogb(carry) : INT_MIN;
                 int f = lpos;                                  // first lane that needs the sequential treatment
                 if (eb >= -960 && eb <= 1000) {
-                    const double q = pow2d(eb - 52), top = pow2d(eb + 1);
+                    const double scale = pow2d(52 - eb), q = pow2d(eb - 52), top = pow2d(eb + 1);
                     double A = 0.0;
                     bool tie = false;
-                    const int which = slot >= 0 ? eb - pre_tab.ecand[slot] : -1;
-                    if (which == 0 || which == 1) {
-                        // phase A classified the chunk for this binade already (same arithmetic, off the serial path)
-                        if (lane >= lpos) {
-                            A = pre_tab.A[(slot * 2 + which) * 32 + lane];
-                            tie = (pre_tab.tie[slot * 2 + which] >> lane) & 1u;
+                    if (lane >= lpos) {
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            double v = x[t] * scale;
+                            double kf = floor(v);
+                            double fr = v - kf;
+                            tie |= (fr == 0.5);
+                            A += kf + (fr > 0.5 ? 1.0 : 0.0);
                         }
-                    } else if (lane >= lpos) {
-                        classify8(x, eb, A, tie);
                     }
                     double pre = A;                            // inclusive prefix over lanes >= lpos (exact integers)
 #pragma unroll
@@ -269,6 +241,8 @@ __device__ __forceinline__ double walk_dirty_tile(const double *__restrict__ d, 
     return carry;
 }
 
+constexpr int SW_SLOTS = 64;      // replay chunks staged in shared memory (64 x 2 KB); more fall back to global loads
+
 template <bool DIV>
 __device__ __forceinline__ void walk_body(const double *__restrict__ d, int64_t n, const double *Sptr,
                                           double *__restrict__ D, const int32_t *__restrict__ cls, int nch,
@@ -281,10 +255,6 @@ __device__ __forceinline__ void walk_body(const double *__restrict__ d, int64_t 
     const int ntile = (nch + 31) / 32;
     constexpr int NW = SW_THREADS / 32;
     // xs: [SW_SLOTS][SC_CH], element (lane*8+t) at [t*32+lane]
-    double *Apre = xs + SW_SLOTS * SC_CH;
-    unsigned *tiemask = reinterpret_cast<unsigned *>(Apre + SW_SLOTS * 2 * 32);
-    int *ecand = reinterpret_cast<int *>(tiemask + SW_SLOTS * 2);
-    const WalkPre pre_tab{Apre, tiemask, ecand};
     __shared__ int nslots;
     if (threadIdx.x == 0) nslots = 0;
     __syncthreads();
@@ -303,32 +273,11 @@ __device__ __forceinline__ void walk_body(const double *__restrict__ d, int64_t 
             int slot = 0;
             if (lane == 0) slot = atomicAdd(&nslots, 1);
             slot = __shfl_sync(full, slot, 0);
-            const double cand = __shfl_sync(full, Dk, src);     // classify parked the candidate binade here
             if (slot < SW_SLOTS) {
                 const int64_t base = (int64_t)(t * 32 + src) * SC_CH + lane * 8;
-                double xv[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    xv[q] = (base + q) < n ? elem<DIV>(d, base + q, S) : 0.0;
-                    xs[slot * SC_CH + q * 32 + lane] = xv[q];
-                }
-                // pre-classify for the two binades the running sum can be in when the walk arrives here
-                const int ec = (cand >= -960.0 && cand <= 999.0) ? (int)cand : SC_NO_CAND;
-                if (ec != SC_NO_CAND) {
-#pragma unroll
-                    for (int w = 0; w < 2; ++w) {
-                        double A;
-                        bool tie;
-                        classify8(xv, ec + w, A, tie);
-                        Apre[(slot * 2 + w) * 32 + lane] = A;
-                        const unsigned tm = __ballot_sync(full, tie);
-                        if (lane == 0) tiemask[slot * 2 + w] = tm;
-                    }
-                }
-                if (lane == 0) ecand[slot] = ec;
+                for (int q = 0; q < 8; ++q) xs[slot * SC_CH + q * 32 + lane] = (base + q) < n ? elem<DIV>(d, base + q, S) : 0.0;
                 if (lane == src) D[k] = -(double)(slot + 1);
-            } else if (lane == src) {
-                D[k] = 0.0;                                      // not staged: the walk reloads it from global memory
             }
         }
         const int e0 = __shfl_sync(full, e, 0);
@@ -361,7 +310,7 @@ __device__ __forceinline__ void walk_body(const double *__restrict__ d, int64_t 
                     const int k0 = (t0 + q) * 32, k = k0 + lane;
                     const bool live = k < nch;
                     carry = walk_dirty_tile<DIV>(d, n, S, k0, nch, live ? cls[k] : INT_MIN + 1, live ? D[k] : 0.0, carry, cstart,
-                                                 lane, violated, xs, pre_tab);
+                                                 lane, violated, xs);
                     ++q;
                     continue;
                 }
@@ -524,15 +473,15 @@ extern "C" int rpc_sample_pivots(rpc_ctx *ctx, void *stream, const double *diag,
     int32_t *cls = ctx->flags, *bad = ctx->flags + nch, *tile_e = ctx->flags + nch + 8;
     static bool configured = false;
     if (!configured) {
-        RPC_CUDA(cudaFuncSetAttribute(sc_walk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM_BYTES));
-        RPC_CUDA(cudaFuncSetAttribute(sc_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM_BYTES));
-        RPC_CUDA(cudaFuncSetAttribute(sc_fused_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM_BYTES));
+        RPC_CUDA(cudaFuncSetAttribute(sc_walk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SLOTS * SC_CH * 8));
+        RPC_CUDA(cudaFuncSetAttribute(sc_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SLOTS * SC_CH * 8));
+        RPC_CUDA(cudaFuncSetAttribute(sc_fused_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SLOTS * SC_CH * 8));
         configured = true;
     }
     const double delta = ((double)n_pad + 256.0) * 1.1102230246251565e-16 * 1.01;
     if (n_pad <= SC_FUSED_MAX) {
         const double delta_b = (2.0 * (double)n_pad + 512.0) * 1.1102230246251565e-16 * 1.01;
-        sc_fused_small<<<1, SW_THREADS, SW_SMEM_BYTES, st>>>(diag, n_pad, u, m, idx, stats, csum, D, cA, cB,
+        sc_fused_small<<<1, SW_THREADS, SW_SLOTS * SC_CH * sizeof(double), st>>>(diag, n_pad, u, m, idx, stats, csum, D, cA, cB,
                                                                                  tile_tot, tile_carry, cls, bad, tile_e, nch,
                                                                                  delta, delta_b);
         RPC_LAUNCHED(ctx);
@@ -548,7 +497,7 @@ extern "C" int rpc_sample_pivots(rpc_ctx *ctx, void *stream, const double *diag,
     RPC_LAUNCHED(ctx);
     sc_classify<false><<<grid, SC_WARPS * 32, 0, st>>>(diag, n_pad, nullptr, csum, delta, D, cls);
     RPC_LAUNCHED(ctx);
-    sc_walk<false><<<1, SW_THREADS, SW_SMEM_BYTES, st>>>(diag, n_pad, nullptr, D, cls, nch, cA, tile_tot, tile_carry,
+    sc_walk<false><<<1, SW_THREADS, SW_SLOTS * SC_CH * sizeof(double), st>>>(diag, n_pad, nullptr, D, cls, nch, cA, tile_tot, tile_carry,
                                                                              tile_e, bad, nullptr);
     RPC_LAUNCHED(ctx);
 
@@ -556,7 +505,7 @@ extern "C" int rpc_sample_pivots(rpc_ctx *ctx, void *stream, const double *diag,
     const double delta_b = (2.0 * (double)n_pad + 512.0) * 1.1102230246251565e-16 * 1.01;
     sc_classify<true><<<grid, SC_WARPS * 32, 0, st>>>(diag, n_pad, Sptr, cA, delta_b, D, cls);
     RPC_LAUNCHED(ctx);
-    sc_walk<true><<<1, SW_THREADS, SW_SMEM_BYTES, st>>>(diag, n_pad, Sptr, D, cls, nch, cB, tile_tot, tile_carry,
+    sc_walk<true><<<1, SW_THREADS, SW_SLOTS * SC_CH * sizeof(double), st>>>(diag, n_pad, Sptr, D, cls, nch, cB, tile_tot, tile_carry,
                                                                             tile_e, bad, stats);
     RPC_LAUNCHED(ctx);
     if (m > 0) {
