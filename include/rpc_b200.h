@@ -50,6 +50,8 @@ typedef struct rpc_kernel_spec {
 } rpc_kernel_spec;
 
 int rpc_abi_version(void);
+/* sizeof of the structs that cross the ABI, for bindings to check their layout: 0 = rpc_kernel_spec, 1 = rpc_peers. */
+int rpc_abi_sizeof(int which);
 const char *rpc_last_error(void);
 
 int rpc_ctx_create(int device, rpc_ctx **out);

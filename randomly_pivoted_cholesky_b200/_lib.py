@@ -85,6 +85,7 @@ _DBL = C.c_double
 _SIGNATURES = {
     # name: (restype, argtypes)
     "rpc_abi_version": (_INT, []),
+    "rpc_abi_sizeof": (_INT, [_INT]),
     "rpc_last_error": (C.c_char_p, []),
     "rpc_ctx_create": (_INT, [_INT, C.POINTER(_P)]),
     "rpc_ctx_destroy": (_INT, [_P]),

@@ -14,6 +14,9 @@ void rpc_set_error(const char *fmt, ...) {
 
 extern "C" const char *rpc_last_error(void) { return g_err; }
 extern "C" int rpc_abi_version(void) { return RPC_ABI_VERSION; }
+extern "C" int rpc_abi_sizeof(int which) {
+    return which == 0 ? (int)sizeof(rpc_kernel_spec) : which == 1 ? (int)sizeof(rpc_peers) : -1;
+}
 
 extern "C" int rpc_ctx_create(int device, rpc_ctx **out) {
     RPC_CHECK_ARG(out != nullptr, "out is null");

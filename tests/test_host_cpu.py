@@ -29,6 +29,9 @@ def test_library_exports_every_declared_symbol():
     assert loaded.rpc_abi_version() == 1     # no device needed
     assert loaded.rpc_panel_ld(200) % 16 == 4 and loaded.rpc_panel_ld(200) >= 200
     assert loaded.rpc_last_error() is not None
+    # the ctypes mirrors of the structs that cross the ABI have the C layout
+    assert loaded.rpc_abi_sizeof(0) == ctypes.sizeof(_lib.KernelSpec)
+    assert loaded.rpc_abi_sizeof(1) == ctypes.sizeof(_lib.Peers)
 
 
 def test_no_cpu_fallback_without_gpu():
