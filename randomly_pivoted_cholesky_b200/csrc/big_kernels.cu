@@ -1,4 +1,5 @@
 // N-proportional kernels: kernel-row evaluation (K1/K2), fused Schur update (K5), fused simple step (K4).
+#include <stdlib.h>
 #include "dmma_gemm.cuh"
 
 using namespace dg;
@@ -119,6 +120,40 @@ static bool fused_fits(int m, int64_t ldx) {
     return need <= SMEM_LIMIT;
 }
 
+// ---- tail of the column-tile waves (see schur_update_impl) -------------------------------------------------------------
+struct TailFinish {
+    const double *sq;          // [nchunk][sq_ld] column sums of squares of the row chunks
+    int64_t sq_ld;
+    int nchunk, ncols;
+    double *diag;              // first tail column
+    int npeers;
+    double *peer_diag[RPC_MAX_PEERS];
+    unsigned long long *peer_flag[RPC_MAX_PEERS];
+    unsigned long long epoch;
+};
+
+__global__ void __launch_bounds__(1024) schur_tail_finish_kernel(TailFinish f) {
+    for (int col = threadIdx.x; col < f.ncols; col += blockDim.x) {
+        double tot = 0.0;
+        for (int q = 0; q < f.nchunk; ++q) tot += f.sq[q * f.sq_ld + col];       // fixed order: deterministic
+        double dv = f.diag[col] - tot;
+        dv = dv > 0.0 ? dv : 0.0;                                               // .clip(min=0)
+        f.diag[col] = dv;
+        for (int r = 0; r < f.npeers; ++r) f.peer_diag[r][col] = dv;
+    }
+    if (f.npeers > 0) {
+        // the main launch stored its columns into the peers' copies before it completed; this single CTA publishes
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            for (int r = 0; r < f.npeers; ++r)
+                asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(f.peer_flag[r]), "l"(f.epoch) : "memory");
+        }
+    }
+}
+
+static bool g_no_tail = getenv("RPC_B200_NO_TAIL") != nullptr;       // diagnostics: keep every column tile in the main launch
+
 static int schur_update_impl(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At, int64_t ldat,
                              int k_pad, const double *rows_new, int64_t ldr, const int32_t *rowmap, double *diag, int64_t n_pad,
                              const rpc_peers *peers, unsigned long long epoch) {
@@ -135,6 +170,57 @@ static int schur_update_impl(rpc_ctx *ctx, void *stream, double *G, int64_t ldg,
         if (rc) return rc;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    // Tail of the column-tile waves.  The persistent grid walks n_pad/64 column tiles; when they do not fill the last wave
+    // (8-GPU shard of T*: 1954 tiles on 148 SMs = 13.2 waves) the leftover tiles are taken out of the main launch and done
+    // by a second launch of 32-row x 128-column CTAs over (row chunk, column tile) pairs, which spreads them over all SMs
+    // (about half a tile-time instead of a full one).  The chunks leave their column sums of squares in the workspace and
+    // schur_tail_finish_kernel applies them to the diagonal in a fixed order (deterministic).
+    if (s > 128 && s <= 256 && !g_no_tail) {
+        const int ctas = rpc_persistent_ctas(ctx);
+        const int ntiles = (int)(n_pad / 64);
+        const int left = ntiles % ctas;
+        const int nchunk = (s + 31) / 32;
+        const int ncol = left / 2;                                  // n_pad is a multiple of 128, so `left` is even
+        if (left > 0 && left % 2 == 0 && ntiles / ctas >= 4 && ncol * nchunk <= ctas && ldat >= 32 && tile_rows_for(s, true) <= ldat) {
+            const int64_t tail_cols = (int64_t)left * 64, col_lo = n_pad - tail_cols;
+            int rc = rpc_ws_reserve(ctx, (size_t)nchunk * tail_cols * sizeof(double));
+            if (rc) return rc;
+            Params p{};
+            p.At = At; p.ldat = ldat; p.k_pad = k_pad; p.m_valid = s;
+            p.G = G; p.ldg = ldg; p.c = c; p.R = rows_new; p.ldr = ldr; p.K = c + s; p.rowmap = rowmap;
+            p.Cout = G + (int64_t)c * ldg; p.ldc = ldg; p.diag = diag;
+            if (peers) {
+                p.npeers = peers->world;
+                for (int r = 0; r < peers->world; ++r) {
+                    RPC_CHECK_ARG(peers->diag_full[r] && peers->flags[r], "peer table has null entries");
+                    p.peer_diag[r] = peers->diag_full[r] + (int64_t)peers->rank * peers->shard;
+                }
+                p.publish = 0;                                      // the finishing kernel publishes
+            }
+            // main launch: the full waves
+            rc = dispatch_gemm<MODE_SCHUR>(ctx, st, p, s, col_lo);
+            if (rc) return rc;
+            // tail launch
+            Params t = p;
+            t.npeers = 0;
+            t.tile_col0 = col_lo; t.chunk_rows = 32; t.ncol_tiles = ncol;
+            t.chunk_last_start = (int)((ldat - 32) & ~(int64_t)1);
+            t.sq_out = ctx->ws; t.sq_ld = tail_cols;
+            rc = launch_gemm<C32, MODE_SCHUR>(ctx, st, t, (int64_t)ncol * nchunk * C32::N_TILE);
+            if (rc) return rc;
+            TailFinish f{};
+            f.sq = ctx->ws; f.sq_ld = tail_cols; f.nchunk = nchunk; f.diag = diag + col_lo; f.ncols = (int)tail_cols;
+            f.npeers = p.npeers;
+            for (int r = 0; r < p.npeers; ++r) {
+                f.peer_diag[r] = p.peer_diag[r] + col_lo;
+                f.peer_flag[r] = peers->flags[r] + peers->rank;
+            }
+            f.epoch = epoch;
+            schur_tail_finish_kernel<<<1, 1024, 0, st>>>(f);
+            RPC_LAUNCHED(ctx);
+            return 0;
+        }
+    }
     for (int m0 = 0; m0 < s; m0 += 256) {
         int m = s - m0 < 256 ? s - m0 : 256;
         RPC_CHECK_ARG(ldat >= m0 + tile_rows_for(m, true), "ldat too small for the zero-padded row tile");
@@ -151,6 +237,7 @@ static int schur_update_impl(rpc_ctx *ctx, void *stream, double *G, int64_t ldg,
                 p.peer_flag[r] = peers->flags[r] + peers->rank;
             }
             p.epoch = epoch;
+            p.publish = 1;
             p.done_counter = ctx->sync_counter;
         }
         int rc = dispatch_gemm<MODE_SCHUR>(ctx, st, p, m, n_pad);

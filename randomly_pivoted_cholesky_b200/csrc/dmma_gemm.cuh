@@ -88,6 +88,16 @@ struct Params {
     // MODE_SCHUR, row-sharded runs: the updated residual diagonal of this rank's columns is ALSO stored straight into
     // every rank's copy of the full diagonal (peer memory over NVLink; entry r already points at this rank's block),
     // and the last CTA to finish publishes `epoch` in each rank's flag word for this source (csrc/peers.cu)
+    // MODE_SCHUR, tail launch (chunk_rows > 0): the "tile" index runs over (row chunk, column tile) pairs of the last partial
+    // wave of column tiles, so that wave is spread over all SMs.  Chunk q covers panel rows [rstart, rstart + M_TILE) with
+    // rstart = min(q * chunk_rows, chunk_last_start); rows below q * chunk_rows are duplicates of the previous chunk and are
+    // neither stored nor summed.  The column sums of squares go to sq_out[q * sq_ld + column] (the diagonal is updated by a
+    // finishing kernel once all chunks are in), tile_col0 is the first column of the tail.
+    int64_t tile_col0;
+    int chunk_rows, chunk_last_start, ncol_tiles;
+    double *sq_out;
+    int64_t sq_ld;
+    int publish;           // with npeers > 0: the last CTA publishes the epoch (0: a later kernel does)
     int npeers;
     double *peer_diag[RPC_MAX_PEERS];
     unsigned long long *peer_flag[RPC_MAX_PEERS];
@@ -166,11 +176,11 @@ __device__ __forceinline__ unsigned stage_bytes(const Params &p, int k0) {
 
 // the producer warp: the panel stage in one copy, lane r issues row r of the B tile
 template <class C, int MODE>
-__device__ __forceinline__ void produce_stage(const Params &p, double *As, double *Bs, uint64_t *full, int k0, int64_t col0,
-                                              int lane) {
+__device__ __forceinline__ void produce_stage(const Params &p, const double *At, double *As, double *Bs, uint64_t *full, int k0,
+                                              int64_t col0, int lane) {
     if (lane == 0) mbar_expect_tx(full, stage_bytes<C, MODE>(p, k0));
     __syncwarp();
-    produce_panel<C>(As, p.At, p.ldat, k0, full, lane);
+    produce_panel<C>(As, At, p.ldat, k0, full, lane);
     if (MODE == MODE_SCHUR) {
         if (lane >= 32 - KT) {
             const int r = lane - (32 - KT);
@@ -333,7 +343,14 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
         int it = 0;
         unsigned tpar = 0;                                   // parity of this CTA's tile counter
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, tpar ^= 1) {
-            const int64_t col0 = (int64_t)tile * C::N_TILE;
+            int ct = tile, rstart = 0;
+            if (MODE == MODE_SCHUR && p.chunk_rows) {        // tail launch: (row chunk, column tile)
+                const int chunk = tile / p.ncol_tiles;
+                ct = tile - chunk * p.ncol_tiles;
+                rstart = min(chunk * p.chunk_rows, p.chunk_last_start);
+            }
+            const int64_t col0 = p.tile_col0 + (int64_t)ct * C::N_TILE;
+            const double *At_tile = p.At + rstart;
             if (XRES) {
                 mbar_wait(xempty, tpar ^ 1);                 // consumers are done with the previous X tile
                 if (lane == 0) {
@@ -357,7 +374,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
                     rows_waited = true;
                 }
                 mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);   // first lap: returns immediately
-                produce_stage<C, MODE == MODE_FUSED ? MODE_SCHUR : MODE>(p, As_base + s * C::A_STAGE,
+                produce_stage<C, MODE == MODE_FUSED ? MODE_SCHUR : MODE>(p, At_tile, As_base + s * C::A_STAGE,
                                                                           Bs_base + s * C::B_STAGE, &full[s], kt * KT, col0, lane);
             }
         }
@@ -387,7 +404,15 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
     int it = 0;
     unsigned tpar = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, tpar ^= 1) {
-        const int64_t col0 = (int64_t)tile * C::N_TILE;
+        int ct = tile, chunk = 0, rstart = 0, first_new = 0;
+        if (MODE == MODE_SCHUR && p.chunk_rows) {            // tail launch: (row chunk, column tile)
+            chunk = tile / p.ncol_tiles;
+            ct = tile - chunk * p.ncol_tiles;
+            rstart = min(chunk * p.chunk_rows, p.chunk_last_start);
+            first_new = chunk * p.chunk_rows - rstart;
+        }
+        const int64_t col0 = p.tile_col0 + (int64_t)ct * C::N_TILE;
+        const int m_valid = p.m_valid - rstart;              // rows of this tile that exist
         double acc[C::MI][C::NI][2];
 #pragma unroll
         for (int i = 0; i < C::MI; ++i)
@@ -437,17 +462,21 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
 #pragma unroll
             for (int i = 0; i < C::MI; ++i) {
                 const int row = m0 + i * 8 + lr;
-                if (i < mi_cnt && row < p.m_valid) {         // fragments >= mi_cnt belong to the next warp row
-                    double *dst = p.Cout + (int64_t)row * p.ldc + col0 + n0 + 2 * lk;
+                const bool live = i < mi_cnt && row < m_valid && row >= first_new;   // fragments >= mi_cnt: next warp row
+                if (live) {
+                    double *dst = p.Cout + (int64_t)(rstart + row) * p.ldc + col0 + n0 + 2 * lk;
 #pragma unroll
                     for (int j = 0; j < C::NI; ++j)
                         *reinterpret_cast<double2 *>(dst + j * 8) = make_double2(acc[i][j][0], acc[i][j][1]);
                 }
-                // rows >= m_valid are exactly zero (At zero padded), so they add nothing below
+                // rows >= m_valid are exactly zero (At zero padded), so they add nothing below; a tail chunk also holds
+                // duplicate rows (< first_new) and, past the panel's last column, rows fed by the next panel row
+                if (!(MODE == MODE_SCHUR && p.chunk_rows) || live) {
 #pragma unroll
-                for (int j = 0; j < C::NI; ++j) {
-                    csum[j][0] = fma(acc[i][j][0], acc[i][j][0], csum[j][0]);
-                    csum[j][1] = fma(acc[i][j][1], acc[i][j][1], csum[j][1]);
+                    for (int j = 0; j < C::NI; ++j) {
+                        csum[j][0] = fma(acc[i][j][0], acc[i][j][0], csum[j][0]);
+                        csum[j][1] = fma(acc[i][j][1], acc[i][j][1], csum[j][1]);
+                    }
                 }
             }
             // reduce over the 8 row groups of the warp (lanes with equal lk)
@@ -474,6 +503,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
                 double sres = 0.0;
 #pragma unroll
                 for (int w = 0; w < C::WM; ++w) sres += red[w * C::N_TILE + n];
+                if (MODE == MODE_SCHUR && p.sq_out) {      // tail chunk: the finishing kernel updates the diagonal
+                    p.sq_out[chunk * p.sq_ld + (col0 - p.tile_col0) + n] = sres;
+                    continue;
+                }
                 double dv = p.diag[col0 + n] - sres;
                 dv = dv > 0.0 ? dv : 0.0;                  // .clip(min=0)
                 p.diag[col0 + n] = dv;
@@ -484,7 +517,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
             eval_epilogue<C>(p, acc, p.Cout, p.ldc, col0, m0, n0, lr, lk, mi_cnt);
         }
     }
-    if (MODE == MODE_SCHUR && p.npeers > 0) {
+    if (MODE == MODE_SCHUR && p.npeers > 0 && p.publish) {
         // release pattern: this CTA's peer stores -> system fence -> CTA counter; the last CTA publishes the epoch
         consumer_bar_sync(C::CONSUMERS * 32);
         if (tid == 0) {

@@ -286,6 +286,55 @@ def test_schur_update_matches_numpy(rpc, c, s):
     assert np.array_equal(G[:c].cpu().numpy(), Gh[:c])
 
 
+@pytest.mark.parametrize("c,s,left", [(40, 167, 30), (0, 136, 2), (96, 200, 40), (16, 256, 36), (30, 129, 58)])
+def test_schur_update_tail_of_the_tile_waves(rpc, c, s, left):
+    """Shapes whose column tiles do not fill the last wave of the persistent grid: the leftover tiles go through the
+    row-chunked tail launch + finishing kernel; results must equal the plain path's."""
+    from randomly_pivoted_cholesky_b200 import ops
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    rng = np.random.default_rng(c * 1000 + s)
+    n_pad = (4 * sms + left) * 64
+    assert n_pad % 128 == 0
+    k = c + s
+    Gh = np.zeros((k, n_pad))
+    Gh[:c] = rng.standard_normal((c, n_pad))
+    rows = rng.standard_normal((s, n_pad))
+    P = rng.standard_normal((c, s))
+    Lh = np.tril(rng.standard_normal((s, s))) + 4 * np.sqrt(s) * np.eye(s)
+    diag = rng.random(n_pad) * 50
+    want = np.linalg.solve(Lh, rows - P.T @ Gh[:c])
+    wdiag = np.clip(diag - np.sum(want ** 2, axis=0), 0, None)
+    dev = torch.device("cuda")
+    G = torch.from_numpy(Gh).to(dev)
+    dg = torch.from_numpy(diag).to(dev)
+    ops.schur_update(G, c, torch.from_numpy(rows).to(dev), torch.from_numpy(P).to(dev), torch.from_numpy(Lh).to(dev), dg)
+    got = G[c:].cpu().numpy()
+    assert relerr(got, want) <= 1e-12
+    # every tail column separately (a chunk that dropped or double-counted rows would show up here)
+    np.testing.assert_allclose(dg.cpu().numpy(), wdiag, rtol=1e-11, atol=1e-10)
+    assert np.array_equal(G[:c].cpu().numpy(), Gh[:c])
+
+
+def test_speculative_rows_and_tail_launch_against_oracle(rpc, monkeypatch):
+    """The >= 4-GPU code path forced on one GPU: all proposals evaluated on the side stream, accepted rows read through the
+    row map, on a shape whose Schur update also takes the row-chunked tail launch."""
+    import importlib
+    drivers = importlib.import_module("randomly_pivoted_cholesky_b200.rpcholesky")     # the module, not the function
+    monkeypatch.setattr(drivers, "USE_SPEC", "1")
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    n, d, k, b = (4 * sms + 30) * 64 - 5, 9, 500, 200
+    X = np.random.default_rng(17).standard_normal((n, d))
+    bw = float(np.sqrt(d))
+    A = rpc.KernelMatrix(X, kernel="gaussian", bandwidth=bw)
+    with replay(23):
+        lra = rpc.accelerated_rpcholesky(A, k, b=b)
+    rng, legacy = orc.make_streams(23)
+    ref = orc.accelerated_rpcholesky(orc.OracleKernelMatrix(X, kernel="gaussian", bandwidth=bw), k, b, rng, legacy)
+    assert np.array_equal(np.asarray(lra.idx), ref.idx)
+    assert relerr(lra.G, ref.G) <= F_TOL and relerr(lra.rows, ref.rows) <= F_TOL
+    assert A.num_queries() == n + k * n + b * b * len(ref.rounds)
+
+
 def test_configs_c1_c2_against_oracle(rpc):
     """BASELINE.json configs[0] in full and configs[1] at reduced N: GPU vs oracle on replayed draws."""
     # C1: simple_rpcholesky, Gaussian, N=10,000 d=10 k=100

@@ -21,7 +21,11 @@ for (alg, kernel, n, d, k, b, bw, kw) in [("accel", "gaussian", 20000, 20, 600, 
                                            ("accel", "matern", 30011, 3, 500, 64, np.sqrt(3), {"nu": 2.5}),
                                            ("rbrp", "gaussian", 12000, 8, 300, 60, np.sqrt(8), {}),
                                            ("bgreedy", "laplace", 9000, 6, 200, 50, 6.0, {}),
-                                           ("accel", "gaussian", 20000, 20, 600, 120, np.sqrt(20), {})]:
+                                           ("accel", "gaussian", 20000, 20, 600, 120, np.sqrt(20), {}),
+                                           # shard of (4*148+30) column tiles and s > 128: the Schur update goes through the
+                                           # row-chunked tail launch, whose finishing kernel publishes the diagonal epoch
+                                           ("accel", "gaussian", world * (4 * 148 + 30) * 64, 12, 520, 200, np.sqrt(12), {}),
+                                           ("block", "gaussian", world * (4 * 148 + 30) * 64, 12, 400, 180, np.sqrt(12), {})]:
     X = np.random.default_rng(3).standard_normal((n, d))
     A = rpc.KernelMatrix(X, kernel=kernel, bandwidth=float(bw), sharded=True, **kw)
     with replay(77):
