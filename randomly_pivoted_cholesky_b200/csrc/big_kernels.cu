@@ -152,6 +152,21 @@ __global__ void __launch_bounds__(1024) schur_tail_finish_kernel(TailFinish f) {
     }
 }
 
+// one panel per row chunk with the leading dimension of the tail tile, so that a 16-row stage of it is ONE bulk copy (with
+// the main panel's stride the producer warp needs 16 row copies per stage and the TMA issue rate bounds the tail CTAs)
+__global__ void __launch_bounds__(256) tail_panel_repack_kernel(const double *__restrict__ At, int64_t ldat, int k_pad, int nchunk,
+                                                                int chunk_rows, int chunk_last_start, int ld_out,
+                                                                double *__restrict__ out) {
+    const int64_t total = (int64_t)nchunk * k_pad * ld_out;
+    for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < total; q += (int64_t)gridDim.x * 256) {
+        const int j = (int)(q % ld_out);
+        const int64_t t = q / ld_out;
+        const int r = (int)(t % k_pad), chunk = (int)(t / k_pad);
+        const int rstart = min(chunk * chunk_rows, chunk_last_start);
+        out[q] = (j < chunk_rows && rstart + j < ldat) ? At[(int64_t)r * ldat + rstart + j] : 0.0;
+    }
+}
+
 static bool g_no_tail = getenv("RPC_B200_NO_TAIL") != nullptr;       // diagnostics: keep every column tile in the main launch
 
 static int schur_update_impl(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At, int64_t ldat,
@@ -183,8 +198,11 @@ static int schur_update_impl(rpc_ctx *ctx, void *stream, double *G, int64_t ldg,
         const int ncol = left / 2;                                  // n_pad is a multiple of 128, so `left` is even
         if (left > 0 && left % 2 == 0 && ntiles / ctas >= 4 && ncol * nchunk <= ctas && ldat >= 32 && tile_rows_for(s, true) <= ldat) {
             const int64_t tail_cols = (int64_t)left * 64, col_lo = n_pad - tail_cols;
-            int rc = rpc_ws_reserve(ctx, (size_t)nchunk * tail_cols * sizeof(double));
+            const size_t sq_doubles = ((size_t)nchunk * tail_cols + 15) & ~(size_t)15;      // keeps the panels 128-byte aligned
+            const size_t panel_doubles = (size_t)nchunk * k_pad * C32::LDA;
+            int rc = rpc_ws_reserve(ctx, (sq_doubles + panel_doubles) * sizeof(double));
             if (rc) return rc;
+            double *tail_panels = ctx->ws + sq_doubles;
             Params p{};
             p.At = At; p.ldat = ldat; p.k_pad = k_pad; p.m_valid = s;
             p.G = G; p.ldg = ldg; p.c = c; p.R = rows_new; p.ldr = ldr; p.K = c + s; p.rowmap = rowmap;
@@ -206,6 +224,14 @@ static int schur_update_impl(rpc_ctx *ctx, void *stream, double *G, int64_t ldg,
             t.tile_col0 = col_lo; t.chunk_rows = 32; t.ncol_tiles = ncol;
             t.chunk_last_start = (int)((ldat - 32) & ~(int64_t)1);
             t.sq_out = ctx->ws; t.sq_ld = tail_cols;
+            {
+                const int64_t total = (int64_t)panel_doubles;
+                int grid = (int)((total + 256 * 4 - 1) / (256 * 4));
+                if (grid > ctx->sm_count * 4) grid = ctx->sm_count * 4;
+                tail_panel_repack_kernel<<<grid, 256, 0, st>>>(At, ldat, k_pad, nchunk, 32, t.chunk_last_start, C32::LDA, tail_panels);
+                RPC_LAUNCHED(ctx);
+            }
+            t.At = tail_panels; t.ldat = C32::LDA; t.chunk_panel_stride = (int64_t)k_pad * C32::LDA;
             rc = launch_gemm<C32, MODE_SCHUR>(ctx, st, t, (int64_t)ncol * nchunk * C32::N_TILE);
             if (rc) return rc;
             TailFinish f{};

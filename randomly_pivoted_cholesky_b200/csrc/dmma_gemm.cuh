@@ -95,6 +95,7 @@ struct Params {
     // finishing kernel once all chunks are in), tile_col0 is the first column of the tail.
     int64_t tile_col0;
     int chunk_rows, chunk_last_start, ncol_tiles;
+    int64_t chunk_panel_stride;   // > 0: At holds one re-packed panel per chunk (ld = LDA of the tail tile: one bulk copy per stage)
     double *sq_out;
     int64_t sq_ld;
     int publish;           // with npeers > 0: the last CTA publishes the epoch (0: a later kernel does)
@@ -351,6 +352,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
             }
             const int64_t col0 = p.tile_col0 + (int64_t)ct * C::N_TILE;
             const double *At_tile = p.At + rstart;
+            if (MODE == MODE_SCHUR && p.chunk_rows && p.chunk_panel_stride) At_tile = p.At + (int64_t)(tile / p.ncol_tiles) * p.chunk_panel_stride;
             if (XRES) {
                 mbar_wait(xempty, tpar ^ 1);                 // consumers are done with the previous X tile
                 if (lane == 0) {
