@@ -45,6 +45,17 @@ def test_no_cpu_fallback_without_gpu():
         rpc.rpcholesky(np.eye(4), 2)
 
 
+def test_driver_argument_errors_match_the_reference():
+    """Errors raised before any device work (rpcholesky.py:37, 97, 126 of the reference): same types, same messages."""
+    import randomly_pivoted_cholesky_b200 as rpc
+    with pytest.raises(RuntimeError, match="Algorithm 'nope' not recognized"):
+        rpc.block_cholesky_helper(np.eye(4), 2, 2, "nope")
+    with pytest.raises(ValueError, match="'nope' is not a valid strategy for block RPCholesky"):
+        rpc.block_cholesky_helper(np.eye(4), 2, 2, "rp", strategy="nope")
+    with pytest.raises(RuntimeError, match="Algorithm 'nope' not recognized"):
+        rpc.cholesky_helper(np.eye(4), 2, "nope")
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "randomly_pivoted_cholesky_b200")
     for dirpath, _, files in os.walk(pkg):
