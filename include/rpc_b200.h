@@ -33,6 +33,9 @@ extern "C" {
 #define RPC_COL_ALIGN 128   /* n_pad granularity (widest column tile of the DMMA kernels) */
 #define RPC_FEAT_ALIGN 4    /* d_pad granularity (one DMMA k-step) */
 #define RPC_KT 16           /* k-depth of one shared-memory stage; panel K is padded to this */
+#define RPC_MAX_BLOCK 1536  /* largest proposal block b / accepted block s of one round (shared memory of the single-CTA
+                               rejection Cholesky and of the panel solve); the reference accepts any b, the drivers raise
+                               ValueError above this and cap the auto-tuned b at it */
 
 /* kernel functions, reference kernels.py */
 #define RPC_KERN_GAUSSIAN 0 /* kernels.py:32-39 */
@@ -153,7 +156,8 @@ int rpc_select_largest(rpc_ctx *ctx, void *stream, const double *diag, int64_t n
  *    At[c + i, j] = Minv[j, i]                          i < s
  *    zero elsewhere (rows up to k_pad, columns up to m_pad).
  * so that G_new = At^T [G[:c]; rows_new] = L^{-1} (rows_new - P_acc^T G[:c])
- * (rpcholesky.py:102+107, 206+207; np.linalg.solve replaced by the explicit small inverse).
+ * (rpcholesky.py:102+107, 206+207; np.linalg.solve(L, .) is folded into the panel by one forward substitution
+ * per panel row -- no explicit inverse is formed; mode 1 takes a dense Minv for the eigh fallback).
  * acc may be NULL (= identity selection). */
 int rpc_build_panel(rpc_ctx *ctx, void *stream, const double *P, int64_t ldP, int c, const int32_t *acc, int s,
                     const double *L, int64_t ldl, int mode, double *At, int64_t ldat, int k_pad);

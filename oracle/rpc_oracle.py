@@ -50,7 +50,17 @@ def euclidean_distances(X, Y):
 
 
 def manhattan_distances(X, Y):
-    """scipy cdist(..., 'cityblock') as reached from kernels.py:20: sequential sum over features."""
+    """sklearn manhattan_distances as reached from kernels.py:20 = scipy cdist(X, Y, 'cityblock') (the call the
+    reference itself makes); without scipy, the restated loop below (bit-equal: tests/test_oracle.py)."""
+    try:
+        from scipy.spatial.distance import cdist
+    except ImportError:
+        return manhattan_distances_loop(X, Y)
+    return cdist(np.asarray(X, dtype=np.float64), np.asarray(Y, dtype=np.float64), "cityblock")
+
+
+def manhattan_distances_loop(X, Y):
+    """cdist(..., 'cityblock') restated: sum_f |x_f - y_f| accumulated strictly in feature order."""
     X = np.asarray(X, dtype=np.float64)
     Y = np.asarray(Y, dtype=np.float64)
     D = np.zeros((X.shape[0], Y.shape[0]))
@@ -308,6 +318,7 @@ def block_rpcholesky(A, k, b, rng, stoptol=1e-14, strategy="regularize", rbrp_at
     rows = np.zeros((k, n))
     arr_idx = []
     counter = 0
+    conds = []          # diagnostics only, see g_tolerance
     while counter < k:
         block_size = min(k - counter, b)
         if alg == "rp":
@@ -328,6 +339,7 @@ def block_rpcholesky(A, k, b, rng, stoptol=1e-14, strategy="regularize", rbrp_at
             C = G[counter:counter + block_size, idx]                           # :103
             try:
                 L = np.linalg.cholesky(C + EPS * b * scale * np.identity(block_size))  # :106
+                conds.append(float(np.linalg.cond(L)))
                 G[counter:counter + block_size, :] = np.linalg.solve(L, G[counter:counter + block_size, :])  # :107
             except np.linalg.LinAlgError:                                      # :109-114
                 warnings.warn("Cholesky failed in block partial Cholesky. Falling back to eigendecomposition")
@@ -339,6 +351,7 @@ def block_rpcholesky(A, k, b, rng, stoptol=1e-14, strategy="regularize", rbrp_at
             H = A.block(idx) - G[0:counter, idx].T @ G[0:counter, idx]
             L, piv, rank = _greedy_cholesky(H, rtol=rbrp_rtol, atol=rbrp_atol)
             idx = idx[piv[0:rank] - 1]
+            conds.append(float(np.linalg.cond(L[0:rank, 0:rank])))
             arr_idx.extend(idx)
             rows[counter:counter + len(idx), :] = A.rows(idx)
             G[counter:counter + len(idx), :] = rows[counter:counter + len(idx), :] - G[0:counter, idx].T @ G[0:counter, :]
@@ -352,7 +365,9 @@ def block_rpcholesky(A, k, b, rng, stoptol=1e-14, strategy="regularize", rbrp_at
             G = G[:counter, :]
             rows = rows[:counter, :]
             break
-    return OracleResult(G, arr_idx, rows)
+    res = OracleResult(G, arr_idx, rows)
+    res.cond_L = conds
+    return res
 
 
 def rejection_cholesky(H, u):
@@ -391,6 +406,7 @@ def accelerated_rpcholesky(A, k, b, rng, legacy, stoptol=1e-13):
     arr_idx = np.zeros(k, dtype=int)
     counter = 0
     rounds = []
+    conds = []          # diagnostics only: 2-norm condition number of each round's triangular factor (see g_tolerance)
     while counter < k:
         idx = sample_pivots(diags, rng.random(b))                              # :184
         H = A.block(idx) - G[0:counter, idx].T @ G[0:counter, idx]             # :189
@@ -401,6 +417,7 @@ def accelerated_rpcholesky(A, k, b, rng, legacy, stoptol=1e-13):
             accepted = accepted[:num_sel]
             L = L[:num_sel, :num_sel]
         idx = idx[accepted]
+        conds.append(float(np.linalg.cond(L)) if num_sel > 0 else 1.0)
         arr_idx[counter:counter + num_sel] = idx
         rows[counter:counter + num_sel, :] = A.rows(idx)                       # :205
         G[counter:counter + num_sel, :] = (
@@ -416,7 +433,18 @@ def accelerated_rpcholesky(A, k, b, rng, legacy, stoptol=1e-13):
             break
     res = OracleResult(G, arr_idx, rows)
     res.rounds = rounds
+    res.cond_L = conds
     return res
+
+
+def g_tolerance(res, floor=1e-10):
+    """Bar for ||G - G_ref||_F / ||G_ref||_F.  north_star's 1e-10 wherever the rounds' triangular factors are well
+    conditioned; a block whose factor L has cond_2(L) = kappa turns the round-off of ANY backward-stable solve
+    (the reference's LU `np.linalg.solve(L, .)`, rpcholesky.py:107,207, as much as the device's forward substitution)
+    into a relative forward error of order kappa * eps in G_new, so two correct implementations may differ by that much:
+    the bar is max(1e-10, 8 * eps * max_round kappa).  rows = A[S,:] involve no solve and keep the flat 1e-10."""
+    kappa = max(getattr(res, "cond_L", None) or [1.0])
+    return max(floor, 8.0 * EPS * kappa)
 
 
 def relative_trace_error(A, res):

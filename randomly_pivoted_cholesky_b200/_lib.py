@@ -27,6 +27,7 @@ NVCC_FLAGS = [
 COL_ALIGN = 128
 FEAT_ALIGN = 4
 KT = 16
+MAX_BLOCK = 1536          # RPC_MAX_BLOCK of include/rpc_b200.h
 KERN_GAUSSIAN, KERN_LAPLACE, KERN_MATERN = 0, 1, 2
 
 

@@ -497,10 +497,13 @@ extern "C" int rpc_rejection_cholesky(rpc_ctx *ctx, void *stream, double *H, int
     if (!configured) {
         RPC_CUDA(cudaFuncSetAttribute(rejection_cholesky_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       220 * 1024));
+        RPC_CUDA(cudaFuncSetAttribute(rejection_cholesky_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      220 * 1024));
         configured = true;
     }
     // thr[m] | Lb[RB][m] | accpos[m] + blk ints | (packed lower triangle)
     const size_t head = ((size_t)m + RB * m + (m + 16) / 2 + 8 + RB) * sizeof(double);
+    RPC_CHECK_ARG(m <= RPC_MAX_BLOCK, "block larger than RPC_MAX_BLOCK");
     if (m <= RC_SMEM_MAX_M) {
         size_t shm = head + (size_t)m * (m + 1) / 2 * sizeof(double);
         rejection_cholesky_kernel<true><<<1, RC_THREADS, shm, st>>>(H, m, ldh, u, max_accept, mode, shift, ctx->ws, L, ldl,
@@ -687,7 +690,7 @@ static int launch_panel_trsm(rpc_ctx *ctx, cudaStream_t st, const double *P, int
     size_t shm_l = shm + (size_t)s * (s + 1) / 2 * sizeof(double);
     static bool configured = false;
     if (!configured) {
-        RPC_CUDA(cudaFuncSetAttribute(panel_trsm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        RPC_CUDA(cudaFuncSetAttribute(panel_trsm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         RPC_CUDA(cudaFuncSetAttribute(panel_trsm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
@@ -709,7 +712,7 @@ extern "C" int rpc_build_panel_dev(rpc_ctx *ctx, void *stream, const double *P, 
                                    const int64_t *idx, const double *Xpiv, const double *pnorm, int64_t ldp, int64_t *sel_idx,
                                    double *Xsel, double *nsel) {
     RPC_CHECK_ARG(ctx && L && At && acc && s_dev && idx && sel_idx, "null pointer");
-    RPC_CHECK_ARG(s_max >= 1 && s_max <= 768 && c >= 0 && (c == 0 || P), "bad sizes");
+    RPC_CHECK_ARG(s_max >= 1 && s_max <= RPC_MAX_BLOCK && c >= 0 && (c == 0 || P), "bad sizes (s_max <= RPC_MAX_BLOCK)");
     cudaStream_t st = (cudaStream_t)stream;
     if (!ctx->panel_ld_table) {
         int32_t host[257];
@@ -728,7 +731,7 @@ extern "C" int rpc_build_panel_dev(rpc_ctx *ctx, void *stream, const double *P, 
 extern "C" int rpc_build_panel(rpc_ctx *ctx, void *stream, const double *P, int64_t ldP, int c, const int32_t *acc, int s,
                                const double *L, int64_t ldl, int mode, double *At, int64_t ldat, int k_pad) {
     RPC_CHECK_ARG(ctx && L && At, "null pointer");
-    RPC_CHECK_ARG(s >= 1 && s <= 768 && c >= 0 && (c == 0 || P), "bad sizes");
+    RPC_CHECK_ARG(s >= 1 && s <= RPC_MAX_BLOCK && c >= 0 && (c == 0 || P), "bad sizes (s <= RPC_MAX_BLOCK)");
     RPC_CHECK_ARG(k_pad >= c + s && ldat >= s, "k_pad >= c+s and ldat >= s required");
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == 0) return launch_panel_trsm(ctx, st, P, ldP, c, acc, s, L, ldl, At, ldat, k_pad, nullptr, nullptr);

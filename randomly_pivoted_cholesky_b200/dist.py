@@ -2,16 +2,25 @@
 
 GPU r owns a contiguous block of points X[lo:hi] and the matching columns of G, rows and the residual
 diagonal (= row sharding of F = G^T).  Every N-proportional kernel runs on the local shard with no
-communication; per round there are exactly two small NCCL collectives over NVLink:
+communication; per round there are exactly two small exchanges over NVLink:
 
-  1. all-gather of the residual-diagonal shards (8 bytes per point) so that EVERY rank runs the exact
-     pivot sampler on the full diagonal and draws the same, reference-identical pivots;
-  2. sum all-reduce of the pivot payload [X[idx] | |x|^2 | G[:c, idx]]: the owning shard writes the
-     values, all others write zeros, so the sum has exactly one non-zero contributor per slot (exact).
+  1. the residual-diagonal shards (8 bytes per point), so that EVERY rank runs the exact pivot sampler on
+     the full diagonal and draws the same, reference-identical pivots;
+  2. the pivot payload [X[idx] | |x|^2 | G[:c, idx]], written by the shard that owns each pivot.
+
+Data plane (recorded in bench.py's `config.data_plane`):
+  * "peer"  (default on one box): `PeerWindow` below -- one buffer per rank mapped into every process over CUDA
+    IPC; the Schur kernel's epilogue stores its block of the new diagonal into every rank's copy and the pivot
+    gather stores the owners' entries into every rank's payload, each followed by a release/acquire epoch
+    (csrc/peers.cu, csrc/dmma_gemm.cuh).  No NCCL call is left inside a round except the broadcast of the
+    round's uniforms (control data, overlapped with the Schur update on a side stream);
+  * "nccl"  (RPC_B200_PEER=0, or peer mapping unavailable): `gather_diag` = all-gather, `exchange_payload` =
+    sum all-reduce in which every slot has exactly one non-zero contributor (exact).
 
 The b x b work (residual Gram, rejection / shifted Cholesky, panel solve) is replicated: identical inputs
-and identical kernels give identical results on every rank.  The functions below are plain torch /
-torch.distributed and also run on CPU tensors with the gloo backend (tests/test_dist_cpu.py).
+and identical kernels give identical results on every rank; `broadcast_draws` makes the inputs identical (rank
+0's uniforms win).  The plain collectives below also run on CPU tensors with the gloo backend
+(tests/test_dist_cpu.py).
 """
 from __future__ import annotations
 
@@ -77,6 +86,32 @@ def exchange_payload(info: ShardInfo, payload: torch.Tensor) -> torch.Tensor:
     if info.world > 1:
         dist.all_reduce(payload, op=dist.ReduceOp.SUM, group=info.group)
     return payload
+
+
+def _src_rank(info: ShardInfo) -> int:
+    """Global rank of the group's rank 0 (torch.distributed addresses broadcast sources by GLOBAL rank)."""
+    if info.group is None:
+        return 0
+    return dist.get_global_rank(info.group, 0)
+
+
+def broadcast_draws(info: ShardInfo, t: torch.Tensor) -> torch.Tensor:
+    """Every rank must consume the SAME uniforms (replicated sampler / rejection Cholesky): rank 0's draws win.
+    The reference draws from unseeded generators (rpcholesky.py:25,82,151,179), so nothing else ties the ranks'
+    streams together.  In place; a no-op for world 1."""
+    if info.world > 1:
+        dist.broadcast(t, src=_src_rank(info), group=info.group)
+    return t
+
+
+def agree_on_int(info: ShardInfo, value: int, device) -> int:
+    """Rank 0's value of a host-side integer decision (the auto-tuned proposal count b of accelerated RPCholesky is
+    derived from rank-local wall-clock time, rpcholesky.py:211-220): one tiny broadcast + host read."""
+    if info.world == 1:
+        return int(value)
+    t = torch.tensor([int(value)], dtype=torch.int64, device=device)
+    dist.broadcast(t, src=_src_rank(info), group=info.group)
+    return int(t.item())
 
 
 def gather_columns(info: ShardInfo, local: torch.Tensor) -> torch.Tensor:

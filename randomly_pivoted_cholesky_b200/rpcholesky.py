@@ -44,6 +44,8 @@ USE_SPEC = _os.environ.get("RPC_B200_SPEC", "auto")
 
 # bench.py sets this to a list to collect (start_event, end_event, flops, bytes, phase) per timed launch
 KERNEL_TIMERS = None
+# data plane the last factorisation actually ran on: "single" | "peer" (NVLink peer windows) | "nccl" (collectives)
+LAST_DATA_PLANE = "single"
 
 
 class _timed:
@@ -111,6 +113,8 @@ class _State:
         self.diag_pending = False              # True: the last Schur update published the new diagonal into diag_full
         if self.info.world > 1 and USE_PEER and not USE_FUSED and self.dev.type == "cuda" and self.ldx:
             self.peer = rdist.PeerWindow.get(self.info, self.ctx, self.dev, payload_len)     # None: no peer access here
+        global LAST_DATA_PLANE
+        LAST_DATA_PLANE = "single" if self.info.world == 1 else ("peer" if self.peer is not None else "nccl")
         if self.peer is not None:
             self.payload = self.peer.payload[:payload_len]
             self.diag_full = self.peer.diag_full
@@ -136,6 +140,8 @@ class _State:
         self.sel_host = torch.empty((m_max,), dtype=torch.int64).pin_memory()
         self.rb_host = None
         self.spec = False
+        self.draw_stream = None                # sharded: side stream of the uniform upload + broadcast
+        self.ev_u_free = None
         A._dev_diag_into(self.diag)
         A._count(self.n)                                       # A.diag() counts N queries (matrix.py:33-39)
 
@@ -176,13 +182,29 @@ class _State:
 
     # ---- thin wrappers over the C ABI ------------------------------------------------------------
     def upload_uniforms(self, up, ur=None):
+        """u_dev <- [proposal uniforms | rejection uniforms].  Row-sharded runs use RANK 0's draws on every rank (the
+        reference's generators are unseeded, so nothing else makes the ranks' streams agree): upload + broadcast run on a
+        side stream, beside the previous round's Schur update, and the sampler waits for them."""
         m = len(up)
         self.u_host[:m] = torch.from_numpy(up)
         tot = m
         if ur is not None:
             self.u_host[m:m + len(ur)] = torch.from_numpy(ur)
             tot = m + len(ur)
-        self.u_dev[:tot].copy_(self.u_host[:tot], non_blocking=True)
+        if self.info.world == 1 or self.dev.type != "cuda":
+            self.u_dev[:tot].copy_(self.u_host[:tot], non_blocking=True)
+            rdist.broadcast_draws(self.info, self.u_dev[:tot])
+            return
+        if self.draw_stream is None:
+            self.draw_stream = torch.cuda.Stream(device=self.dev)
+            self.ev_draw = torch.cuda.Event()
+        if self.ev_u_free is not None:
+            self.draw_stream.wait_event(self.ev_u_free)        # the last kernel that read the previous round's uniforms
+        with torch.cuda.stream(self.draw_stream):
+            self.u_dev[:tot].copy_(self.u_host[:tot], non_blocking=True)
+            rdist.broadcast_draws(self.info, self.u_dev[:tot])
+            self.ev_draw.record(self.draw_stream)
+        torch.cuda.current_stream().wait_event(self.ev_draw)
 
     def sample(self, m, u_off=0):
         """Every rank samples on the FULL residual diagonal (all-gathered when sharded): identical pivots everywhere."""
@@ -239,6 +261,9 @@ class _State:
         check(self.lib.rpc_rejection_cholesky(self.ctx.handle, _stream(), _ptr(self.H), m, self.m_max, u, max_accept, mode,
                                               float(shift), _ptr(self.L), self.m_max, _ptr(self.acc), _ptr(self.info_dev)),
               "rpc_rejection_cholesky")
+        if self.draw_stream is not None:
+            self.ev_u_free = torch.cuda.Event()
+            self.ev_u_free.record()
 
     # ---- speculative evaluation of all proposals beside the rejection Cholesky (accelerated, sharded) ---------------------
     def enable_speculation(self):
@@ -369,6 +394,16 @@ class _State:
         return PSDLowRank(self.G[:count, :nl], n=self.n, idx=arr_idx, rows=self.rows[:count, :nl], shard_info=self.info)
 
 
+def _checked_block(b):
+    """The reference accepts any block size; the single-CTA b x b kernels hold one block in shared memory."""
+    b = int(b)
+    if b < 1:
+        raise ValueError("block size b must be positive")
+    if b > _lib.MAX_BLOCK:
+        raise ValueError("block size b = %d exceeds the device limit RPC_MAX_BLOCK = %d (include/rpc_b200.h)" % (b, _lib.MAX_BLOCK))
+    return b
+
+
 def _raise_if_invalid(stats_host):
     if stats_host[2] != 0.0:
         raise RuntimeError("internal error: exact-scan binade bound violated")
@@ -483,7 +518,7 @@ def block_cholesky_helper(A, k, b, alg, stoptol=1e-14, strategy="regularize", rb
     A = _as_operator(A)
     if stoptol is None:
         stoptol = 1e-14
-    b = int(b)
+    b = _checked_block(b)
     if rbrp_rtol == "1/b":                                                    # rpcholesky.py:75-76
         rbrp_rtol = 1.0 / b
     use_tol = rbrp_rtol is not None and rbrp_atol is not None                 # rpcholesky.py:56
@@ -575,8 +610,9 @@ def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
     if b == "auto":                                            # :169-173
         b = int(np.ceil(k / 10))
         auto_b = True
-    b = int(b)
-    b_cap = max(b, int(math.ceil(k / 3)), 10) if auto_b else b
+    b = _checked_block(b)
+    # the auto-tuned b may grow to ceil(k/3) (:216); the device kernels hold one block per CTA: capped at RPC_MAX_BLOCK
+    b_cap = min(max(b, int(math.ceil(k / 3)), 10), _lib.MAX_BLOCK) if auto_b else b
     st = _State(A, k, b_cap)
     st.enable_speculation()
     rng = np.random.default_rng()
@@ -635,6 +671,7 @@ def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
             target = int(np.ceil(b * process_time / (4 * max(rejection_time, 1e-9))))
             b = max([min([target, int(np.ceil(1.5 * b)), int(np.ceil(k / 3))]), int(np.ceil(b / 3)), 10])
             b = min(b, b_cap)
+            b = rdist.agree_on_int(st.info, b, st.dev)         # sharded: wall-clock differs per rank, rank 0 decides
         if verbose:
             print("Accepted {} / {}".format(num_sel, len(accepted)))
     else:

@@ -66,6 +66,12 @@ def _worker(rank, world, port, n, k, m):
         rdist.exchange_payload(info, payload)
         assert np.array_equal(Xp.numpy(), X_full[idx.numpy()])
         assert np.array_equal(P.numpy(), G_full[:, idx.numpy()])
+        # 2b. the round's uniforms: every rank draws from its OWN unseeded stream, rank 0's draws win everywhere
+        mine = torch.from_numpy(np.random.default_rng(1000 + rank).random(2 * m))
+        want = np.random.default_rng(1000).random(2 * m)
+        rdist.broadcast_draws(info, mine)
+        assert np.array_equal(mine.numpy(), want)
+        assert rdist.agree_on_int(info, 100 + 7 * rank, "cpu") == 100
         # 3. column shards assemble back into the full factor
         Gl = torch.zeros((k, info.shard), dtype=torch.float64)
         Gl[:, :info.n_loc] = torch.from_numpy(G_full[:, info.lo:info.hi])

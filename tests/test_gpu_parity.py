@@ -423,7 +423,7 @@ def test_reconstruction_property_large(rpc):
 
 
 @pytest.mark.parametrize("kernel,kw,b,k", [("matern", {"nu": 2.5}, 400, 900), ("gaussian", {}, 640, 1400),
-                                           ("laplace", {}, 288, 600)])
+                                           ("laplace", {}, 288, 600), ("laplace", {}, 1000, 2200), ("matern", {"nu": 1.5}, 1536, 3000)])
 def test_large_proposal_blocks_against_oracle(rpc, kernel, kw, b, k):
     """configs[3] shape (accelerated, b = 400 > one 256-row tile, Matern-5/2, d = 3) at N = 24,000 and two more
     kernels: exercises the row-chunked evaluator / Schur update and the global-memory rejection path."""
@@ -438,7 +438,10 @@ def test_large_proposal_blocks_against_oracle(rpc, kernel, kw, b, k):
     assert lra.rounds == ref.rounds
     if b > 600:
         assert max(ref.rounds) > 256          # more accepted pivots than one 256-row tile: row-chunked update
-    assert relerr(lra.G, ref.G) <= 1e-9 and relerr(lra.rows, ref.rows) <= F_TOL
+    # G: 1e-10 unless a round's triangular factor is ill conditioned (oracle.g_tolerance states the argument); rows: 1e-10
+    eg = relerr(lra.G, ref.G)
+    assert eg <= orc.g_tolerance(ref), (eg, max(ref.cond_L))
+    assert relerr(lra.rows, ref.rows) <= F_TOL
 
 
 def test_block_large_b_against_oracle(rpc):
@@ -448,7 +451,9 @@ def test_block_large_b_against_oracle(rpc):
     rng, _ = orc.make_streams(41)
     ref = orc.block_rpcholesky(orc.OracleKernelMatrix(X, kernel="gaussian", bandwidth=float(np.sqrt(5))), 700, 320, rng)
     assert [int(i) for i in lra.idx] == [int(i) for i in ref.idx]
-    assert relerr(lra.G, ref.G) <= 1e-9 and relerr(lra.rows, ref.rows) <= F_TOL
+    eg = relerr(lra.G, ref.G)
+    assert eg <= orc.g_tolerance(ref), (eg, max(ref.cond_L))
+    assert relerr(lra.rows, ref.rows) <= F_TOL
 
 
 # ---- first "next" row: KRR_Nystrom on top of the hot path ------------------------------------------
@@ -509,8 +514,13 @@ def test_tiny_and_ragged_sizes(rpc, n, d, k, b):
         assert [int(i) for i in lra.idx] == [int(i) for i in ref.idx], alg
         assert lra.G.shape == ref.G.shape
         assert relerr(lra.rows, ref.rows) <= F_TOL
-        assert relerr(lra.G.T @ lra.G, ref.G.T @ ref.G) <= 1e-9
-        assert relerr(lra.G, ref.G) <= 1e-9
+        if alg == "simple":
+            tol = F_TOL                      # one pivot per step: a division by sqrt(diag), no triangular solve
+        else:
+            tol = orc.g_tolerance(ref)       # 1e-10 unless a round's factor is ill conditioned (tiny N: pivots crowd together)
+        eg = relerr(lra.G, ref.G)
+        assert eg <= tol, (alg, eg, getattr(ref, "cond_L", None))
+        assert relerr(lra.G.T @ lra.G, ref.G.T @ ref.G) <= 2 * tol
         assert A.num_queries() == A0.num_queries()
 
 

@@ -84,6 +84,7 @@ def test_manhattan_is_sequential_cdist():
     from scipy.spatial.distance import cdist
     rng = np.random.default_rng(3)
     X = rng.standard_normal((9, 50)); Y = rng.standard_normal((200, 50))
+    assert np.array_equal(orc.manhattan_distances_loop(X, Y), cdist(X, Y, "cityblock"))
     assert np.array_equal(orc.manhattan_distances(X, Y), cdist(X, Y, "cityblock"))
 
 
