@@ -10,8 +10,9 @@ Prints ONE JSON line (rank 0).  `value` = A.num_queries() / wall with X resident
 through the public API starting from a pinned HOST copy of X (H2D inside the timed region) and reading
 the pivots and the trace-norm error back; `roofline` = the fused Schur-update DMMA kernel against the
 measured FP64 peak; `cpu_baseline` = the numpy oracle on a bounded sample on this box's host cores.
-`--impl reference` times the oracle port alone (the reference itself is Python that cannot travel to
-the GPU box; oracle/rpc_oracle.py restates it call for call and is pinned to it by tests/golden).
+`--impl reference` times the reference's own CPU implementation of the path: the UNMODIFIED reference modules copied
+into oracle/_ref/ by oracle/make_ref.py (kind "reference"; git-ignored, travels with gpurun) under the replay patch, or,
+when that copy is absent, the numpy port oracle/rpc_oracle.py (kind "port", pinned to the reference by tests/golden).
 """
 import argparse
 import json
@@ -71,6 +72,58 @@ def make_points(n, d):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference (numpy/OpenBLAS with all host threads)
 # ------------------------------------------------------------------------------------------------
+_REF = None
+
+
+def reference_modules():
+    """The unmodified reference from oracle/_ref (oracle/make_ref.py), or None."""
+    global _REF
+    if _REF is None:
+        try:
+            from oracle import make_ref
+            _REF = make_ref.load() or False
+        except Exception:
+            _REF = False
+    return _REF or None
+
+
+def cpu_kind(w):
+    return "reference" if (reference_modules() and w["alg"] != "krr") else "port"
+
+
+def run_reference(w, n_sample):
+    """One factorisation by the UNMODIFIED reference (oracle/_ref) on the replayed draws: (queries, seconds)."""
+    ref = reference_modules()
+    X = make_points(n_sample, w["d"])
+    A = ref["matrix"].KernelMatrix(X, kernel=w["kernel"], bandwidth=bandwidth(w), **w.get("kw", {}))
+    drv = ref["rpcholesky"]
+    with replay():
+        t0 = time.perf_counter()
+        if w["alg"] == "accelerated":
+            drv.accelerated_rpcholesky(A, w["k"], b=w["b"])
+        elif w["alg"] == "block":
+            drv.block_rpcholesky(A, w["k"], b=w["b"])
+        else:
+            drv.simple_rpcholesky(A, w["k"])
+        dt = time.perf_counter() - t0
+    return A.num_queries(), dt
+
+
+def run_cpu(w, n_sample):
+    return run_reference(w, n_sample) if cpu_kind(w) == "reference" else run_oracle(w, n_sample)
+
+
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core (VERDICT r1 #4)."""
+    n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)
+    except Exception:
+        pass
+    return n
+
+
 def run_oracle(w, n_sample):
     from oracle import rpc_oracle as orc
     X = make_points(n_sample, w["d"])
@@ -108,7 +161,8 @@ def sample_size(w, target_seconds):
     """Points for a CPU run of about `target_seconds`: a short probe of the same workload is timed and scaled (the cost
     is linear in N); BLAS-bound and cdist-bound kernels differ by 100x, so a fixed guess does not work."""
     n0 = int(min(w["N"], max(2 * w["k"], 4000)))
-    _, t0 = run_oracle(w, n0)
+    run_cpu(w, n0)                               # imports, BLAS thread pool start-up
+    _, t0 = run_cpu(w, n0)
     n = int(min(w["N"], max(n0, n0 * target_seconds / max(t0, 1e-3))))
     return max(n0, n // 1000 * 1000)
 
@@ -117,26 +171,51 @@ def reference_arm(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_all_host_threads()
     n_s = sample_size(w, 8.0)
     for _ in range(args.warmup):
-        run_oracle(w, n_s)
+        run_cpu(w, n_s)
     t_tot, q_tot = 0.0, 0
     for _ in range(args.steps):
-        q, dt = run_oracle(w, n_s)
+        q, dt = run_cpu(w, n_s)
         t_tot += dt
         q_tot += q
     value = q_tot / t_tot
-    sample = "same workload at N=%d (k, b, d, kernel unchanged; cost is linear in N)" % n_s
+    kind = cpu_kind(w)
+    sample = "same workload at N=%d (k, b, d, kernel unchanged; cost is linear in N); %s" % (
+        n_s, "unmodified reference modules (oracle/_ref)" if kind == "reference" else "numpy port oracle/rpc_oracle.py")
     out = {
         "impl": "reference", "metric": "kernel entries/s (rank-k RPCholesky, A.num_queries()/wall)", "value": value,
         "unit": "entries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": {"workload": w["text"], "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "entries/s", "cores": cpu_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "entries/s", "cores": cpu_threads(), "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(out), flush=True)
+
+
+PLANE_TEXT = {"peer": "the producing kernels' stores into NVLink peer windows (CUDA IPC) + release/acquire epochs, no NCCL in the data path",
+              "nccl": "NCCL all-gather + exact sum all-reduce (peer windows unavailable or RPC_B200_PEER=0)"}
+
+
+def schur_executed_flops(c, s, n_cols, tri=True):
+    """Flops the Schur kernel's DMMAs execute for one update of s rows on c previous rows over n_cols columns: 8-row
+    fragments x 4-deep k steps, rows padded to the tile (csrc/big_kernels.cu tile_rows_for), and -- with the triangular skip
+    -- only the fragments at or below the diagonal of the L^{-T} block (csrc/dmma_gemm.cuh consume_stage_tri)."""
+    total = 0
+    for m0 in range(0, s, 256):
+        m = min(256, s - m0)
+        mt = (m + 7) // 8 * 8 if m > 128 else next(t for t in (16, 32, 64, 96, 128) if m <= t)
+        nfrag = mt // 8
+        for kk0 in range(0, (c + s + 3) // 4 * 4, 4):
+            if tri and kk0 - c > 7:
+                first = max(0, -(-(kk0 - c - 7 - m0) // 8))        # first fragment whose last row reaches panel row kk0
+                total += max(0, nfrag - first) * 8 * 4 * 2
+            else:
+                total += nfrag * 8 * 4 * 2
+    return float(total) * n_cols
 
 
 # ------------------------------------------------------------------------------------------------
@@ -305,6 +384,7 @@ def gpu_arm(args, w):
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
+    data_plane = getattr(drv, "LAST_DATA_PLANE", "single")      # what the timed factorisations actually ran on
     launches = _lib.total_launches() - l0
     timers = drv.KERNEL_TIMERS
     drv.KERNEL_TIMERS = None
@@ -317,17 +397,26 @@ def gpu_arm(args, w):
 
     # ---- roofline of the dominant kernel (fused Schur update), from the CUDA events of the timed region
     phases = {}
-    for ev0, ev1, phase, flops, nbytes in timers:
+    for ev0, ev1, phase, flops, nbytes, *_ in timers:
         p = phases.setdefault(phase, [0.0, 0.0, 0.0, 0])
         p[0] += ev0.elapsed_time(ev1) * 1e-3
         p[1] += flops
         p[2] += nbytes
         p[3] += 1
-    peak_tf = FP64_PEAK_FALLBACK_TFLOPS
+    # FP64 roofline denominator: the DMMA stream peak measured NOW on this device (rpc_probe_fp64_peak, best of 5 launches of
+    # ~10 ms, after the timed region); the tracked round-1 figure is only the cross-check / fallback
+    tracked_tf = FP64_PEAK_FALLBACK_TFLOPS
     try:
-        peak_tf = json.load(open(os.path.join(ROOT, "profiles", "fp64_peaks_r01.json")))["fp64_peak_tflops"]
+        tracked_tf = json.load(open(os.path.join(ROOT, "profiles", "fp64_peaks_r01.json")))["fp64_peak_tflops"]
     except Exception:
         pass
+    try:
+        from randomly_pivoted_cholesky_b200 import ops
+        peak_tf = float(ops.fp64_peak_tflops(dev))
+        peak_src = "DMMA.8x8x4 stream measured in this run on this device (rpc_probe_fp64_peak: %d CTAs x 8 warps x 16 accumulators, best of 5); " \
+                   "cross-check profiles/fp64_peaks_r01.json = %.1f" % (torch.cuda.get_device_properties(dev).multi_processor_count, tracked_tf)
+    except Exception as exc:                      # pragma: no cover
+        peak_tf, peak_src = tracked_tf, "profiles/fp64_peaks_r01.json (in-run probe failed: %s)" % exc
     hbm = None
     try:
         hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -343,17 +432,23 @@ def gpu_arm(args, w):
     if "schur" in phases:
         sec, flops, nbytes, cnt = phases["schur"]
         ach = flops / sec / 1e12
-        roofline = {"bound": "tensor", "kernel": "dg::gemm_kernel<MODE_SCHUR> (FP64 DMMA, fused diag update)",
+        # flops the DMMA pipe actually executes: row-tile and k padding, and the fragment staircase along the diagonal of the
+        # triangular block (whose zero half is skipped) -- from the launch shapes of the timed region
+        executed = sum(schur_executed_flops(t[5][0], t[5][1], t[5][2]) for t in timers if t[2] == "schur" and len(t) > 5 and t[5])
+        roofline = {"bound": "tensor", "kernel": "dg::gemm_kernel<MODE_SCHUR> (FP64 DMMA: Schur product + triangular solve + diag update fused)",
                     "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
                     "traffic_source": "profiles/traffic_r01.json (ncu, same command)" if traffic else None,
-                    "peak_source": "measured FP64 DMMA peak, profiles/fp64_peaks_r01.json (MEASURED_PEAKS.json holds bf16/HBM only)",
+                    "peak_source": peak_src, "peak_tracked_r01": tracked_tf,
                     "launches": cnt, "avg_launch_ms": 1e3 * sec / cnt, "share_of_step": sec / (ms * 1e-3),
                     "algorithmic_flops_per_launch": flops / cnt, "algorithmic_bytes_per_launch": nbytes / cnt,
+                    "algorithmic_flops_rule": "SURVEY 8(d): s (2c + s) N_loc per launch = Schur product 2 s c N + triangular solve s^2 N",
+                    "executed_flops_per_launch": executed / cnt if executed else None,
+                    "executed_tflops": executed / sec / 1e12 if executed else None,
                     "hbm_gbs_achieved": nbytes / sec / 1e9, "hbm_peak_gbs": hbm}
     elif "simple" in phases:
         sec, flops, nbytes, cnt = phases["simple"]
         ach = nbytes / sec / 1e9
-        roofline = {"bound": "hbm", "kernel": "simple_step_kernel (fused GEMV over G[:i] + kernel row + diag update)",
+        roofline = {"bound": "hbm", "kernel": "simple_step_kernel (fused GEMV over G[:i] + kernel row + diag update) + exact sampler, whole k-step loop per launch bracket",
                     "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm if hbm else None, "traffic": None,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs", "launches": cnt, "avg_launch_ms": 1e3 * sec / cnt,
                     "share_of_step": sec / (ms * 1e-3), "algorithmic_bytes_per_launch": nbytes / cnt}
@@ -409,9 +504,10 @@ def gpu_arm(args, w):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
+            use_all_host_threads()
             n_s = sample_size(w, 12.0)
-            q, dt = run_oracle(w, n_s)
-            cpu = {"value": q / dt, "unit": "entries/s", "cores": cpu_threads(), "kind": "port",
+            q, dt = run_cpu(w, n_s)
+            cpu = {"value": q / dt, "unit": "entries/s", "cores": cpu_threads(), "kind": cpu_kind(w),
                    "sample": "same workload at N=%d, one run (%.1f s); cost is linear in N" % (n_s, dt)}
         out = {
             "metric": "kernel entries/s (rank-k RPCholesky, A.num_queries()/wall)", "value": value, "unit": "entries/s",
@@ -419,8 +515,10 @@ def gpu_arm(args, w):
             "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": w["text"], "rank": rank_k, "accepted_per_round": rounds, "l2": "inputs (G: %.1f GB) larger than L2" % (8e-9 * w["k"] * n),
-                       "parallelism": "row-sharded x%d (N/%d points per GPU, NCCL diag all-gather + payload all-reduce per round)"
-                       % (world, world) if world > 1 else "single GPU"},
+                       "data_plane": data_plane,
+                       "parallelism": ("row-sharded x%d (N/%d points per GPU; per round: residual diagonal + pivot payload exchanged by %s; "
+                                       "the round's uniforms broadcast from rank 0)" % (world, world, PLANE_TEXT.get(data_plane, data_plane)))
+                       if world > 1 else "single GPU"},
             "wall_time_s": ms * 1e-3 / args.steps, "phase_ms_per_step": phase_ms, "dominant_kernel_launches_ms_tflops": detail,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
         }

@@ -227,10 +227,20 @@ int rpc_gather_rows(rpc_ctx *ctx, void *stream, const double *src, int64_t lds, 
                     const int32_t *count_dev, int max_rows, double *dst, int64_t ldd, int64_t n_pad);
 
 /* rpc_schur_update with the new rows taken from rows_src through a row map (new row i = rows_src[rowmap[i], :]; rowmap
- * may be NULL) and, when peers != NULL, the fused diagonal exchange of rpc_schur_update_peers. */
+ * may be NULL) and, when peers != NULL, the fused diagonal exchange of rpc_schur_update_peers.
+ * panel_lower != 0 declares that panel rows c..c+s-1 hold the transpose of a LOWER-triangular matrix, At[c + i, j] == 0
+ * for j < i -- what rpc_build_panel mode 0 / rpc_build_panel_dev produce (L^{-T}; np.linalg.solve(L, .) of
+ * rpcholesky.py:107,207 is a triangular solve) -- so the kernel skips the structurally-zero half of that block: the
+ * executed flops are then the algorithmic s (2c + s) n_pad instead of 2 s (c + s) n_pad.  Pass 0 for a dense panel
+ * (rpc_build_panel mode 1, the eigh fallback of rpcholesky.py:109-114). */
 int rpc_schur_update_ex(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At, int64_t ldat,
                         int k_pad, const double *rows_src, int64_t ldr, const int32_t *rowmap, double *diag, int64_t n_pad,
-                        const struct rpc_peers *peers, unsigned long long epoch);
+                        const struct rpc_peers *peers, unsigned long long epoch, int panel_lower);
+
+/* Measurement aid (bench.py's roofline denominator): enqueues one launch of a pure DMMA.8x8x4 stream (one 256-thread CTA
+ * per SM, 16 independent accumulator pairs per warp, `iters` rounds) and returns its flop count through the HOST pointer
+ * flops_per_launch; the caller times it with CUDA events on `stream`.  Replaces no reference call site. */
+int rpc_probe_fp64_peak(rpc_ctx *ctx, void *stream, int iters, double *flops_per_launch_host);
 
 /* ---- peer-memory exchange for row-sharded runs (one process per GPU of one NVSwitch box) --------------------------
  * The two per-round exchanges of the sharded factorisation (the residual-diagonal all-gather and

@@ -117,7 +117,7 @@ _SIGNATURES = {
     "rpc_ctx_reserve_sms": (_INT, [_P, _INT]),
     "rpc_gather_rows": (_INT, [_P, _P, _P, _I64, _P, _P, _INT, _P, _I64, _I64]),
     "rpc_schur_update_ex": (_INT, [_P, _P, _P, _I64, _INT, _INT, _P, _I64, _INT, _P, _I64, _P, _P, _I64, C.POINTER(Peers),
-                                   C.c_uint64]),
+                                   C.c_uint64, _INT]),
     "rpc_peer_alloc": (_INT, [_P, _I64, C.POINTER(_P), _P]),
     "rpc_peer_free": (_INT, [_P, _P]),
     "rpc_peer_open": (_INT, [_P, _P, C.POINTER(_P)]),
@@ -127,6 +127,7 @@ _SIGNATURES = {
                                       C.c_uint64]),
     "rpc_gather_pivots_peers": (_INT, [_P, _P, _P, _INT, _P, _P, _INT, _I64, _I64, _I64, _P, _I64, _INT, _I64, _I64, _I64, _I64,
                                        C.POINTER(Peers), C.c_uint64]),
+    "rpc_probe_fp64_peak": (_INT, [_P, _P, _INT, C.POINTER(_DBL)]),
     "rpc_simple_run": (_INT, [_P, _P, _INT, C.POINTER(KernelSpec), _P, _P, _INT, _I64, _P, _I64, _I64, _P, _P, _P, _INT, _INT, _P,
                               _I64, _P, _I64, _P, _I64]),
     "rpc_simple_step": (_INT, [_P, _P, C.POINTER(KernelSpec), _P, _P, _INT, _I64, _P, _I64, _I64, _P, _INT, _P, _I64, _P,

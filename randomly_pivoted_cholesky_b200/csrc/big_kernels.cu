@@ -168,11 +168,13 @@ __global__ void __launch_bounds__(256) tail_panel_repack_kernel(const double *__
 }
 
 static bool g_no_tail = getenv("RPC_B200_NO_TAIL") != nullptr;       // diagnostics: keep every column tile in the main launch
+static bool g_no_tri = getenv("RPC_B200_NO_TRI") != nullptr;         // diagnostics: run the zero half of the triangular block too
 
 static int schur_update_impl(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At, int64_t ldat,
                              int k_pad, const double *rows_new, int64_t ldr, const int32_t *rowmap, double *diag, int64_t n_pad,
-                             const rpc_peers *peers, unsigned long long epoch) {
+                             const rpc_peers *peers, unsigned long long epoch, int panel_lower) {
     RPC_CHECK_ARG(ctx && G && At && rows_new && diag, "null pointer");
+    const int tri = (panel_lower && !g_no_tri) ? 1 : 0;
     RPC_CHECK_ARG(s >= 1 && c >= 0, "s >= 1, c >= 0");
     RPC_CHECK_ARG(n_pad > 0 && n_pad % RPC_COL_ALIGN == 0, "n_pad must be a positive multiple of RPC_COL_ALIGN");
     RPC_CHECK_ARG(k_pad % RPC_KT == 0 && k_pad >= c + s, "k_pad must be a multiple of RPC_KT and >= c+s");
@@ -207,6 +209,7 @@ static int schur_update_impl(rpc_ctx *ctx, void *stream, double *G, int64_t ldg,
             p.At = At; p.ldat = ldat; p.k_pad = k_pad; p.m_valid = s;
             p.G = G; p.ldg = ldg; p.c = c; p.R = rows_new; p.ldr = ldr; p.K = c + s; p.rowmap = rowmap;
             p.Cout = G + (int64_t)c * ldg; p.ldc = ldg; p.diag = diag;
+            p.tri = tri; p.row_base = 0;
             if (peers) {
                 p.npeers = peers->world;
                 for (int r = 0; r < peers->world; ++r) {
@@ -254,6 +257,7 @@ static int schur_update_impl(rpc_ctx *ctx, void *stream, double *G, int64_t ldg,
         p.At = At + m0; p.ldat = ldat; p.k_pad = k_pad; p.m_valid = m;
         p.G = G; p.ldg = ldg; p.c = c; p.R = rows_new; p.ldr = ldr; p.K = c + s; p.rowmap = rowmap;
         p.Cout = G + (int64_t)(c + m0) * ldg; p.ldc = ldg; p.diag = diag;
+        p.tri = tri; p.row_base = m0;
         if (peers && m0 + 256 >= s) {
             // the last row chunk leaves the final diagonal: it stores it into every rank's copy and publishes the epoch
             p.npeers = peers->world;
@@ -275,20 +279,22 @@ static int schur_update_impl(rpc_ctx *ctx, void *stream, double *G, int64_t ldg,
 extern "C" int rpc_schur_update(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At,
                                 int64_t ldat, int k_pad, const double *rows_new, int64_t ldr, double *diag,
                                 int64_t n_pad) {
-    return schur_update_impl(ctx, stream, G, ldg, c, s, At, ldat, k_pad, rows_new, ldr, nullptr, diag, n_pad, nullptr, 0);
+    return schur_update_impl(ctx, stream, G, ldg, c, s, At, ldat, k_pad, rows_new, ldr, nullptr, diag, n_pad, nullptr, 0, 0);
 }
 
 extern "C" int rpc_schur_update_ex(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At,
                                    int64_t ldat, int k_pad, const double *rows_src, int64_t ldr, const int32_t *rowmap,
-                                   double *diag, int64_t n_pad, const rpc_peers *peers, unsigned long long epoch) {
-    return schur_update_impl(ctx, stream, G, ldg, c, s, At, ldat, k_pad, rows_src, ldr, rowmap, diag, n_pad, peers, epoch);
+                                   double *diag, int64_t n_pad, const rpc_peers *peers, unsigned long long epoch,
+                                   int panel_lower) {
+    return schur_update_impl(ctx, stream, G, ldg, c, s, At, ldat, k_pad, rows_src, ldr, rowmap, diag, n_pad, peers, epoch,
+                             panel_lower);
 }
 
 extern "C" int rpc_schur_update_peers(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At,
                                       int64_t ldat, int k_pad, const double *rows_new, int64_t ldr, double *diag, int64_t n_pad,
                                       const rpc_peers *peers, unsigned long long epoch) {
     RPC_CHECK_ARG(peers != nullptr, "peer table required");
-    return schur_update_impl(ctx, stream, G, ldg, c, s, At, ldat, k_pad, rows_new, ldr, nullptr, diag, n_pad, peers, epoch);
+    return schur_update_impl(ctx, stream, G, ldg, c, s, At, ldat, k_pad, rows_new, ldr, nullptr, diag, n_pad, peers, epoch, 0);
 }
 
 extern "C" int rpc_fused_update_supported(const rpc_kernel_spec *spec, int s, int64_t ldx) {

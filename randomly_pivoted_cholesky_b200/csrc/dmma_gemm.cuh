@@ -40,6 +40,11 @@ struct Cfg {
     static_assert(CONSUMERS % 4 == 0, "consumer warps must form whole warpgroups (setmaxnreg, even SMSP load)");
     static constexpr int M_TILE = (WM * MI - (ODD ? 1 : 0)) * 8;
     static constexpr int N_TILE = WN * NI * 8;
+    // Row fragments are dealt to the warp rows round robin: fragment i of warp row wm covers rows (i * WM + wm) * 8 .. + 7.
+    // The panel of the Schur update ends in the transpose of a triangular inverse (zero above the diagonal); with
+    // interleaved rows every warp row owns the same share of the non-zero triangle (contiguous row blocks would leave
+    // the last warp row with three times the work of the first).
+    static constexpr int RSTEP = WM * 8;
     static constexpr int LDA = (M_TILE % 16 == 0) ? M_TILE + 4 : M_TILE + 12;   // == 4 (mod 16)
     static constexpr int LDB = N_TILE + 4;
     static constexpr int A_STAGE = KT * LDA;                                  // doubles
@@ -69,6 +74,10 @@ struct Params {
     int64_t ldr;
     const int32_t *rowmap;   // optional: new row i is row rowmap[i] of R (rows evaluated speculatively for ALL proposals)
     int K;
+    // tri != 0: panel rows kk >= c hold the transpose of a LOWER-triangular s x s matrix (L^{-T}): At[c + i, j] == 0 for
+    // j < i, so output row j only needs the k range kk <= c + j and the DMMAs of the structurally-zero half are skipped.
+    // row_base = panel column (= row of the whole update) of this launch's row 0 (row chunks of updates with s > 256).
+    int tri, row_base;
     double *Cout;
     int64_t ldc;
     double *diag;
@@ -213,7 +222,7 @@ __device__ __forceinline__ void consume_stage_n(double (&acc)[C::MI][C::NI][2], 
         return Bs[j * 8 * ldx + kk];
     };
 #pragma unroll
-    for (int i = 0; i < C::MI; ++i) a[0][i] = i < mi_cnt ? As[lk * C::LDA + i * 8] : 0.0;
+    for (int i = 0; i < C::MI; ++i) a[0][i] = i < mi_cnt ? As[lk * C::LDA + i * C::RSTEP] : 0.0;
 #pragma unroll
     for (int j = 0; j < C::NI; ++j) b[0][j] = ldb(j, lk);
 #pragma unroll
@@ -222,7 +231,7 @@ __device__ __forceinline__ void consume_stage_n(double (&acc)[C::MI][C::NI][2], 
         if (ks + 1 < KT / 4 && ks + 1 < ksteps) {
             const int kk = (ks + 1) * 4 + lk;
 #pragma unroll
-            for (int i = 0; i < C::MI; ++i) a[nxt][i] = i < mi_cnt ? As[kk * C::LDA + i * 8] : 0.0;
+            for (int i = 0; i < C::MI; ++i) a[nxt][i] = i < mi_cnt ? As[kk * C::LDA + i * C::RSTEP] : 0.0;
 #pragma unroll
             for (int j = 0; j < C::NI; ++j) b[nxt][j] = ldb(j, kk);
         }
@@ -245,6 +254,50 @@ __device__ __forceinline__ void consume_stage(double (&acc)[C::MI][C::NI][2], co
     else consume_stage_n<C, BKIND, C::MI>(acc, As, Bs, ldx, lk, ksteps);
 }
 
+// A k-stage inside the triangular block of the Schur panel (k-major B): fragment i (rows r_i .. r_i + 7 of the update) meets
+// non-zero panel entries only in the k4-steps that start at or below panel row c + r_i + 7, i.e. iff i * RSTEP >= lim with
+// lim = rel0 + 4 * ks (rel0 = stage start - c - first row of the warp - 7); the others are skipped, loads included.  The active
+// fragments of a k4-step are a suffix of the warp's fragments; every test is warp uniform.
+template <class C, int CMI>
+__device__ __forceinline__ void consume_stage_tri_n(double (&acc)[C::MI][C::NI][2], const double *As, const double *Bs, int lk,
+                                                    int ksteps, int rel0) {
+    double a[2][C::MI], b[2][C::NI];
+#pragma unroll
+    for (int i = 0; i < CMI; ++i)
+        if (i * C::RSTEP >= rel0) a[0][i] = As[lk * C::LDA + i * C::RSTEP];
+#pragma unroll
+    for (int j = 0; j < C::NI; ++j) b[0][j] = Bs[lk * C::LDB + j * 8];
+#pragma unroll
+    for (int ks = 0; ks < KT / 4; ++ks) {
+        const int cur = ks & 1, nxt = cur ^ 1;
+        if (ks + 1 < KT / 4 && ks + 1 < ksteps) {
+            const int kk = (ks + 1) * 4 + lk;
+            const int lim = rel0 + 4 * (ks + 1);
+#pragma unroll
+            for (int i = 0; i < CMI; ++i)
+                if (i * C::RSTEP >= lim) a[nxt][i] = As[kk * C::LDA + i * C::RSTEP];
+#pragma unroll
+            for (int j = 0; j < C::NI; ++j) b[nxt][j] = Bs[kk * C::LDB + j * 8];
+        }
+        if (ks < ksteps) {
+            const int lim = rel0 + 4 * ks;
+#pragma unroll
+            for (int i = 0; i < CMI; ++i)
+                if (i * C::RSTEP >= lim) {
+#pragma unroll
+                    for (int j = 0; j < C::NI; ++j) dmma884(acc[i][j], a[cur][i], b[cur][j]);
+                }
+        }
+    }
+}
+
+template <class C>
+__device__ __forceinline__ void consume_stage_tri(double (&acc)[C::MI][C::NI][2], const double *As, const double *Bs, int lk,
+                                                  int ksteps, int mi_cnt, int rel0) {
+    if (C::ODD && mi_cnt != C::MI) consume_stage_tri_n<C, (C::ODD ? C::MI - 1 : C::MI)>(acc, As, Bs, lk, ksteps, rel0);
+    else consume_stage_tri_n<C, C::MI>(acc, As, Bs, lk, ksteps, rel0);
+}
+
 // kernel values from the x.y accumulators -> Cout (MODE_EVAL and phase 1 of MODE_FUSED)
 template <class C>
 __device__ __forceinline__ void eval_epilogue(const Params &p, double (&acc)[C::MI][C::NI][2], double *out, int64_t ldo,
@@ -257,7 +310,7 @@ __device__ __forceinline__ void eval_epilogue(const Params &p, double (&acc)[C::
     }
 #pragma unroll
     for (int i = 0; i < C::MI; ++i) {
-        const int row = m0 + i * 8 + lr;
+        const int row = m0 + i * C::RSTEP + lr;
         if (i < mi_cnt && row < p.m_valid) {
             const double pn = p.pnorm[row];
             double *dst = out + (int64_t)row * ldo + col0 + n0 + 2 * lk;
@@ -400,7 +453,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
     const int n0 = wn * C::NI * 8;
     const int lr = lane >> 2, lk = lane & 3;
     const int mi_cnt = (C::ODD && wm == 1) ? C::MI - 1 : C::MI;
-    const int m0 = wm * C::MI * 8;
+    const int m0 = wm * 8;                                   // fragment i: rows m0 + i * RSTEP .. + 7
     const int k_real = (MODE == MODE_EVAL) ? p.d : p.K;
 
     int it = 0;
@@ -449,22 +502,29 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
             if (MODE == MODE_EVAL)
                 consume_stage<C, 1>(acc, As_base + s * C::A_STAGE + m0 + lr, Bs_base + s * C::B_STAGE + (n0 + lr) * LDBK, 0,
                                     lk, live_ksteps(kt, k_real), mi_cnt);
-            else
-                consume_stage<C, 0>(acc, As_base + s * C::A_STAGE + m0 + lr, Bs_base + s * C::B_STAGE + n0 + lr, 0, lk,
-                                    live_ksteps(kt, k_real), mi_cnt);
+            else {
+                // rel0 + 12 > 0: the last k4-step of the stage lies past the diagonal of this warp's first fragment
+                const int rel0 = kt * KT - p.c - p.row_base - rstart - m0 - 7;
+                if (MODE == MODE_SCHUR && p.tri && rel0 + 12 > 0)
+                    consume_stage_tri<C>(acc, As_base + s * C::A_STAGE + m0 + lr, Bs_base + s * C::B_STAGE + n0 + lr, lk,
+                                         live_ksteps(kt, k_real), mi_cnt, rel0);
+                else
+                    consume_stage<C, 0>(acc, As_base + s * C::A_STAGE + m0 + lr, Bs_base + s * C::B_STAGE + n0 + lr, 0, lk,
+                                        live_ksteps(kt, k_real), mi_cnt);
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);         // this warp is done reading the stage
         }
 
-        // C fragment: row = m0 + i*8 + lr, cols = n0 + j*8 + 2*lk + {0,1}
+        // C fragment: row = m0 + i*RSTEP + lr, cols = n0 + j*8 + 2*lk + {0,1}
         if (MODE != MODE_EVAL) {
             double csum[C::NI][2];
 #pragma unroll
             for (int j = 0; j < C::NI; ++j) { csum[j][0] = 0.0; csum[j][1] = 0.0; }
 #pragma unroll
             for (int i = 0; i < C::MI; ++i) {
-                const int row = m0 + i * 8 + lr;
-                const bool live = i < mi_cnt && row < m_valid && row >= first_new;   // fragments >= mi_cnt: next warp row
+                const int row = m0 + i * C::RSTEP + lr;
+                const bool live = i < mi_cnt && row < m_valid && row >= first_new;   // fragments >= mi_cnt do not exist
                 if (live) {
                     double *dst = p.Cout + (int64_t)(rstart + row) * p.ldc + col0 + n0 + 2 * lk;
 #pragma unroll

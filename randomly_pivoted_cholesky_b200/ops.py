@@ -85,7 +85,7 @@ def shifted_cholesky(Cm, shift, device=None):
     return L[:int(ih[0]), :int(ih[0])], int(ih[1])
 
 
-def schur_update(G, c, rows_new, P, L, diag, device=None):
+def schur_update(G, c, rows_new, P, L, diag, device=None, panel_lower=True):
     """One block update on explicit operands (test / bench helper).
 
     G: (k, n_pad) tensor updated in place at rows [c, c+s); rows_new: (s, n_pad); P: (c, s) = G[:c, S];
@@ -103,8 +103,10 @@ def schur_update(G, c, rows_new, P, L, diag, device=None):
     Ld = L.contiguous()
     check(ctx.lib.rpc_build_panel(ctx.handle, _stream(), _ptr(Pd), s, c, None, s, _ptr(Ld), s, 0, _ptr(At), ldat, k_pad),
           "rpc_build_panel")
-    check(ctx.lib.rpc_schur_update(ctx.handle, _stream(), _ptr(G), G.stride(0), c, s, _ptr(At), ldat, k_pad, _ptr(rows_new),
-                                   rows_new.stride(0), _ptr(diag), n_pad), "rpc_schur_update")
+    # the panel of rpc_build_panel mode 0 ends in L^{-T}: the kernel may skip the zero half of that block
+    check(ctx.lib.rpc_schur_update_ex(ctx.handle, _stream(), _ptr(G), G.stride(0), c, s, _ptr(At), ldat, k_pad, _ptr(rows_new),
+                                      rows_new.stride(0), None, _ptr(diag), n_pad, None, 0, 1 if panel_lower else 0),
+          "rpc_schur_update_ex")
     return At
 
 
@@ -136,3 +138,22 @@ def select_largest(diag, b, device=None):
     idx = torch.empty((b,), dtype=torch.int64, device=dev)
     check(ctx.lib.rpc_select_largest(ctx.handle, _stream(), _ptr(d), d.numel(), int(b), _ptr(idx)), "rpc_select_largest")
     return idx
+
+
+def fp64_peak_tflops(device=None, iters=4000, reps=5):
+    """FP64 tensor-pipe (DMMA) peak of this device in TFLOP/s, measured now: best of `reps` launches of the library's pure
+    DMMA stream (rpc_probe_fp64_peak), timed with CUDA events.  ~10 ms per launch at iters = 4000."""
+    dev = _cuda_device(device)
+    ctx = _ctx(dev)
+    fl = C.c_double(0.0)
+    best = float("inf")
+    with torch.cuda.device(dev):
+        for r in range(reps + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            check(ctx.lib.rpc_probe_fp64_peak(ctx.handle, _stream(), int(iters), C.byref(fl)), "rpc_probe_fp64_peak")
+            e1.record()
+            torch.cuda.synchronize(dev)
+            if r > 0:
+                best = min(best, e0.elapsed_time(e1))
+    return fl.value / best / 1e9

@@ -51,9 +51,9 @@ LAST_DATA_PLANE = "single"
 class _timed:
     """CUDA-event bracket around one launch on the current stream (only active under bench.py)."""
 
-    def __init__(self, phase, flops, nbytes):
+    def __init__(self, phase, flops, nbytes, shape=None):
         self.on = KERNEL_TIMERS is not None
-        self.meta = (phase, flops, nbytes)
+        self.meta = (phase, flops, nbytes, shape)
 
     def __enter__(self):
         if self.on:
@@ -353,7 +353,7 @@ class _State:
             # the rows of all proposals were evaluated on the side stream; the accepted ones are read through acc
             torch.cuda.current_stream().wait_event(self.ev_eval)
             A._count(s * self.n)
-            self._schur(c, s, ldat, k_pad, _ptr(self.rows_all), _ptr(self.acc))
+            self._schur(c, s, ldat, k_pad, _ptr(self.rows_all), _ptr(self.acc), panel_mode == 0)
             return
         spec = getattr(A, "_spec", None)
         if USE_FUSED and spec is not None and self.lib.rpc_fused_update_supported(C.byref(spec), s, A.ldx):
@@ -368,20 +368,24 @@ class _State:
         with _timed("eval", 2.0 * s * n * d, 8.0 * n * (s + d)):
             A._dev_rows_into(sel_idx, s, sel_piv, rows_ptr, self.n_pad)
         A._count(s * self.n)
-        self._schur(c, s, ldat, k_pad, rows_ptr, None)
+        self._schur(c, s, ldat, k_pad, rows_ptr, None, panel_mode == 0)
 
-    def _schur(self, c, s, ldat, k_pad, rows_src, rowmap):
+    def _schur(self, c, s, ldat, k_pad, rows_src, rowmap, panel_lower=True):
         """G[c:c+s] = At^T [G[:c]; rows_new], diag update; new row i is rows_src[rowmap[i]] (rowmap None: rows_src[i]).
         Sharded with peer windows: the kernel also stores the new diagonal into every rank's copy and publishes the epoch.
-        Algorithmic work: 2 s (c+s) N flops; reads G[:c] and rows_new, writes G_new."""
+        Algorithmic work: s (2c + s) N flops; reads G[:c] and rows_new, writes G_new."""
         n = self.n_loc
         peers, epoch = None, 0
         if self.peer is not None:
             self.peer.epoch_diag += 1
             peers, epoch = C.byref(self.peer.peers), self.peer.epoch_diag
-        with _timed("schur", 2.0 * s * (c + s) * n, 8.0 * n * (c + 2 * s + 2)):
+        # algorithmic flops (SURVEY.md 8d): Schur product 2 s c N + triangular solve s^2 N; with a dense panel (eigh fallback)
+        # the s x s block is a full product
+        flops = (1.0 * s * (2 * c + s) if panel_lower else 2.0 * s * (c + s)) * n
+        with _timed("schur", flops, 8.0 * n * (c + 2 * s + 2), (c, s, self.n_pad) if panel_lower else None):
             check(self.lib.rpc_schur_update_ex(self.ctx.handle, _stream(), _ptr(self.G), self.n_pad, c, s, _ptr(self.At), ldat,
-                                               k_pad, rows_src, self.n_pad, rowmap, _ptr(self.diag), self.n_pad, peers, epoch),
+                                               k_pad, rows_src, self.n_pad, rowmap, _ptr(self.diag), self.n_pad, peers, epoch,
+                                               1 if panel_lower else 0),
                   "rpc_schur_update_ex")
         self.diag_pending = self.peer is not None
 
@@ -462,9 +466,12 @@ def cholesky_helper(A, k, alg, stoptol=0):
     fast = (not check_every_step) and alg in ("rp", "greedy")
     if fast:
         # no stoptol test and no host-side tie break: the whole loop is enqueued by one native call
-        check(lib.rpc_simple_run(ctx.handle, _stream(), 1 if alg == "greedy" else 0, spec_ref, _ptr(X), _ptr(xn), d, ldx,
-                                 _ptr(Ad), lda, st.n, _ptr(u_all), _ptr(idx_all), _ptr(stats_all), 0, k, _ptr(st.G), st.n_pad,
-                                 _ptr(st.rows), st.n_pad, _ptr(st.diag), st.n_pad), "rpc_simple_run")
+        # algorithmic traffic of the k steps together (per step: stream G[:i], read X, write G[i] and rows[i], diag r/w, and
+        # the sampler's two passes over the diagonal): the bracket covers sampler + step launches of the whole loop
+        with _timed("simple", 2.0 * st.n * (k * (k - 1) / 2 + k * d), 8.0 * st.n * (k * (k - 1) / 2 + k * (d + 7))):
+            check(lib.rpc_simple_run(ctx.handle, _stream(), 1 if alg == "greedy" else 0, spec_ref, _ptr(X), _ptr(xn), d, ldx,
+                                     _ptr(Ad), lda, st.n, _ptr(u_all), _ptr(idx_all), _ptr(stats_all), 0, k, _ptr(st.G), st.n_pad,
+                                     _ptr(st.rows), st.n_pad, _ptr(st.diag), st.n_pad), "rpc_simple_run")
         A._count(k * st.n)
     for i in range(0 if not fast else k, k):
         if alg == "rp":

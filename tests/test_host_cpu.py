@@ -118,5 +118,35 @@ def test_bench_reference_arm_prints_one_json_line():
     lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
-    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    # kind "reference" when oracle/make_ref.py's copy of the unmodified reference is present, else the numpy port
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "rpcholesky.py"))
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["unit"] == "entries/s"
+    assert d["cpu_baseline"]["cores"] == (os.cpu_count() or 1)       # every host core, whatever OMP_NUM_THREADS said
+
+
+def test_reference_copy_is_unmodified_and_agrees_with_the_port():
+    """oracle/_ref (git-ignored, made by oracle/make_ref.py) is a byte-for-byte copy of the reference's modules, and the numpy
+    port reproduces it on replayed draws: the two CPU arms of bench.py measure the same computation."""
+    import hashlib
+    from unittest import mock
+    sys.path.insert(0, ROOT)
+    from oracle import make_ref, rpc_oracle as orc
+    if not os.path.isdir(make_ref.REF_ROOT):
+        pytest.skip("/root/reference is not present here")
+    assert make_ref.make(verbose=False)
+    man = json.load(open(os.path.join(make_ref.DEST, "MANIFEST.json")))
+    for name, digest in man["sha256"].items():
+        assert hashlib.sha256(open(os.path.join(make_ref.DEST, name), "rb").read()).hexdigest() == digest
+        assert open(os.path.join(make_ref.DEST, name), "rb").read() == open(os.path.join(make_ref.REF_ROOT, name), "rb").read()
+    ref = make_ref.load()
+    X = np.random.default_rng(0).standard_normal((3000, 6))
+    A = ref["matrix"].KernelMatrix(X, kernel="gaussian", bandwidth=2.0)
+    np.random.seed(5)
+    with mock.patch("numpy.random.default_rng", lambda *a, **k: np.random.Generator(np.random.PCG64(5))):
+        got = ref["rpcholesky"].accelerated_rpcholesky(A, 150, b=30)
+    rng, legacy = orc.make_streams(5)
+    want = orc.accelerated_rpcholesky(orc.OracleKernelMatrix(X, kernel="gaussian", bandwidth=2.0), 150, 30, rng, legacy)
+    assert np.array_equal(got.idx, want.idx)
+    np.testing.assert_allclose(got.G, want.G, rtol=0, atol=1e-12)
+    assert A.num_queries() == 3000 + 150 * 3000 + 30 * 30 * len(want.rounds)

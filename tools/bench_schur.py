@@ -1,6 +1,8 @@
 #!/usr/bin/env python3
-"""Micro-benchmark of the fused Schur-update DMMA kernel (rpc_schur_update) in isolation.
-usage: python tools/bench_schur.py [N] [c,s c,s ...]   -> one JSON line per shape"""
+"""Micro-benchmark of the fused Schur-update DMMA kernel (rpc_schur_update_ex) in isolation.
+usage: [TRI=0|1] python tools/bench_schur.py [N] [c,s c,s ...]   -> one JSON line per shape
+TRI=1 (default): the kernel skips the structurally-zero half of the panel's L^{-T} block (panel_lower); TRI=0: dense panel.
+`tflops` counts the ALGORITHMIC flops s (2c + s) N in both cases; `dense_tflops` counts 2 s (c + s) N."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -11,6 +13,7 @@ n = (n + 127) // 128 * 128
 shapes = [tuple(int(v) for v in a.split(",")) for a in sys.argv[2:]] or [(1000, 256), (1000, 200), (1000, 192), (1800, 200), (200, 200), (1000, 128), (1000, 64)]
 dev = torch.device("cuda")
 reps = int(os.environ.get("REPS", "3"))
+tri = int(os.environ.get("TRI", "1"))
 for c, s in shapes:
     torch.manual_seed(0)
     G = torch.randn((c + s, n), dtype=torch.float64, device=dev)
@@ -30,11 +33,11 @@ for c, s in shapes:
         ctx = _lib.Context.get(0)
         k_pad = _round_up(c + s, 16)
         e0.record()
-        _lib.check(ctx.lib.rpc_schur_update(ctx.handle, _stream(), _ptr(G), G.stride(0), c, s, _ptr(At), At.stride(0), k_pad,
-                                            _ptr(rows), rows.stride(0), _ptr(diag), n))
+        _lib.check(ctx.lib.rpc_schur_update_ex(ctx.handle, _stream(), _ptr(G), G.stride(0), c, s, _ptr(At), At.stride(0), k_pad,
+                                               _ptr(rows), rows.stride(0), None, _ptr(diag), n, None, 0, tri))
         e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
-    fl = 2.0 * s * (c + s) * n
-    print(json.dumps({"c": c, "s": s, "n": n, "ms": best, "tflops": fl / best / 1e9, "frac_of_36.9": fl / best / 1e9 / 36.9,
-                      "hbm_gbs": 8.0 * n * (c + 2 * s) / best / 1e6}), flush=True)
+    fl = 1.0 * s * (2 * c + s) * n
+    print(json.dumps({"c": c, "s": s, "n": n, "tri": tri, "ms": best, "tflops": fl / best / 1e9, "frac_of_36.9": fl / best / 1e9 / 36.9,
+                      "dense_tflops": 2.0 * s * (c + s) * n / best / 1e9, "hbm_gbs": 8.0 * n * (c + 2 * s) / best / 1e6}), flush=True)
     del G, rows
