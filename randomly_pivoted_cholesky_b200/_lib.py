@@ -16,12 +16,13 @@ import threading
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "librpc_b200.so")
+# RPC_B200_LIB: load another build of the library (A/B measurements of kernel variants; tools/build_variant.py)
+LIB_PATH = os.environ.get("RPC_B200_LIB") or os.path.join(PKG_DIR, "librpc_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false",           # numpy/BLAS op order in the epilogues; FMAs are written explicitly
-    "-shared", "-Xcompiler", "-fPIC",
+    "-shared", "-Xcompiler", "-fPIC", "--threads", "0",
 ]
 
 COL_ALIGN = 128
@@ -57,8 +58,16 @@ def _stale():
     return any(os.path.getmtime(p) > t for p in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile librpc_b200.so for sm_100a with nvcc.  Returns the path of the library."""
+def build(force: bool = False, verbose: bool = False, out: str = None, defines=()) -> str:
+    """Compile librpc_b200.so for sm_100a with nvcc.  Returns the path of the library.  `out` / `defines` build a variant
+    (e.g. defines=("RPC_ROW_INTERLEAVE=0",)) to another path for A/B measurements (RPC_B200_LIB selects it at load time)."""
+    if out is not None:
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", out] + _sources()
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr[-4000:]))
+        return out
     if not force and not _stale():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
@@ -150,6 +159,8 @@ def load():
             # else: a prebuilt library travelled with the tree (file times may be newer than it): use it
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
+            if os.environ.get("RPC_B200_LIB") and not hasattr(lib, name):
+                continue                     # an older variant build under A/B measurement lacks newer entry points
             fn = getattr(lib, name)          # AttributeError if the symbol is missing: fail loudly
             fn.restype = res
             fn.argtypes = args

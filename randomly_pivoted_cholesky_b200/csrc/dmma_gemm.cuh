@@ -20,6 +20,10 @@
 #pragma once
 #include "rpc_common.cuh"
 
+#ifndef RPC_ROW_INTERLEAVE
+#define RPC_ROW_INTERLEAVE 1     // 0: contiguous row blocks per warp row (diagnostic builds only)
+#endif
+
 namespace dg {
 
 constexpr int KT = RPC_KT;      // k-depth per stage
@@ -44,7 +48,8 @@ struct Cfg {
     // The panel of the Schur update ends in the transpose of a triangular inverse (zero above the diagonal); with
     // interleaved rows every warp row owns the same share of the non-zero triangle (contiguous row blocks would leave
     // the last warp row with three times the work of the first).
-    static constexpr int RSTEP = WM * 8;
+    static constexpr int RSTEP = RPC_ROW_INTERLEAVE ? WM * 8 : 8;
+    static constexpr int WARP_ROW0 = RPC_ROW_INTERLEAVE ? 8 : MI * 8;          // first row of warp row wm = wm * WARP_ROW0
     static constexpr int LDA = (M_TILE % 16 == 0) ? M_TILE + 4 : M_TILE + 12;   // == 4 (mod 16)
     static constexpr int LDB = N_TILE + 4;
     static constexpr int A_STAGE = KT * LDA;                                  // doubles
@@ -254,48 +259,56 @@ __device__ __forceinline__ void consume_stage(double (&acc)[C::MI][C::NI][2], co
     else consume_stage_n<C, BKIND, C::MI>(acc, As, Bs, ldx, lk, ksteps);
 }
 
-// A k-stage inside the triangular block of the Schur panel (k-major B): fragment i (rows r_i .. r_i + 7 of the update) meets
-// non-zero panel entries only in the k4-steps that start at or below panel row c + r_i + 7, i.e. iff i * RSTEP >= lim with
-// lim = rel0 + 4 * ks (rel0 = stage start - c - first row of the warp - 7); the others are skipped, loads included.  The active
-// fragments of a k4-step are a suffix of the warp's fragments; every test is warp uniform.
+// A k-stage inside the triangular block of the Schur panel (k-major B).  Fragment i of the warp (rows r_i .. r_i + 7 of the
+// update, r_i = first row of the warp + i * RSTEP) meets non-zero panel entries only in stages that start at or below panel row
+// c + r_i + 7, so the fragments that take part in a stage are a SUFFIX i >= first of the warp's fragments.  ptxas turns a
+// predicated mma.sync into a branch around it, and a branch per DMMA pair stalls the pipe (measured: slower than the dense
+// stage), so the stage is written fragment-major -- per fragment 4 k4-steps x NI DMMAs from the stage's B fragments, the next
+// fragment's A values in flight -- and entered at fragment `first` through ONE switch with fall-through cases: one indirect
+// branch per stage, no code duplication, and inside a fragment every DMMA depends on the one NI instructions earlier only.
+template <class C, int CMI, int I>
+__device__ __forceinline__ void tri_fragment(double (&acc)[C::MI][C::NI][2], double (&a)[2][KT / 4], const double (&b)[KT / 4][C::NI],
+                                             const double *As, int lk) {
+    if (I < CMI) {
+        if (I + 1 < CMI) {
+#pragma unroll
+            for (int ks = 0; ks < KT / 4; ++ks) a[(I + 1) & 1][ks] = As[(ks * 4 + lk) * C::LDA + (I + 1) * C::RSTEP];
+        }
+#pragma unroll
+        for (int ks = 0; ks < KT / 4; ++ks)
+#pragma unroll
+            for (int j = 0; j < C::NI; ++j) dmma884(acc[I < C::MI ? I : 0][j], a[I & 1][ks], b[ks][j]);
+    }
+}
+
 template <class C, int CMI>
 __device__ __forceinline__ void consume_stage_tri_n(double (&acc)[C::MI][C::NI][2], const double *As, const double *Bs, int lk,
-                                                    int ksteps, int rel0) {
-    double a[2][C::MI], b[2][C::NI];
-#pragma unroll
-    for (int i = 0; i < CMI; ++i)
-        if (i * C::RSTEP >= rel0) a[0][i] = As[lk * C::LDA + i * C::RSTEP];
-#pragma unroll
-    for (int j = 0; j < C::NI; ++j) b[0][j] = Bs[lk * C::LDB + j * 8];
+                                                    int first) {
+    static_assert(C::MI <= 16, "the fall-through switch below lists 16 fragments");
+    if (first >= CMI) return;                       // this warp's rows all lie above the stage: nothing to add
+    double a[2][KT / 4], b[KT / 4][C::NI];
 #pragma unroll
     for (int ks = 0; ks < KT / 4; ++ks) {
-        const int cur = ks & 1, nxt = cur ^ 1;
-        if (ks + 1 < KT / 4 && ks + 1 < ksteps) {
-            const int kk = (ks + 1) * 4 + lk;
-            const int lim = rel0 + 4 * (ks + 1);
 #pragma unroll
-            for (int i = 0; i < CMI; ++i)
-                if (i * C::RSTEP >= lim) a[nxt][i] = As[kk * C::LDA + i * C::RSTEP];
-#pragma unroll
-            for (int j = 0; j < C::NI; ++j) b[nxt][j] = Bs[kk * C::LDB + j * 8];
-        }
-        if (ks < ksteps) {
-            const int lim = rel0 + 4 * ks;
-#pragma unroll
-            for (int i = 0; i < CMI; ++i)
-                if (i * C::RSTEP >= lim) {
-#pragma unroll
-                    for (int j = 0; j < C::NI; ++j) dmma884(acc[i][j], a[cur][i], b[cur][j]);
-                }
-        }
+        for (int j = 0; j < C::NI; ++j) b[ks][j] = Bs[(ks * 4 + lk) * C::LDB + j * 8];
+        a[0][ks] = As[(ks * 4 + lk) * C::LDA + first * C::RSTEP];      // the entry fragment's values, in both register sets
+        a[1][ks] = a[0][ks];
     }
+#define RPC_TRI_CASE(I) case I: tri_fragment<C, CMI, I>(acc, a, b, As, lk); [[fallthrough]];
+    switch (first) {
+        RPC_TRI_CASE(0) RPC_TRI_CASE(1) RPC_TRI_CASE(2) RPC_TRI_CASE(3) RPC_TRI_CASE(4) RPC_TRI_CASE(5) RPC_TRI_CASE(6) RPC_TRI_CASE(7)
+        RPC_TRI_CASE(8) RPC_TRI_CASE(9) RPC_TRI_CASE(10) RPC_TRI_CASE(11) RPC_TRI_CASE(12) RPC_TRI_CASE(13) RPC_TRI_CASE(14)
+        RPC_TRI_CASE(15)
+        default: break;
+    }
+#undef RPC_TRI_CASE
 }
 
 template <class C>
 __device__ __forceinline__ void consume_stage_tri(double (&acc)[C::MI][C::NI][2], const double *As, const double *Bs, int lk,
-                                                  int ksteps, int mi_cnt, int rel0) {
-    if (C::ODD && mi_cnt != C::MI) consume_stage_tri_n<C, (C::ODD ? C::MI - 1 : C::MI)>(acc, As, Bs, lk, ksteps, rel0);
-    else consume_stage_tri_n<C, C::MI>(acc, As, Bs, lk, ksteps, rel0);
+                                                  int mi_cnt, int first) {
+    if (C::ODD && mi_cnt != C::MI) consume_stage_tri_n<C, (C::ODD ? C::MI - 1 : C::MI)>(acc, As, Bs, lk, first);
+    else consume_stage_tri_n<C, C::MI>(acc, As, Bs, lk, first);
 }
 
 // kernel values from the x.y accumulators -> Cout (MODE_EVAL and phase 1 of MODE_FUSED)
@@ -453,7 +466,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
     const int n0 = wn * C::NI * 8;
     const int lr = lane >> 2, lk = lane & 3;
     const int mi_cnt = (C::ODD && wm == 1) ? C::MI - 1 : C::MI;
-    const int m0 = wm * 8;                                   // fragment i: rows m0 + i * RSTEP .. + 7
+    const int m0 = wm * C::WARP_ROW0;                        // fragment i: rows m0 + i * RSTEP .. + 7
     const int k_real = (MODE == MODE_EVAL) ? p.d : p.K;
 
     int it = 0;
@@ -503,11 +516,12 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
                 consume_stage<C, 1>(acc, As_base + s * C::A_STAGE + m0 + lr, Bs_base + s * C::B_STAGE + (n0 + lr) * LDBK, 0,
                                     lk, live_ksteps(kt, k_real), mi_cnt);
             else {
-                // rel0 + 12 > 0: the last k4-step of the stage lies past the diagonal of this warp's first fragment
+                // rel0 > 0: the stage starts below the diagonal of this warp's first fragment(s); fragment i is needed iff
+                // i * RSTEP >= rel0 (a stage past K's last real row meets zero panel rows and finite B rows: harmless)
                 const int rel0 = kt * KT - p.c - p.row_base - rstart - m0 - 7;
-                if (MODE == MODE_SCHUR && p.tri && rel0 + 12 > 0)
-                    consume_stage_tri<C>(acc, As_base + s * C::A_STAGE + m0 + lr, Bs_base + s * C::B_STAGE + n0 + lr, lk,
-                                         live_ksteps(kt, k_real), mi_cnt, rel0);
+                if (MODE == MODE_SCHUR && p.tri && rel0 > 0)
+                    consume_stage_tri<C>(acc, As_base + s * C::A_STAGE + m0 + lr, Bs_base + s * C::B_STAGE + n0 + lr, lk, mi_cnt,
+                                         (rel0 + C::RSTEP - 1) / C::RSTEP);
                 else
                     consume_stage<C, 0>(acc, As_base + s * C::A_STAGE + m0 + lr, Bs_base + s * C::B_STAGE + n0 + lr, 0, lk,
                                         live_ksteps(kt, k_real), mi_cnt);

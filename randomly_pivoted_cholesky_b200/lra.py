@@ -105,6 +105,12 @@ class CompactEigenvalueDecomposition(AbstractPSDLowRank):
             return b / lam + self.V @ (np.divide(VTb, diag) - VTb / lam)
         return b / lam + self.V @ (np.divide(VTb, diag[:, np.newaxis]) - VTb / lam)
 
+    def krr_vec(self, b, lam):
+        """lra.py:82-85: (A_hat + lam I)^{-1} b for a block of right-hand sides b of shape (N, m)."""
+        VTb = self.V.T @ b
+        diag = np.asarray(self.Lambda).reshape(VTb.shape[0]) + lam
+        return b / lam + self.V @ (np.divide(VTb, diag[:, np.newaxis]) - VTb / lam)
+
 
 class PSDLowRank(AbstractPSDLowRank):
     """A ~= G^T G with G of shape (k, N): lra.py:87-116."""
@@ -175,3 +181,65 @@ class PSDLowRank(AbstractPSDLowRank):
 
     def get_right_factor(self):
         return self.G
+
+
+class NystromExtension(AbstractPSDLowRank):
+    """A ~= rows^T core^{-1} rows, held as the k x k core and the k x N rows (lra.py:118-171).  Host numpy, off the
+    hot path: the other samplers of the reference (uniform, leverage scores, DPP) return this type through
+    utils.lra_from_sample.  The factor G = L^{-1} rows (L = Cholesky factor of the symmetrised core shifted by
+    trace(core) * eps, lra.py:131-133) is formed lazily on first use."""
+
+    def __init__(self, core, factor=None, interpolation=None, **kwargs):
+        super().__init__(**kwargs)
+        if "rows" not in kwargs:
+            raise RuntimeError("Need to specify rows for Nystrom extension")
+        core = np.asarray(core)
+        self.C = (core + core.T) / 2
+        self.shape = (self.rows.shape[1], self.rows.shape[1])
+        self.L = None
+        self.G = factor
+        self.W = interpolation
+
+    def get_core_factor(self):
+        if self.L is None:
+            k = self.C.shape[0]
+            shift = np.trace(self.C) * np.finfo(float).eps
+            self.L = np.linalg.cholesky(self.C + shift * np.identity(k))
+        return self.L
+
+    def get_factor(self):
+        if self.G is None:
+            self.G = np.linalg.solve(self.get_core_factor(), self.rows)
+        return self.G
+
+    def get_interpolation(self):
+        if self.W is None:
+            # as the reference writes it (lra.py:140-143): L^T against the LEFT factor
+            self.W = np.linalg.solve(self.get_core_factor().T, self.get_left_factor())
+        return self.W
+
+    def get_left_factor(self):
+        return self.get_factor().T
+
+    def get_right_factor(self):
+        return self.get_factor()
+
+    def trace(self):
+        return np.linalg.norm(self.get_factor()) ** 2
+
+    def __matmul__(self, other):
+        return self.get_left_factor() @ (self.get_right_factor() @ other)
+
+    def rank(self):
+        return self.C.shape[0]
+
+    def matrix(self):
+        return self.get_left_factor() @ self.get_right_factor()
+
+    def eigenvalue_decomposition(self):
+        return CompactEigenvalueDecomposition.from_G(self.get_factor(), idx=self.idx, rows=self.rows)
+
+    def scale(self, scaling):
+        scaling = np.asarray(scaling)
+        G = None if self.G is None else self.G * np.sqrt(scaling[np.newaxis, :])
+        return NystromExtension(self.C, idx=self.idx, rows=self.rows * scaling[np.newaxis, :], factor=G, interpolation=self.W)
