@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(256) tail_panel_repack_kernel(const double *__
 }
 
 static bool g_no_tail = getenv("RPC_B200_NO_TAIL") != nullptr;       // diagnostics: keep every column tile in the main launch
+static bool g_no_evalp = getenv("RPC_B200_NO_EVALP") != nullptr;     // diagnostics: evaluator with the panel streamed (MODE_EVALX)
 static bool g_no_tri = getenv("RPC_B200_NO_TRI") != nullptr;         // diagnostics: run the zero half of the triangular block too
 
 static int schur_update_impl(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At, int64_t ldat,
@@ -442,6 +443,17 @@ extern "C" int rpc_kernel_rows(rpc_ctx *ctx, void *stream, const rpc_kernel_spec
     const int k_pad = (d + RPC_KT - 1) / RPC_KT * RPC_KT;
     for (int m0 = 0; m0 < s; m0 += 256) {
         int m = s - m0 < 256 ? s - m0 : 256;
+        // short contractions: the pivot panel stays resident in shared memory and the point tiles stream (csrc/eval_panel.cu)
+        const int ld_res = (ldx % 2 == 0 && !g_no_evalp) ? rpc_eval_panel_ld(m, d, ldx) : 0;
+        if (ld_res > 0) {
+            int rc = rpc_ws_reserve(ctx, (size_t)d * ld_res * sizeof(double));
+            if (rc) return rc;
+            rc = rpc_transpose_pad(ctx, st, Xpiv + (int64_t)m0 * ldp, ldp, m, d, ctx->ws, ld_res, d);
+            if (rc) return rc;
+            rc = rpc_eval_panel_rows(ctx, st, kp, X, xnorm, n_pad, d, ldx, ctx->ws, pnorm + m0, m, out + (int64_t)m0 * ldo, ldo);
+            if (rc) return rc;
+            continue;
+        }
         const int ld = panel_ld_for(m);
         int rc = rpc_ws_reserve(ctx, (size_t)k_pad * ld * sizeof(double));
         if (rc) return rc;

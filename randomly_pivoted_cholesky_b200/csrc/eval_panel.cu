@@ -1,0 +1,355 @@
+// Kernel-row evaluator with the PIVOT PANEL RESIDENT in shared memory (Gaussian / Matern in sklearn's expanded form,
+// kernels.py:32-39, 71-85):   out[s x n_pad] = k(Xpiv, X)   with   D2 = ((-2 Xpiv.X^T) + |xpiv|^2) + |x|^2.
+//
+// dg::gemm_kernel<MODE_EVALX> keeps the X tile resident and streams the panel through the stage ring once per 64-column
+// tile: at d = 50 that is 80 KB of panel copies and 4 barrier round trips per tile for 13 k4-steps of DMMAs (ncu, round 1:
+// 13% of the stall samples sat on the stage barriers, 19% on the global loads of the row norms in the epilogue).  Here the
+// roles are swapped, which is the natural order for a SHORT contraction (K = d):
+//   * the panel Xpiv^T (d x s, leading dimension = the tile's LDA) and the pivot norms are loaded ONCE per persistent CTA;
+//   * the point tiles X[col0 : col0 + N_TILE, :] (one contiguous block: X is point-major) and their norms stream through a
+//     2-3 deep ring of TMA bulk copies issued by a producer warp (full/empty mbarriers per buffer);
+//   * a consumer warp runs its whole k loop without any barrier, releases the buffer, and only then does the epilogue, so
+//     the warps of a CTA drift apart and the DMMA phase of one overlaps the exp phase of another on the shared FP64 pipe.
+// Epilogue (Gaussian): exp(g D2), g = -1/(2 bw^2), evaluated as exp(min(fma(x.y, -2g, g|xpiv|^2 + g|x|^2), 0)) with the
+// 32-entry-table exponential below: 13 FP64-pipe instructions per entry instead of 25 (the DMMAs cost 2d/16 = 6.5 pipe
+// cycles per entry at d = 52, the old epilogue 3.1).  The scaled form differs from the reference's rounding sequence by a
+// few ulp of g(|xpiv|^2 + |x|^2), i.e. ~1e-16 relative in the kernel value (parity bar: 1e-10).
+#include "dmma_gemm.cuh"
+
+using namespace dg;
+
+namespace ep {
+
+struct EvalParams {
+    const double *Pan;      // kp x LDA: Xpiv^T zero padded to the row tile
+    int kp;                 // contraction length (d_pad, a multiple of 4)
+    const double *pnorm;    // [m_valid] squared norms of the pivots
+    int m_valid;
+    const double *X;        // n_pad x ldx points
+    int64_t ldx;
+    const double *xnorm;    // [n_pad]
+    KernParams kparm;
+    double *out;
+    int64_t ldo;
+    int ntiles;             // n_pad / N_TILE
+    int xb;                 // X buffers in the ring (2 or 3)
+};
+
+// 2^(j/32), correctly rounded
+__constant__ double c_exp2_tab[32] = {
+    0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, 0x1.11301d0125b51p+0,
+    0x1.172b83c7d517bp+0, 0x1.1d4873168b9aap+0, 0x1.2387a6e756238p+0, 0x1.29e9df51fdee1p+0,
+    0x1.306fe0a31b715p+0, 0x1.371a7373aa9cbp+0, 0x1.3dea64c123422p+0, 0x1.44e086061892dp+0,
+    0x1.4bfdad5362a27p+0, 0x1.5342b569d4f82p+0, 0x1.5ab07dd485429p+0, 0x1.6247eb03a5585p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.71f75e8ec5f74p+0, 0x1.7a11473eb0187p+0, 0x1.82589994cce13p+0,
+    0x1.8ace5422aa0dbp+0, 0x1.93737b0cdc5e5p+0, 0x1.9c49182a3f090p+0, 0x1.a5503b23e255dp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0,
+    0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0, 0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
+
+// exp(x) for x <= 0, N values at a time (interleaved chains), all 32 lanes of the warp converged.
+//   k = round(32 x / ln2),  x = k ln2/32 + r,  |r| <= ln2/64  (two-term Cody-Waite: k * HI is exact, HI has 36 significant bits)
+//   exp(x) = 2^(k >> 5) * T[k & 31] * (1 + p(r)),  p = expm1 to degree 6 (remainder < 2^-57)
+// T[j] sits in lane j's register and is fetched with a warp shuffle (no shared-memory table, no bank conflicts); the power of
+// two is added to the exponent field on the integer pipe.  Results below 2^-1020 are flushed to zero.  <= 1.2 ulp from the
+// correctly rounded value (4e7 random arguments in [-700, 0], checked on the host: tools/exp_check.c).
+template <int N>
+__device__ __forceinline__ void exp_tab_batch(double (&x)[N], double tab_lane) {
+    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52: the rounded integer lands in the low mantissa bits
+    const double INV = 0x1.71547652b82fep+5;                  // 32 / ln2
+    const double HI = 0x1.62e42fefa0000p-6, LO = 0x1.cf79abc9e3b3ap-45;   // ln2 / 32
+    double r[N], t[N], q[N];
+    int k[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double tm = fma(x[i], INV, MAGIC);
+        k[i] = __double2loint(tm);
+        const double kf = tm - MAGIC;
+        r[i] = fma(kf, -HI, x[i]);
+        r[i] = fma(kf, -LO, r[i]);
+        q[i] = 0x1.6c16c16c16c17p-10;                        // 1/720
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) t[i] = __shfl_sync(0xffffffffu, tab_lane, k[i] & 31);
+    const double cf[4] = {0x1.1111111111111p-7, 0x1.5555555555555p-5, 0x1.5555555555555p-3, 0.5};   // 1/120, 1/24, 1/6, 1/2
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < N; ++i) q[i] = fma(q[i], r[i], cf[c]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double r2 = r[i] * r[i];
+        const double p = fma(q[i], r2, r[i]);
+        const double v = fma(t[i], p, t[i]);
+        const int m = k[i] >> 5;
+        const double sc = __hiloint2double(__double2hiint(v) + (m << 20), __double2loint(v));
+        x[i] = m < -1020 ? 0.0 : sc;
+    }
+}
+
+// one fragment row of a warp: 2 * NI scaled arguments -> kernel values -> NI double2 stores (if the row exists)
+static __device__ __noinline__ void gauss_tab_store8(double *dst, int ok, double tab_lane, double x0, double x1, double x2, double x3,
+                                                     double x4, double x5, double x6, double x7) {
+    double x[8] = {x0, x1, x2, x3, x4, x5, x6, x7};
+    exp_tab_batch<8>(x, tab_lane);
+    if (ok) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<double2 *>(dst + j * 8) = make_double2(x[2 * j], x[2 * j + 1]);
+    }
+}
+static __device__ __noinline__ void gauss_tab_store4(double *dst, int ok, double tab_lane, double x0, double x1, double x2, double x3) {
+    double x[4] = {x0, x1, x2, x3};
+    exp_tab_batch<4>(x, tab_lane);
+    if (ok) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) *reinterpret_cast<double2 *>(dst + j * 8) = make_double2(x[2 * j], x[2 * j + 1]);
+    }
+}
+
+template <class C>
+struct Smem {
+    // doubles: panel | pivot norms | X ring | norm ring | barriers
+    static size_t doubles(int kp, int64_t ldx, int xb) {
+        return (size_t)kp * C::LDA + C::M_TILE + (size_t)xb * (C::N_TILE * ldx + C::N_TILE) + 16;
+    }
+};
+
+// acc += Pan[:, rows of the warp]^T X_tile[cols of the warp, :]^T over the whole contraction; fragments double buffered, two
+// k4-steps per trip, no barrier inside
+template <class C, int CMI>
+__device__ __forceinline__ void k_loop(double (&acc)[C::MI][C::NI][2], const double *Ap, const double *Bp, int ldx, int lk, int nks) {
+    double a0[C::MI], b0[C::NI], a1[C::MI], b1[C::NI];
+    auto load = [&](double (&a)[C::MI], double (&bb)[C::NI], int ks) {
+        const int kk = ks * 4 + lk;
+#pragma unroll
+        for (int i = 0; i < CMI; ++i) a[i] = Ap[kk * C::LDA + i * C::RSTEP];
+#pragma unroll
+        for (int j = 0; j < C::NI; ++j) bb[j] = Bp[j * 8 * ldx + kk];
+    };
+    auto mma = [&](const double (&a)[C::MI], const double (&bb)[C::NI]) {
+#pragma unroll
+        for (int i = 0; i < CMI; ++i)
+#pragma unroll
+            for (int j = 0; j < C::NI; ++j) dmma884(acc[i][j], a[i], bb[j]);
+    };
+    load(a0, b0, 0);
+    int ks = 0;
+    for (; ks + 1 < nks; ks += 2) {
+        load(a1, b1, ks + 1);
+        mma(a0, b0);
+        if (ks + 2 < nks) load(a0, b0, ks + 2);
+        mma(a1, b1);
+    }
+    if (nks & 1) mma(a0, b0);
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, 1) eval_panel_kernel(const EvalParams p) {
+    extern __shared__ __align__(16) double smem[];
+    const int ldx = (int)p.ldx;
+    const int xtile = C::N_TILE * ldx;
+    double *Pan = smem;
+    double *pns = Pan + (size_t)p.kp * C::LDA;
+    double *Xs = pns + C::M_TILE;
+    double *xns = Xs + (size_t)p.xb * xtile;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(xns + p.xb * C::N_TILE);      // [0] panel, [1 + b] full, [1 + xb + b] empty
+    uint64_t *xfull = bars + 1, *xempty = bars + 1 + p.xb;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool gauss = p.kparm.kind == RPC_KERN_GAUSSIAN;
+    const double g = gauss ? p.kparm.gscale : 1.0;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        for (int b = 0; b < p.xb; ++b) {
+            mbar_init(&xfull[b], 1);
+            mbar_init(&xempty[b], C::CONSUMERS);
+        }
+        fence_barrier_init();
+    }
+    for (int r = tid; r < C::M_TILE; r += C::THREADS) pns[r] = r < p.m_valid ? g * p.pnorm[r] : 0.0;
+    __syncthreads();
+
+    if (warp >= C::CONSUMERS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+        if (warp != C::CONSUMERS || lane != 0) return;
+        // ------------------------------- producer: one thread, one or two bulk copies per tile -------------------
+        const unsigned pan_bytes = (unsigned)((size_t)p.kp * C::LDA * 8);
+        mbar_expect_tx(&bars[0], pan_bytes);
+        bulk_g2s(Pan, p.Pan, pan_bytes, &bars[0]);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+            const int b = it % p.xb;
+            mbar_wait(&xempty[b], ((it / p.xb) & 1) ^ 1);             // first lap: returns immediately
+            const int64_t col0 = (int64_t)tile * C::N_TILE;
+            mbar_expect_tx(&xfull[b], (unsigned)((xtile + C::N_TILE) * 8));
+            bulk_g2s(Xs + (size_t)b * xtile, p.X + col0 * p.ldx, (unsigned)(xtile * 8), &xfull[b]);
+            bulk_g2s(xns + b * C::N_TILE, p.xnorm + col0, (unsigned)(C::N_TILE * 8), &xfull[b]);
+        }
+        return;
+    }
+
+    // ----------------------------------- consumer warps ------------------------------------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
+    int wm, wn;
+    if (C::ODD) {
+        const int half = warp >> 2, sp = warp & 3;
+        wm = (sp + half) & 1;
+        wn = (sp >> 1) + 2 * half;
+    } else {
+        wm = warp % C::WM;
+        wn = warp / C::WM;
+    }
+    const int n0 = wn * C::NI * 8;
+    const int lr = lane >> 2, lk = lane & 3;
+    constexpr int CMI_FULL = C::MI;
+    const int mi_cnt = (C::ODD && wm == 1) ? C::MI - 1 : C::MI;
+    const int m0 = wm * C::WARP_ROW0;
+    const int nks = p.kp >> 2;
+    const double tab_lane = c_exp2_tab[lane];
+    const double m2g = -2.0 * g;
+    const double *Ap = Pan + m0 + lr;
+
+    mbar_wait(&bars[0], 0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        const int b = it % p.xb;
+        const int64_t col0 = (int64_t)tile * C::N_TILE;
+        mbar_wait(&xfull[b], (it / p.xb) & 1);
+        const double *Bp = Xs + (size_t)b * xtile + (size_t)(n0 + lr) * ldx;
+
+        double acc[C::MI][C::NI][2];
+#pragma unroll
+        for (int i = 0; i < C::MI; ++i)
+#pragma unroll
+            for (int j = 0; j < C::NI; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+        // k loop over the whole contraction (the fragment count is a compile-time constant of each branch, as in the Schur kernel)
+        if (C::ODD && mi_cnt != C::MI) k_loop<C, (C::ODD ? C::MI - 1 : C::MI)>(acc, Ap, Bp, ldx, lk, nks);
+        else k_loop<C, C::MI>(acc, Ap, Bp, ldx, lk, nks);
+
+        // the tile's (scaled) point norms, then the buffer goes back to the producer
+        double xn[C::NI][2];
+#pragma unroll
+        for (int j = 0; j < C::NI; ++j) {
+            const double2 v = *reinterpret_cast<const double2 *>(xns + b * C::N_TILE + n0 + j * 8 + 2 * lk);
+            xn[j][0] = g * v.x;
+            xn[j][1] = g * v.y;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xempty[b]);
+
+#pragma unroll
+        for (int i = 0; i < CMI_FULL; ++i) {
+            const int rbase = m0 + i * C::RSTEP;
+            if (i < mi_cnt && rbase < p.m_valid) {                       // warp uniform: all lanes take part in the shuffles
+                const int row = rbase + lr;
+                const int ok = row < p.m_valid;
+                const double pn = pns[row];
+                double *dst = p.out + (int64_t)row * p.ldo + col0 + n0 + 2 * lk;
+                if (gauss && (C::NI == 4 || C::NI == 2)) {
+                    double xx[C::NI][2];
+#pragma unroll
+                    for (int j = 0; j < C::NI; ++j)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const double v = fma(acc[i][j][e], m2g, pn + xn[j][e]);      // g * D2
+                            xx[j][e] = v < 0.0 ? v : 0.0;                                 // D2 clamped at 0 (sklearn)
+                        }
+                    if (C::NI == 4)
+                        gauss_tab_store8(dst, ok, tab_lane, xx[0][0], xx[0][1], xx[1][0], xx[1][1], xx[2 % C::NI][0], xx[2 % C::NI][1],
+                                         xx[3 % C::NI][0], xx[3 % C::NI][1]);
+                    else
+                        gauss_tab_store4(dst, ok, tab_lane, xx[0][0], xx[0][1], xx[1][0], xx[1][1]);
+                } else if (ok) {
+#pragma unroll
+                    for (int j = 0; j < C::NI; ++j) {
+                        // sklearn: D2 = ((-2 * X.Y^T) + XX) + YY, clamped at 0
+                        double d0 = (-2.0 * acc[i][j][0] + pn) + xn[j][0], d1 = (-2.0 * acc[i][j][1] + pn) + xn[j][1];
+                        d0 = d0 > 0.0 ? d0 : 0.0;
+                        d1 = d1 > 0.0 ? d1 : 0.0;
+                        *reinterpret_cast<double2 *>(dst + j * 8) = kern_from_d2_pair(p.kparm, d0, d1);
+                    }
+                }
+            }
+        }
+    }
+}
+
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+
+template <class C>
+static int launch(rpc_ctx *ctx, cudaStream_t st, EvalParams p, int64_t n_pad) {
+    static bool configured = false;
+    if (!configured) {
+        RPC_CUDA(cudaFuncSetAttribute(eval_panel_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        configured = true;
+    }
+    p.ntiles = (int)(n_pad / C::N_TILE);
+    p.xb = Smem<C>::doubles(p.kp, p.ldx, 3) * 8 <= SMEM_LIMIT ? 3 : 2;
+    const size_t shm = Smem<C>::doubles(p.kp, p.ldx, p.xb) * 8;
+    const int ctas = rpc_persistent_ctas(ctx);
+    const unsigned grid = (unsigned)(p.ntiles < ctas ? p.ntiles : ctas);
+    eval_panel_kernel<C><<<grid, C::THREADS, shm, st>>>(p);
+    RPC_LAUNCHED(ctx);
+    return 0;
+}
+
+template <class C>
+static bool fits(int kp, int64_t ldx) { return Smem<C>::doubles(kp, ldx, 2) * 8 <= SMEM_LIMIT; }
+
+// the row tiles of the Schur update (csrc/big_kernels.cu): 8-row steps above 128 rows
+#define RPC_EP_FINE(X) X(136, 9, true) X(144, 9, false) X(152, 10, true) X(160, 10, false) X(168, 11, true) X(176, 11, false) \
+    X(184, 12, true) X(192, 12, false) X(200, 13, true) X(208, 13, false) X(216, 14, true) X(224, 14, false) X(232, 15, true)   \
+    X(240, 15, false) X(248, 16, true)
+typedef Cfg<4, 2, 8, 4> E256;
+typedef Cfg<2, 4, 8, 4> E128;
+typedef Cfg<2, 4, 6, 4> E96;
+typedef Cfg<2, 4, 4, 4> E64;
+typedef Cfg<1, 8, 4, 2> E32;
+typedef Cfg<1, 8, 2, 2> E16;
+
+}  // namespace ep
+
+// rows tile for m <= 256 rows of the evaluator (same rule as the Schur update)
+static int ep_tile_rows(int m) {
+    if (m > 128) return m <= 248 ? (m + 7) / 8 * 8 : 256;
+    const int tiles[] = {16, 32, 64, 96, 128};
+    for (int t : tiles) if (m <= t) return t;
+    return 128;
+}
+
+// leading dimension the panel must be built with for m rows, or 0 when the shape does not fit in shared memory
+int rpc_eval_panel_ld(int m, int kp, int64_t ldx) {
+    using namespace ep;
+    switch (ep_tile_rows(m)) {
+#define RPC_EP_LD(M, MI, ODD) case M: return fits<Cfg<2, 4, MI, 2, ODD>>(kp, ldx) ? Cfg<2, 4, MI, 2, ODD>::LDA : 0;
+        RPC_EP_FINE(RPC_EP_LD)
+#undef RPC_EP_LD
+        case 16: return fits<E16>(kp, ldx) ? E16::LDA : 0;
+        case 32: return fits<E32>(kp, ldx) ? E32::LDA : 0;
+        case 64: return fits<E64>(kp, ldx) ? E64::LDA : 0;
+        case 96: return fits<E96>(kp, ldx) ? E96::LDA : 0;
+        case 128: return fits<E128>(kp, ldx) ? E128::LDA : 0;
+        default: return fits<E256>(kp, ldx) ? E256::LDA : 0;
+    }
+}
+
+// out[m x n_pad] = k(Xpiv, X) for m <= 256 pivots whose transposed, zero-padded panel Pan (kp x rpc_eval_panel_ld) is given
+int rpc_eval_panel_rows(rpc_ctx *ctx, cudaStream_t st, const KernParams &kparm, const double *X, const double *xnorm, int64_t n_pad,
+                        int kp, int64_t ldx, const double *Pan, const double *pnorm, int m, double *out, int64_t ldo) {
+    using namespace ep;
+    EvalParams p{};
+    p.Pan = Pan; p.kp = kp; p.pnorm = pnorm; p.m_valid = m; p.X = X; p.ldx = ldx; p.xnorm = xnorm; p.kparm = kparm;
+    p.out = out; p.ldo = ldo;
+    switch (ep_tile_rows(m)) {
+#define RPC_EP_CASE(M, MI, ODD) case M: return launch<Cfg<2, 4, MI, 2, ODD>>(ctx, st, p, n_pad);
+        RPC_EP_FINE(RPC_EP_CASE)
+#undef RPC_EP_CASE
+        case 16: return launch<E16>(ctx, st, p, n_pad);
+        case 32: return launch<E32>(ctx, st, p, n_pad);
+        case 64: return launch<E64>(ctx, st, p, n_pad);
+        case 96: return launch<E96>(ctx, st, p, n_pad);
+        case 128: return launch<E128>(ctx, st, p, n_pad);
+        default: return launch<E256>(ctx, st, p, n_pad);
+    }
+}

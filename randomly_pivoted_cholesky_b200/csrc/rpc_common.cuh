@@ -163,3 +163,8 @@ struct rpc_ctx;
 int rpc_direct_rows_tma(rpc_ctx *ctx, cudaStream_t st, const KernParams &kp, bool l1, const double *X, int64_t ldx, int d,
                         const double *Pt, int ldpt, int s, double *out, int64_t ldo, int64_t n_pad);
 int rpc_direct_pi_for(int s, bool l1);
+// csrc/eval_panel.cu: DMMA evaluator with the pivot panel resident in shared memory (short contractions).
+// rpc_eval_panel_ld: leading dimension to build the transposed panel with for m <= 256 rows, 0 if the shape does not fit.
+int rpc_eval_panel_ld(int m, int kp, int64_t ldx);
+int rpc_eval_panel_rows(rpc_ctx *ctx, cudaStream_t st, const KernParams &kparm, const double *X, const double *xnorm, int64_t n_pad,
+                        int kp, int64_t ldx, const double *Pan, const double *pnorm, int m, double *out, int64_t ldo);

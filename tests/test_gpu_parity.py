@@ -122,8 +122,11 @@ def test_laplace_l1_distance_is_bit_exact(rpc):
 
 
 @pytest.mark.parametrize("d", [3, 20, 50, 130])
-@pytest.mark.parametrize("s", [1, 7, 33, 120, 200, 300])
+@pytest.mark.parametrize("s", [1, 7, 33, 120, 137, 167, 200, 250, 300])
 def test_dmma_evaluator_shapes(rpc, d, s):
+    """Gaussian rows against the oracle over the row tiles of both DMMA evaluators: the panel-resident kernel
+    (csrc/eval_panel.cu: 8-row-step tiles, short contractions) and the streamed one it falls back to (d = 130 with a
+    tall panel does not fit in shared memory)."""
     rng = np.random.default_rng(d * 1000 + s)
     n = 1000 + 37 * s
     X = rng.standard_normal((n, d))
