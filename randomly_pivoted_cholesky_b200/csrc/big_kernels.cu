@@ -11,16 +11,16 @@ constexpr size_t SMEM_LIMIT = 227 * 1024;
 
 template <class C, int MODE>
 static int launch_gemm(rpc_ctx *ctx, cudaStream_t st, const Params &p, int64_t n_pad) {
-    static bool configured = false;
+    static unsigned long long configured = 0;   // one bit per device: function attributes are per device
     size_t shm = (MODE == MODE_FUSED || MODE == MODE_EVALX) ? C::fused_smem_bytes((int)p.ldx) : C::SMEM_BYTES;
     if (shm > SMEM_LIMIT) {
         rpc_set_error("launch_gemm: %zu bytes of shared memory needed, %zu available", shm, SMEM_LIMIT);
         return -4;
     }
-    if (!configured) {
+    if (!rpc_dev_bit(configured, ctx)) {
         RPC_CUDA(cudaFuncSetAttribute(gemm_kernel<C, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (MODE == MODE_FUSED || MODE == MODE_EVALX) ? (int)SMEM_LIMIT : (int)C::SMEM_BYTES));
-        configured = true;
+        configured |= 1ull << (ctx->device & 63);
     }
     // persistent: one CTA per SM walks the column tiles; the producer warp prefetches across tile boundaries
     Params q = p;
@@ -579,10 +579,10 @@ static int simple_step_launch(rpc_ctx *ctx, cudaStream_t st, const rpc_kernel_sp
     int cap = ctx->sm_count * 8;
     if (grid > cap) grid = cap;
     size_t shm = (size_t)(i + (spec ? d : 0) + 1) * sizeof(double);
-    static size_t configured = 48 * 1024;
-    if (shm > configured) {
+    static unsigned long long configured = 0;   // one bit per device: function attributes are per device
+    if (!rpc_dev_bit(configured, ctx)) {
         RPC_CUDA(cudaFuncSetAttribute(simple_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = 200 * 1024;
+        configured |= 1ull << (ctx->device & 63);
     }
     RPC_CHECK_ARG(shm <= 200 * 1024, "rank too large for the fused simple step");
     simple_step_kernel<<<grid, SS_THREADS, shm, st>>>(spec ? 1 : 0, kp, X, xnorm, d, ldx, A, lda, n, idx_dev, i, G, ldg,

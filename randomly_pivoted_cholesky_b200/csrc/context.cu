@@ -5,6 +5,16 @@
 
 static thread_local char g_err[512] = "";
 
+// the library never changes the caller's current device: allocations of a context happen on ITS device under this guard
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 void rpc_set_error(const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -23,7 +33,7 @@ extern "C" int rpc_ctx_create(int device, rpc_ctx **out) {
     int count = 0;
     RPC_CUDA(cudaGetDeviceCount(&count));
     RPC_CHECK_ARG(device >= 0 && device < count, "no such CUDA device");
-    RPC_CUDA(cudaSetDevice(device));
+    DeviceGuard guard(device);
     cudaDeviceProp prop;
     RPC_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) {
@@ -41,7 +51,7 @@ extern "C" int rpc_ctx_create(int device, rpc_ctx **out) {
 
 extern "C" int rpc_ctx_destroy(rpc_ctx *ctx) {
     if (!ctx) return 0;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->flags) cudaFree(ctx->flags);
     if (ctx->sync_counter) cudaFree(ctx->sync_counter);
@@ -61,6 +71,7 @@ extern "C" int64_t rpc_ctx_launch_count(const rpc_ctx *ctx) { return ctx ? ctx->
 // cudaFree synchronises the device, so growing a buffer that in-flight kernels still read is safe.
 int rpc_ws_reserve(rpc_ctx *ctx, size_t bytes) {
     if (bytes <= ctx->ws_bytes) return 0;
+    DeviceGuard guard(ctx->device);
     size_t want = bytes + bytes / 4 + (1 << 20);
     if (ctx->ws) RPC_CUDA(cudaFree(ctx->ws));
     ctx->ws = nullptr;
@@ -72,6 +83,7 @@ int rpc_ws_reserve(rpc_ctx *ctx, size_t bytes) {
 
 int rpc_sync_reserve(rpc_ctx *ctx) {
     if (ctx->sync_counter) return 0;
+    DeviceGuard guard(ctx->device);
     RPC_CUDA(cudaMalloc((void **)&ctx->sync_counter, 16 * sizeof(unsigned int)));
     RPC_CUDA(cudaMemset(ctx->sync_counter, 0, 16 * sizeof(unsigned int)));
     return 0;
@@ -79,6 +91,7 @@ int rpc_sync_reserve(rpc_ctx *ctx) {
 
 int rpc_flags_reserve(rpc_ctx *ctx, size_t bytes) {
     if (bytes <= ctx->flags_bytes) return 0;
+    DeviceGuard guard(ctx->device);
     size_t want = bytes * 2 + 4096;
     if (ctx->flags) RPC_CUDA(cudaFree(ctx->flags));
     ctx->flags = nullptr;

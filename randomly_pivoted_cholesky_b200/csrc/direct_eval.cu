@@ -98,10 +98,10 @@ __global__ void __launch_bounds__(DE_THREADS, 1) direct_rows_tma(const KernParam
 template <bool L1, int PI>
 static int launch_direct(rpc_ctx *ctx, cudaStream_t st, const KernParams &kp, const double *X, int64_t ldx, int d, const double *Pt,
                          int ldpt, int s, double *out, int64_t ldo, int64_t n_pad, size_t shm) {
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;   // one bit per device: function attributes are per device
+    if (!rpc_dev_bit(configured, ctx)) {
         RPC_CUDA(cudaFuncSetAttribute(direct_rows_tma<L1, PI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
+        configured |= 1ull << (ctx->device & 63);
     }
     const int ntiles = (int)(n_pad / DE_TN);
     const int ctas = rpc_persistent_ctas(ctx);

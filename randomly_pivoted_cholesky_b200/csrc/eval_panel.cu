@@ -8,8 +8,9 @@
 //   * the panel Xpiv^T (d x s, leading dimension = the tile's LDA) and the pivot norms are loaded ONCE per persistent CTA;
 //   * the point tiles X[col0 : col0 + N_TILE, :] (one contiguous block: X is point-major) and their norms stream through a
 //     2-3 deep ring of TMA bulk copies issued by a producer warp (full/empty mbarriers per buffer);
-//   * a consumer warp runs its whole k loop without any barrier, releases the buffer, and only then does the epilogue, so
-//     the warps of a CTA drift apart and the DMMA phase of one overlaps the exp phase of another on the shared FP64 pipe.
+//   * a consumer warp runs its whole k loop without any barrier, releases the buffer, and only then does the epilogue.
+//     (Tried: starting the second warp of every SM sub-partition one k loop late so that one warp's DMMAs overlap the other's
+//     epilogue on the shared FP64 pipe -- no gain, 0.834 vs 0.817 ms at s = 167: the eight-chain epilogue is pipe bound itself.)
 // Epilogue (Gaussian): exp(g D2), g = -1/(2 bw^2), evaluated as exp(min(fma(x.y, -2g, g|xpiv|^2 + g|x|^2), 0)) with the
 // 32-entry-table exponential below: 13 FP64-pipe instructions per entry instead of 25 (the DMMAs cost 2d/16 = 6.5 pipe
 // cycles per entry at d = 52, the old epilogue 3.1).  The scaled form differs from the reference's rounding sequence by a
@@ -86,22 +87,33 @@ __device__ __forceinline__ void exp_tab_batch(double (&x)[N], double tab_lane) {
     }
 }
 
-// one fragment row of a warp: 2 * NI scaled arguments -> kernel values -> NI double2 stores (if the row exists)
-static __device__ __noinline__ void gauss_tab_store8(double *dst, int ok, double tab_lane, double x0, double x1, double x2, double x3,
-                                                     double x4, double x5, double x6, double x7) {
+// Eight scaled arguments g * D2 (not yet clamped) -> kernel values -> two groups of two double2 stores: either two fragment
+// rows of an NI = 2 tile (dstA, dstB) or the two halves of one row of an NI = 4 tile (dstB = dstA + 16).  Eight interleaved
+// chains per call: with four the dependent FP64 chain (about 12 instructions of ~8 cycles) was latency bound (ncu: 440 cycles
+// per call for 112 cycles of FP64 pipe).  Out of line: inlined at every fragment row the epilogue outgrows the instruction cache.
+static __device__ __noinline__ void gauss_tab_store8(double *dstA, int okA, double *dstB, int okB, double tab_lane, double x0, double x1,
+                                                     double x2, double x3, double x4, double x5, double x6, double x7) {
     double x[8] = {x0, x1, x2, x3, x4, x5, x6, x7};
-    exp_tab_batch<8>(x, tab_lane);
-    if (ok) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) *reinterpret_cast<double2 *>(dst + j * 8) = make_double2(x[2 * j], x[2 * j + 1]);
+    for (int i = 0; i < 8; ++i) x[i] = x[i] < 0.0 ? x[i] : 0.0;          // D2 clamped at 0 (sklearn), in the scaled domain
+    exp_tab_batch<8>(x, tab_lane);
+    if (okA) {
+        *reinterpret_cast<double2 *>(dstA) = make_double2(x[0], x[1]);
+        *reinterpret_cast<double2 *>(dstA + 8) = make_double2(x[2], x[3]);
+    }
+    if (okB) {
+        *reinterpret_cast<double2 *>(dstB) = make_double2(x[4], x[5]);
+        *reinterpret_cast<double2 *>(dstB + 8) = make_double2(x[6], x[7]);
     }
 }
 static __device__ __noinline__ void gauss_tab_store4(double *dst, int ok, double tab_lane, double x0, double x1, double x2, double x3) {
     double x[4] = {x0, x1, x2, x3};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = x[i] < 0.0 ? x[i] : 0.0;
     exp_tab_batch<4>(x, tab_lane);
     if (ok) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) *reinterpret_cast<double2 *>(dst + j * 8) = make_double2(x[2 * j], x[2 * j + 1]);
+        *reinterpret_cast<double2 *>(dst) = make_double2(x[0], x[1]);
+        *reinterpret_cast<double2 *>(dst + 8) = make_double2(x[2], x[3]);
     }
 }
 
@@ -142,7 +154,7 @@ __device__ __forceinline__ void k_loop(double (&acc)[C::MI][C::NI][2], const dou
     if (nks & 1) mma(a0, b0);
 }
 
-template <class C>
+template <class C, bool GAUSS>
 __global__ void __launch_bounds__(C::THREADS, 1) eval_panel_kernel(const EvalParams p) {
     extern __shared__ __align__(16) double smem[];
     const int ldx = (int)p.ldx;
@@ -155,8 +167,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) eval_panel_kernel(const EvalPar
     uint64_t *xfull = bars + 1, *xempty = bars + 1 + p.xb;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool gauss = p.kparm.kind == RPC_KERN_GAUSSIAN;
-    const double g = gauss ? p.kparm.gscale : 1.0;
+    const double g = GAUSS ? p.kparm.gscale : 1.0;
 
     if (tid == 0) {
         mbar_init(&bars[0], 1);
@@ -238,36 +249,54 @@ __global__ void __launch_bounds__(C::THREADS, 1) eval_panel_kernel(const EvalPar
         __syncwarp();
         if (lane == 0) mbar_arrive(&xempty[b]);
 
+        double *out0 = p.out + col0 + n0 + 2 * lk;
+        if (GAUSS && C::NI == 2) {
+            // two fragment rows (8 values) per call
 #pragma unroll
-        for (int i = 0; i < CMI_FULL; ++i) {
-            const int rbase = m0 + i * C::RSTEP;
-            if (i < mi_cnt && rbase < p.m_valid) {                       // warp uniform: all lanes take part in the shuffles
-                const int row = rbase + lr;
-                const int ok = row < p.m_valid;
-                const double pn = pns[row];
-                double *dst = p.out + (int64_t)row * p.ldo + col0 + n0 + 2 * lk;
-                if (gauss && (C::NI == 4 || C::NI == 2)) {
-                    double xx[C::NI][2];
+            for (int i = 0; i < C::MI; i += 2) {
+                const int rA = m0 + i * C::RSTEP, rB = rA + C::RSTEP;
+                if (i < mi_cnt && rA < p.m_valid) {                         // warp uniform: all lanes take part in the shuffles
+                    const int rowA = rA + lr, rowB = rB + lr;
+                    const double pnA = pns[rowA];
+                    if (i + 1 < C::MI && i + 1 < mi_cnt) {
+                        const double pnB = pns[rowB];
+                        const int i1 = i + 1 < C::MI ? i + 1 : i;
+                        gauss_tab_store8(out0 + (int64_t)rowA * p.ldo, rowA < p.m_valid, out0 + (int64_t)rowB * p.ldo, rowB < p.m_valid,
+                                         tab_lane, fma(acc[i][0][0], m2g, pnA + xn[0][0]), fma(acc[i][0][1], m2g, pnA + xn[0][1]),
+                                         fma(acc[i][1][0], m2g, pnA + xn[1][0]), fma(acc[i][1][1], m2g, pnA + xn[1][1]),
+                                         fma(acc[i1][0][0], m2g, pnB + xn[0][0]), fma(acc[i1][0][1], m2g, pnB + xn[0][1]),
+                                         fma(acc[i1][1][0], m2g, pnB + xn[1][0]), fma(acc[i1][1][1], m2g, pnB + xn[1][1]));
+                    } else {
+                        gauss_tab_store4(out0 + (int64_t)rowA * p.ldo, rowA < p.m_valid, tab_lane, fma(acc[i][0][0], m2g, pnA + xn[0][0]),
+                                         fma(acc[i][0][1], m2g, pnA + xn[0][1]), fma(acc[i][1][0], m2g, pnA + xn[1][0]),
+                                         fma(acc[i][1][1], m2g, pnA + xn[1][1]));
+                    }
+                }
+            }
+        } else {
 #pragma unroll
-                    for (int j = 0; j < C::NI; ++j)
+            for (int i = 0; i < C::MI; ++i) {
+                const int rbase = m0 + i * C::RSTEP;
+                if (i < mi_cnt && rbase < p.m_valid) {
+                    const int row = rbase + lr;
+                    const int ok = row < p.m_valid;
+                    const double pn = pns[row];
+                    double *dst = out0 + (int64_t)row * p.ldo;
+                    if (GAUSS) {                                            // NI == 4: one row = 8 values
+                        gauss_tab_store8(dst, ok, dst + 16, ok, tab_lane, fma(acc[i][0][0], m2g, pn + xn[0][0]),
+                                         fma(acc[i][0][1], m2g, pn + xn[0][1]), fma(acc[i][1 % C::NI][0], m2g, pn + xn[1 % C::NI][0]),
+                                         fma(acc[i][1 % C::NI][1], m2g, pn + xn[1 % C::NI][1]), fma(acc[i][2 % C::NI][0], m2g, pn + xn[2 % C::NI][0]),
+                                         fma(acc[i][2 % C::NI][1], m2g, pn + xn[2 % C::NI][1]), fma(acc[i][3 % C::NI][0], m2g, pn + xn[3 % C::NI][0]),
+                                         fma(acc[i][3 % C::NI][1], m2g, pn + xn[3 % C::NI][1]));
+                    } else if (ok) {
 #pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const double v = fma(acc[i][j][e], m2g, pn + xn[j][e]);      // g * D2
-                            xx[j][e] = v < 0.0 ? v : 0.0;                                 // D2 clamped at 0 (sklearn)
+                        for (int j = 0; j < C::NI; ++j) {
+                            // sklearn: D2 = ((-2 * X.Y^T) + XX) + YY, clamped at 0
+                            double d0 = (-2.0 * acc[i][j][0] + pn) + xn[j][0], d1 = (-2.0 * acc[i][j][1] + pn) + xn[j][1];
+                            d0 = d0 > 0.0 ? d0 : 0.0;
+                            d1 = d1 > 0.0 ? d1 : 0.0;
+                            *reinterpret_cast<double2 *>(dst + j * 8) = kern_from_d2_pair(p.kparm, d0, d1);
                         }
-                    if (C::NI == 4)
-                        gauss_tab_store8(dst, ok, tab_lane, xx[0][0], xx[0][1], xx[1][0], xx[1][1], xx[2 % C::NI][0], xx[2 % C::NI][1],
-                                         xx[3 % C::NI][0], xx[3 % C::NI][1]);
-                    else
-                        gauss_tab_store4(dst, ok, tab_lane, xx[0][0], xx[0][1], xx[1][0], xx[1][1]);
-                } else if (ok) {
-#pragma unroll
-                    for (int j = 0; j < C::NI; ++j) {
-                        // sklearn: D2 = ((-2 * X.Y^T) + XX) + YY, clamped at 0
-                        double d0 = (-2.0 * acc[i][j][0] + pn) + xn[j][0], d1 = (-2.0 * acc[i][j][1] + pn) + xn[j][1];
-                        d0 = d0 > 0.0 ? d0 : 0.0;
-                        d1 = d1 > 0.0 ? d1 : 0.0;
-                        *reinterpret_cast<double2 *>(dst + j * 8) = kern_from_d2_pair(p.kparm, d0, d1);
                     }
                 }
             }
@@ -279,17 +308,19 @@ constexpr size_t SMEM_LIMIT = 227 * 1024;
 
 template <class C>
 static int launch(rpc_ctx *ctx, cudaStream_t st, EvalParams p, int64_t n_pad) {
-    static bool configured = false;
-    if (!configured) {
-        RPC_CUDA(cudaFuncSetAttribute(eval_panel_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
-        configured = true;
+    static unsigned long long configured = 0;   // one bit per device: function attributes are per device
+    if (!rpc_dev_bit(configured, ctx)) {
+        RPC_CUDA(cudaFuncSetAttribute(eval_panel_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        RPC_CUDA(cudaFuncSetAttribute(eval_panel_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        configured |= 1ull << (ctx->device & 63);
     }
     p.ntiles = (int)(n_pad / C::N_TILE);
     p.xb = Smem<C>::doubles(p.kp, p.ldx, 3) * 8 <= SMEM_LIMIT ? 3 : 2;
     const size_t shm = Smem<C>::doubles(p.kp, p.ldx, p.xb) * 8;
     const int ctas = rpc_persistent_ctas(ctx);
     const unsigned grid = (unsigned)(p.ntiles < ctas ? p.ntiles : ctas);
-    eval_panel_kernel<C><<<grid, C::THREADS, shm, st>>>(p);
+    if (p.kparm.kind == RPC_KERN_GAUSSIAN) eval_panel_kernel<C, true><<<grid, C::THREADS, shm, st>>>(p);
+    else eval_panel_kernel<C, false><<<grid, C::THREADS, shm, st>>>(p);
     RPC_LAUNCHED(ctx);
     return 0;
 }

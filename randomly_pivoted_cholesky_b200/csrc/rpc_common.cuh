@@ -24,6 +24,10 @@ static inline int rpc_persistent_ctas(const rpc_ctx *ctx) {
     return n < 1 ? 1 : n;
 }
 
+// "was this function configured on the context's device?" for the per-function static bit masks that guard
+// cudaFuncSetAttribute (a per-device setting: a second GPU in the same process needs its own opt-in)
+static inline bool rpc_dev_bit(unsigned long long mask, const rpc_ctx *ctx) { return (mask >> (ctx->device & 63)) & 1ull; }
+
 void rpc_set_error(const char *fmt, ...);
 int rpc_ws_reserve(rpc_ctx *ctx, size_t bytes);
 int rpc_flags_reserve(rpc_ctx *ctx, size_t bytes);
@@ -53,7 +57,7 @@ int rpc_transpose_pad(rpc_ctx *ctx, cudaStream_t st, const double *in, int64_t l
 #define RPC_LAUNCHED(ctx)                                                                       \
     do {                                                                                        \
         (ctx)->launches++;                                                                      \
-        cudaError_t e_ = cudaPeekAtLastError();                                                 \
+        cudaError_t e_ = cudaGetLastError();                                                    \
         if (e_ != cudaSuccess) {                                                                \
             rpc_set_error("%s: kernel launch failed: %s", __func__, cudaGetErrorString(e_));    \
             return (int)e_;                                                                     \

@@ -471,12 +471,12 @@ extern "C" int rpc_sample_pivots(rpc_ctx *ctx, void *stream, const double *diag,
     double *csum = ctx->ws, *D = csum + (nch + 2), *cA = D + (nch + 2), *cB = cA + (nch + 2);
     double *tile_tot = cB + (nch + 2), *tile_carry = tile_tot + (ntile + 2);
     int32_t *cls = ctx->flags, *bad = ctx->flags + nch, *tile_e = ctx->flags + nch + 8;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;   // one bit per device: function attributes are per device
+    if (!rpc_dev_bit(configured, ctx)) {
         RPC_CUDA(cudaFuncSetAttribute(sc_walk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SLOTS * SC_CH * 8));
         RPC_CUDA(cudaFuncSetAttribute(sc_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SLOTS * SC_CH * 8));
         RPC_CUDA(cudaFuncSetAttribute(sc_fused_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SLOTS * SC_CH * 8));
-        configured = true;
+        configured |= 1ull << (ctx->device & 63);
     }
     const double delta = ((double)n_pad + 256.0) * 1.1102230246251565e-16 * 1.01;
     if (n_pad <= SC_FUSED_MAX) {

@@ -493,13 +493,13 @@ extern "C" int rpc_rejection_cholesky(rpc_ctx *ctx, void *stream, double *H, int
     cudaStream_t st = (cudaStream_t)stream;
     int rc = rpc_ws_reserve(ctx, (size_t)m * m * sizeof(double));
     if (rc) return rc;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;   // one bit per device: function attributes are per device
+    if (!rpc_dev_bit(configured, ctx)) {
         RPC_CUDA(cudaFuncSetAttribute(rejection_cholesky_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       220 * 1024));
         RPC_CUDA(cudaFuncSetAttribute(rejection_cholesky_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       220 * 1024));
-        configured = true;
+        configured |= 1ull << (ctx->device & 63);
     }
     // thr[m] | Lb[RB][m] | accpos[m] + blk ints | (packed lower triangle)
     const size_t head = ((size_t)m + RB * m + (m + 16) / 2 + 8 + RB) * sizeof(double);
@@ -688,11 +688,11 @@ static int launch_panel_trsm(rpc_ctx *ctx, cudaStream_t st, const double *P, int
     // s is the row count, or its upper bound when the count is read on the device (s_dev)
     size_t shm = ((size_t)TS_WARPS * TS_RW * s + s) * sizeof(double);
     size_t shm_l = shm + (size_t)s * (s + 1) / 2 * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;   // one bit per device: function attributes are per device
+    if (!rpc_dev_bit(configured, ctx)) {
         RPC_CUDA(cudaFuncSetAttribute(panel_trsm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         RPC_CUDA(cudaFuncSetAttribute(panel_trsm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
+        configured |= 1ull << (ctx->device & 63);
     }
     int rows_per_cta = TS_WARPS * TS_RW;
     int blocks = (k_pad + rows_per_cta - 1) / rows_per_cta;
@@ -1009,10 +1009,10 @@ extern "C" int rpc_pivoted_cholesky(rpc_ctx *ctx, void *stream, const double *H,
     int rc = rpc_ws_reserve(ctx, (size_t)m * m * sizeof(double));
     if (rc) return rc;
     const size_t shm = (size_t)m * (4 * sizeof(double) + 2 * sizeof(int32_t));
-    static size_t configured = 48 * 1024;
-    if (shm > configured) {
+    static unsigned long long configured = 0;   // one bit per device: function attributes are per device
+    if (!rpc_dev_bit(configured, ctx)) {
         RPC_CUDA(cudaFuncSetAttribute(pivoted_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = 200 * 1024;
+        configured |= 1ull << (ctx->device & 63);
     }
     pivoted_cholesky_kernel<<<1, PC_THREADS, shm, st>>>(H, m, ldh, use_tol, rtol, atol, ctx->ws, L, ldl, acc, info);
     RPC_LAUNCHED(ctx);

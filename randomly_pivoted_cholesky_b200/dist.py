@@ -164,6 +164,7 @@ class PeerWindow:
             w = cls._cache[key]
             if w is None or w.payload_len >= payload_len:
                 return w
+            w.close()                                  # too small: unmap and free it before a larger one is made
         try:
             # the payload is sized generously so that one window serves every factorisation of this operator
             w = cls(info, ctx, device, max(payload_len, 1 << 20))
@@ -231,6 +232,16 @@ class PeerWindow:
         self.epoch_payload = 0
         dist.barrier(group=info.group)            # every rank has mapped every window before anyone stores into one
 
-    def check_status(self):
-        if int(self.status.item()) != 0:
-            raise RuntimeError("peer-memory exchange timed out waiting for another rank's epoch")
+    def close(self):
+        """Unmap the peers' windows and free this rank's (collective: every rank closes its mappings before any window is
+        freed).  The torch views of the window must not be used afterwards."""
+        import ctypes as C
+        torch.cuda.synchronize(self.device)
+        for q in self._opened:
+            self.ctx.lib.rpc_peer_close(self.ctx.handle, C.c_void_p(q))
+        self._opened = []
+        dist.barrier(group=self.info.group)
+        if self.base:
+            self.ctx.lib.rpc_peer_free(self.ctx.handle, C.c_void_p(self.base))
+            self.base = 0
+        self.diag_full = self.payload = None

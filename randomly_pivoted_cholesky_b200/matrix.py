@@ -35,6 +35,17 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+def _normalise_indices(vec, n):
+    """numpy fancy-index semantics for a list of point indices (the reference evaluates `self.data[vec, :]`, matrix.py:189):
+    negative indices wrap, anything outside [-n, n) raises IndexError.  The device gather itself treats an index outside the
+    owned range as "not mine" (it writes zeros), so the check has to happen here."""
+    arr = np.asarray(vec, dtype=np.int64).ravel()
+    bad = (arr < -n) | (arr >= n)
+    if bad.any():
+        raise IndexError("index {} is out of bounds for axis 0 with size {}".format(int(arr[bad][0]), n))
+    return np.where(arr < 0, arr + n, arr)
+
+
 def _cuda_device(device=None):
     if not torch.cuda.is_available():
         raise RuntimeError("randomly_pivoted_cholesky_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
@@ -263,8 +274,9 @@ class KernelMatrix(AbstractPSDMatrix):
         Xp[:info.n_loc, :d] = Xd
         self._Xd = Xp
         self._xnorm = torch.zeros((self.n_pad,), dtype=torch.float64, device=dev)
-        check(self._ctx.lib.rpc_row_norms(self._ctx.handle, _stream(), _ptr(Xp), self.n_pad, self.d_pad, self.ldx,
-                                          _ptr(self._xnorm)), "rpc_row_norms")
+        with torch.cuda.device(dev):
+            check(self._ctx.lib.rpc_row_norms(self._ctx.handle, _stream(), _ptr(Xp), self.n_pad, self.d_pad, self.ldx,
+                                              _ptr(self._xnorm)), "rpc_row_norms")
 
         if isinstance(bandwidth, str):
             if info.world > 1:
@@ -311,24 +323,27 @@ class KernelMatrix(AbstractPSDMatrix):
         tgt = self if other is None else other
         n = tgt.shape[0]
         mi, mj = len(vec_i), len(vec_j)
-        ti = torch.as_tensor(np.asarray(vec_i, dtype=np.int64), device=self.device)
+        vec_i = _normalise_indices(vec_i, self.shape[0])
+        ti = torch.as_tensor(vec_i, device=self.device)
         piv = _PivotPayload(mi, self.ldx, self.device)
-        self._dev_gather(ti, mi, piv)
-        full = (mj == n) and (vec_j == list(range(n)) if mj < 4096 else
-                              bool(np.array_equal(np.asarray(vec_j, dtype=np.int64), np.arange(n))))
+        with torch.cuda.device(self.device):
+            self._dev_gather(ti, mi, piv)
+        vec_j = _normalise_indices(vec_j, n)
+        full = (mj == n) and bool(np.array_equal(vec_j, np.arange(n)))
         if full:
             Y, ynorm, npad = tgt._Xd, tgt._xnorm, tgt.n_pad
         else:
-            tj = torch.as_tensor(np.asarray(vec_j, dtype=np.int64), device=self.device)
+            tj = torch.as_tensor(vec_j, device=self.device)
             npad = _round_up(mj, COL_ALIGN)
             Y = torch.zeros((npad, self.ldx), dtype=torch.float64, device=self.device)
             Y[:mj] = tgt._Xd[tj]
             ynorm = torch.zeros((npad,), dtype=torch.float64, device=self.device)
             ynorm[:mj] = tgt._xnorm[tj]
         out = torch.empty((mi, npad), dtype=torch.float64, device=self.device)
-        check(self._ctx.lib.rpc_kernel_rows(self._ctx.handle, _stream(), C.byref(self._spec), _ptr(Y), _ptr(ynorm), npad,
-                                            self.d_pad, self.ldx, _ptr(piv.X), _ptr(piv.norm), mi, self.ldx,
-                                            _ptr(out), npad), "rpc_kernel_rows")
+        with torch.cuda.device(self.device):
+            check(self._ctx.lib.rpc_kernel_rows(self._ctx.handle, _stream(), C.byref(self._spec), _ptr(Y), _ptr(ynorm), npad,
+                                                self.d_pad, self.ldx, _ptr(piv.X), _ptr(piv.norm), mi, self.ldx,
+                                                _ptr(out), npad), "rpc_kernel_rows")
         return out[:, :mj].cpu().numpy()
 
     def _getitem_helper(self, *args):                # matrix.py:129-138

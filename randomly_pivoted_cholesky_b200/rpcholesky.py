@@ -41,6 +41,8 @@ USE_PEER = _os.environ.get("RPC_B200_PEER", "1") != "0"
 # through a row map.  Worth it once the evaluation is short compared with the serial chain, i.e. when sharded:
 # RPC_B200_SPEC = "auto" (sharded only) | "1" (always) | "0" (never)
 USE_SPEC = _os.environ.get("RPC_B200_SPEC", "auto")
+# how long a rank waits for another rank's epoch before the factorisation is aborted (0 = the library default, 20 s)
+PEER_TIMEOUT_MS = int(_os.environ.get("RPC_B200_PEER_TIMEOUT_MS", "0"))
 
 # bench.py sets this to a list to collect (start_event, end_event, flops, bytes, phase) per timed launch
 KERNEL_TIMERS = None
@@ -65,6 +67,19 @@ class _timed:
         if self.on:
             self.e1.record()
             KERNEL_TIMERS.append((self.e0, self.e1) + self.meta)
+
+
+def _on_operator_device(fn):
+    """Run a driver with the operator's device current: streams, workspace allocations and launches of the C ABI all refer
+    to the current device, which need not be the one the operator lives on."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(A, *args, **kwargs):
+        A = _as_operator(A)
+        with torch.cuda.device(A.device):
+            return fn(A, *args, **kwargs)
+    return wrapped
 
 
 def _as_operator(A):
@@ -111,7 +126,8 @@ class _State:
         payload_len = nx + (m_max if self.ldx else 0) + max(k, 1) * m_max
         self.peer = None
         self.diag_pending = False              # True: the last Schur update published the new diagonal into diag_full
-        if self.info.world > 1 and USE_PEER and not USE_FUSED and self.dev.type == "cuda" and self.ldx:
+        if (self.info.world > 1 and self.info.world <= _lib.MAX_PEERS and USE_PEER and not USE_FUSED and self.dev.type == "cuda"
+                and self.ldx):
             self.peer = rdist.PeerWindow.get(self.info, self.ctx, self.dev, payload_len)     # None: no peer access here
         global LAST_DATA_PLANE
         LAST_DATA_PLANE = "single" if self.info.world == 1 else ("peer" if self.peer is not None else "nccl")
@@ -160,7 +176,9 @@ class _State:
             self.rb_seq = 0
         self.rb_seq += 1
         seq = float(self.rb_seq)
-        check(self.lib.rpc_publish_round(self.ctx.handle, _stream(), _ptr(self.stats), _ptr(self.info_dev) if with_chol else None,
+        # a timed-out peer wait sets info_dev[3] (sticky): with peer windows the status word travels with every round
+        check(self.lib.rpc_publish_round(self.ctx.handle, _stream(), _ptr(self.stats),
+                                         _ptr(self.info_dev) if (with_chol or self.peer is not None) else None,
                                          _ptr(self.acc) if with_chol else None, _ptr(self.idx_dev), m,
                                          C.c_void_p(self.rb_host.data_ptr()), seq), "rpc_publish_round")
 
@@ -178,6 +196,8 @@ class _State:
                     if buf[0] != seq:
                         raise RuntimeError("read-back kernel did not publish its result")
         out = buf[1:need].copy()
+        if self.peer is not None and out[7] != 0:
+            raise RuntimeError("peer-memory exchange timed out waiting for another rank's epoch (this round's pivots are invalid)")
         return out[0:4], out[4:8].astype(np.int64), out[8:8 + m].astype(np.int64), out[8 + m:8 + 2 * m].astype(np.int64)
 
     # ---- thin wrappers over the C ABI ------------------------------------------------------------
@@ -211,7 +231,7 @@ class _State:
         if self.peer is not None and self.diag_pending:
             # every rank's Schur kernel stored its block of the new diagonal here and published the epoch
             check(self.lib.rpc_peer_wait(self.ctx.handle, _stream(), C.c_void_p(self.peer.flags_ptr), self.info.world,
-                                         self.peer.epoch_diag, 0, _ptr(self.peer.status)), "rpc_peer_wait")
+                                         self.peer.epoch_diag, PEER_TIMEOUT_MS, self._peer_status()), "rpc_peer_wait")
             self.diag_pending = False
             full = self.diag_full
         else:
@@ -219,6 +239,10 @@ class _State:
         u = C.c_void_p(self.u_dev.data_ptr() + 8 * u_off)
         check(self.lib.rpc_sample_pivots(self.ctx.handle, _stream(), _ptr(full), full.numel(), u, m, _ptr(self.idx_dev),
                                          _ptr(self.stats)), "rpc_sample_pivots")
+
+    def _peer_status(self):
+        """Status word of the peer waits: info_dev[3], published to the host with every round's read-back."""
+        return C.c_void_p(self.info_dev.data_ptr() + 12)
 
     def gather(self, idx_dev, m, c):
         """payload <- [X[idx] | |x|^2 | G[:c, idx]]; owners write, the others write zeros, then one sum all-reduce."""
@@ -236,7 +260,7 @@ class _State:
                                                    self.n_pad, c, self.p_off, self.m_max, self.info.lo, self.info.hi,
                                                    C.byref(pw.peers), pw.epoch_payload), "rpc_gather_pivots_peers")
             check(self.lib.rpc_peer_wait(self.ctx.handle, _stream(), C.c_void_p(pw.flags_ptr + 8 * _lib.MAX_PEERS),
-                                         self.info.world, pw.epoch_payload, 0, _ptr(pw.status)), "rpc_peer_wait")
+                                         self.info.world, pw.epoch_payload, PEER_TIMEOUT_MS, self._peer_status()), "rpc_peer_wait")
             return
         check(self.lib.rpc_gather_pivots(self.ctx.handle, _stream(), _ptr(idx_dev), m, _ptr(X), _ptr(xn), d, self.ldx,
                                          _ptr(piv.X) if piv is not None else None,
@@ -393,8 +417,8 @@ class _State:
         # sharded: keep the whole padded shard (equal widths on all ranks, so `.G` can all-gather); else cut to N
         nl = self.n_pad if self.info.world > 1 else self.n_loc
         self.wait_row_gather()
-        if self.peer is not None:
-            self.peer.check_status()
+        if self.peer is not None and int(self.info_dev[3].item()) != 0:
+            raise RuntimeError("peer-memory exchange timed out waiting for another rank's epoch")
         return PSDLowRank(self.G[:count, :nl], n=self.n, idx=arr_idx, rows=self.rows[:count, :nl], shard_info=self.info)
 
 
@@ -421,6 +445,7 @@ def _raise_if_invalid(stats_host):
 # --------------------------------------------------------------------------------------------------
 # simple RPCholesky: cholesky_helper(A, k, 'rp', stoptol) -- rpcholesky.py:12-50
 # --------------------------------------------------------------------------------------------------
+@_on_operator_device
 def cholesky_helper(A, k, alg, stoptol=0):
     if alg not in ("rp", "greedy", "rgreedy"):
         raise RuntimeError("Algorithm '{}' not recognized".format(alg))
@@ -513,6 +538,7 @@ def cholesky_helper(A, k, alg, stoptol=0):
 # --------------------------------------------------------------------------------------------------
 # block RPCholesky: block_cholesky_helper(A, k, b, 'rp', strategy='regularize') -- rpcholesky.py:65-138
 # --------------------------------------------------------------------------------------------------
+@_on_operator_device
 def block_cholesky_helper(A, k, b, alg, stoptol=1e-14, strategy="regularize", rbrp_atol=0.0, rbrp_rtol="1/b"):
     if alg not in ("rp", "greedy"):
         raise RuntimeError("Algorithm '{}' not recognized".format(alg))
@@ -609,6 +635,7 @@ def block_cholesky_helper(A, k, b, alg, stoptol=1e-14, strategy="regularize", rb
 # --------------------------------------------------------------------------------------------------
 # accelerated RPCholesky -- rpcholesky.py:159-232 (rejection_cholesky :140-157 runs on the device)
 # --------------------------------------------------------------------------------------------------
+@_on_operator_device
 def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
     A = _as_operator(A)
     if stoptol is None:

@@ -565,6 +565,16 @@ def test_input_forms(rpc):
     np.testing.assert_allclose(A[4, :], want[4, :], rtol=1e-13)
     with pytest.raises(RuntimeError):
         A["a", 0]
+    # numpy index semantics of the reference's `self.data[vec, :]` (matrix.py:189): negative indices wrap, out-of-range raise
+    np.testing.assert_allclose(A[-1, :], want[-1, :], rtol=1e-13)
+    np.testing.assert_allclose(A[[0, -300], [-2, 299]], want[np.ix_([0, -300], [-2, 299])], rtol=1e-13)
+    for bad in (300, -301):
+        with pytest.raises(IndexError):
+            A[bad, :]
+        with pytest.raises(IndexError):
+            A[[1, 2], [0, bad]]
+    with pytest.raises(IndexError):
+        A.out_of_sample(X64[:3], [0, 300])
     assert A.trace() == 300.0 and isinstance(A.to_matrix(), rpc.PSDMatrix)
     D = X64 @ X64.T
     with replay(2):
