@@ -76,7 +76,8 @@ def _on_operator_device(fn):
 
     @functools.wraps(fn)
     def wrapped(A, *args, **kwargs):
-        A = _as_operator(A)
+        if not isinstance(A, AbstractPSDMatrix):           # a raw array is wrapped on the current device by the driver itself
+            return fn(A, *args, **kwargs)
         with torch.cuda.device(A.device):
             return fn(A, *args, **kwargs)
     return wrapped
