@@ -2,7 +2,7 @@
 """One rank of a row-sharded parity run (launched by tests/test_gpu_sharded.py, or by hand):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node W --master-addr 127.0.0.1 --master-port P \
-        tests/sharded_worker.py --suite replay|unseeded [--log gpurun_out/sharded.jsonl]
+        tests/sharded_worker.py --suite replay|unseeded [--jsonl gpurun_out/sharded.jsonl]
 
 suite "replay":   the row-sharded drivers against the oracle on replayed draws (pivots bit-exact, G and rows to 1e-10,
                   trace, query counts) -- accelerated / block / RBRP / block greedy, shapes that go through the
@@ -122,7 +122,7 @@ def run_unseeded(rpc, orc, rank, world, emit):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--suite", default="replay", choices=["replay", "unseeded"])
-    ap.add_argument("--log", default=None)
+    ap.add_argument("--jsonl", default=None)
     args = ap.parse_args()
     rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(local)
@@ -138,9 +138,9 @@ def main():
             rec["data_plane"] = drv.LAST_DATA_PLANE
             line = json.dumps(rec)
             print(line, flush=True)
-            if args.log:
-                os.makedirs(os.path.dirname(os.path.abspath(args.log)), exist_ok=True)
-                with open(args.log, "a") as f:
+            if args.jsonl:
+                os.makedirs(os.path.dirname(os.path.abspath(args.jsonl)), exist_ok=True)
+                with open(args.jsonl, "a") as f:
                     f.write(line + "\n")
 
     ok = (run_replay if args.suite == "replay" else run_unseeded)(rpc, orc, rank, world, emit)

@@ -37,7 +37,7 @@ def _launch(suite, env_extra, tag):
            "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "sharded_worker.py"), "--suite", suite]
     out_dir = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(out_dir):
-        cmd += ["--log", os.path.join(out_dir, "sharded_w%d_%s.jsonl" % (world, tag))]
+        cmd += ["--jsonl", os.path.join(out_dir, "sharded_w%d_%s.jsonl" % (world, tag))]
     res = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, "sharded %s run failed on %d GPUs:\n%s\n%s" % (tag, world, res.stdout[-4000:], res.stderr[-4000:])
     assert '"ok": true' in res.stdout and '"ok": false' not in res.stdout
