@@ -237,6 +237,34 @@ int rpc_schur_update_ex(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int 
                         int k_pad, const double *rows_src, int64_t ldr, const int32_t *rowmap, double *diag, int64_t n_pad,
                         const struct rpc_peers *peers, unsigned long long epoch, int panel_lower);
 
+/* ---- "next" row 1 of the scope table: KRR_Nystrom on the factor rows the hot path leaves in HBM (KRR_Nystrom.py:34-58) ---- */
+
+/* M = R R^T for R = rows[0:k, 0:n_cols] (row-major, ldr >= n_cols): `KMn @ KnM` of KRR_Nystrom.py:54.  FP64 DMMA over the
+ * 128 x 128 tiles of the lower triangle, operands fetched by tensor-map TMA copies, split over the columns with a
+ * deterministic fixed-order reduction; both triangles of M (k x k, ldm >= k) are written. */
+int rpc_syrk_rows(rpc_ctx *ctx, void *stream, const double *R, int64_t ldr, int k, int64_t n_cols, double *M, int64_t ldm);
+
+/* out[i] = sum_c R[i, c] * y[c], i < k: `KMn @ Ytr` of KRR_Nystrom.py:54 (one pass over R, deterministic). */
+int rpc_rows_dot(rpc_ctx *ctx, void *stream, const double *R, int64_t ldr, int k, int64_t n_cols, const double *y, double *out);
+
+/* out[c] = sum_{i < k} w[i] * R[i, c], c < n_cols (n_cols even): the transposed product G^T w of the Nystrom preconditioner
+ * (block_experiments/pes_code.py:471-473), one pass over R. */
+int rpc_rows_tdot(rpc_ctx *ctx, void *stream, const double *R, int64_t ldr, int k, int64_t n_cols, const double *w, double *out);
+
+/* x <- (L L^T)^{-1} x for the lower-triangular Cholesky factor L (k x k, row-major) and nrhs right-hand sides stored as the
+ * columns of x (k x nrhs, row-major, ldx >= nrhs): the two triangular solves of scipy.linalg.solve(..., assume_a='pos')
+ * (KRR_Nystrom.py:54) after the k x k factorisation. */
+int rpc_chol_solve(rpc_ctx *ctx, void *stream, const double *L, int64_t ldl, int k, double *x, int64_t ldx, int nrhs);
+
+/* Fused kernel-times-vector: out[col] = (accumulate ? out[col] : 0) + sum_{i < s} w[i] * k(Xpiv[i], X[col]) for the n_pad points of
+ * X, no kernel value written to memory (same operands as rpc_kernel_rows; w has s entries, out n_pad).  Replaces
+ * `K_pred[:, :] @ sol` of KRR_Nystrom.predict_Nystrom (KRR_Nystrom.py:60-66, intent) and the blocked mat-vec
+ * `np.dot(A[blocks[i]:blocks[i+1], :], p)` of Nystrom-PCG (block_experiments/pes_code.py:500-506), using k(x, y) = k(y, x) to
+ * put the reduction over the resident pivots.  Deterministic (fixed-order sums). */
+int rpc_kernel_rows_wsum(rpc_ctx *ctx, void *stream, const rpc_kernel_spec *spec, const double *X, const double *xnorm, int64_t n_pad,
+                         int d, int64_t ldx, const double *Xpiv, const double *pnorm, int s, int64_t ldp, const double *w,
+                         double *out, int accumulate);
+
 /* Measurement aid (bench.py's roofline denominator): enqueues one launch of a pure DMMA.8x8x4 stream (one 256-thread CTA
  * per SM, 16 independent accumulator pairs per warp, `iters` rounds) and returns its flop count through the HOST pointer
  * flops_per_launch; the caller times it with CUDA events on `stream`.  Replaces no reference call site. */

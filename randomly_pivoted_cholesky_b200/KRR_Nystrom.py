@@ -2,10 +2,12 @@
 
 Same class and method names as the reference's KRR_Nystrom.py (:9-66).  `fit_Nystrom` keeps the factor rows in HBM:
 the normal equations  (K_Mn K_nM + N lambda K_MM + 100 max(K_MM) eps I) beta = K_Mn y  (KRR_Nystrom.py:52-54) are
-formed with one k x N x k DGEMM (cuBLAS through torch; summed over the shards with an all-reduce when the operator
-is row-sharded) and solved by Cholesky (scipy's assume_a='pos').  `predict_Nystrom` implements the evident intent of
-the reference's broken method (:60-66 multiplies an undefined `KtM`): K(Xts, Xtr[S]) @ sol, evaluated by the CUDA
-kernel-row evaluator with the pivots in the role of the rows.
+formed by the library's own kernels -- `rpc_syrk_rows` (FP64 DMMA over the lower-triangular tiles, tensor-map TMA) for
+K_Mn K_nM and `rpc_rows_dot` for K_Mn y, summed over the shards with an all-reduce when the operator is row-sharded -- and
+solved by Cholesky (scipy's assume_a='pos'): the k x k factorisation is the one library call (cuSOLVER potrf through torch),
+the two triangular solves are `rpc_chol_solve`.  `predict_Nystrom` implements the evident intent of the reference's broken
+method (:60-66 multiplies an undefined `KtM`): K(Xts, Xtr[S]) @ sol, evaluated by the fused kernel-times-vector kernel
+`rpc_kernel_rows_wsum` with the pivots resident and the test points streamed: no kernel value is written to memory.
 """
 from __future__ import annotations
 
@@ -16,6 +18,7 @@ import numpy as np
 import torch
 
 from . import dist as rdist
+from . import ops
 from .matrix import COL_ALIGN, KernelMatrix, _round_up
 
 
@@ -34,8 +37,7 @@ class KRR_Nystrom:
         n = K_exact.shape[0]
         rhs = torch.from_numpy(np.ascontiguousarray(np.asarray(Ytr, dtype=np.float64))).to(self.K.device)
         Lc = torch.linalg.cholesky(K_exact + lamb * n * torch.eye(n, dtype=torch.float64, device=self.K.device))
-        sol = torch.cholesky_solve(rhs.reshape(n, -1), Lc)
-        self.sol = sol.reshape(rhs.shape).cpu().numpy()
+        self.sol = ops.chol_solve(Lc, rhs).cpu().numpy()
         self.linsolve_time = time.time() - ts
 
     def predict(self, Xts):
@@ -79,8 +81,8 @@ class KRR_Nystrom:
         k = rows.shape[0]
         R = rows[:, :info.n_loc]                              # this rank's columns of K_Mn
         y = torch.from_numpy(np.ascontiguousarray(np.asarray(Ytr, dtype=np.float64)[info.lo:info.hi])).to(dev)
-        M = R @ R.T                                           # K_Mn K_nM  (k x N x k DGEMM)
-        rhs = R @ y
+        M = ops.syrk_rows(R, info.n_loc)                      # K_Mn K_nM: rpc_syrk_rows on this rank's columns
+        rhs = ops.rows_dot(R, y, info.n_loc)                  # K_Mn y:    rpc_rows_dot
         # K_MM = K_Mn[:, idx]: every rank contributes the columns it owns
         idx_t = torch.as_tensor(idx[:k], device=dev)
         mine = (idx_t >= info.lo) & (idx_t < info.hi)
@@ -94,8 +96,8 @@ class KRR_Nystrom:
             rhs = packed[2 * k * k:].view(rhs.shape)
         n = info.n
         M = M + n * lamb * KMM + 100 * KMM.max() * np.finfo(float).eps * torch.eye(sample_num, dtype=torch.float64, device=dev)
-        Lc = torch.linalg.cholesky(M)                         # scipy.linalg.solve(..., assume_a='pos')
-        sol = torch.cholesky_solve(rhs.reshape(k, -1), Lc).reshape(rhs.shape)
+        Lc = torch.linalg.cholesky(M)                         # scipy.linalg.solve(..., assume_a='pos'): k x k potrf (library)
+        sol = ops.chol_solve(Lc, rhs)                         # ... and its two triangular solves: rpc_chol_solve
         return sol.cpu().numpy()
 
     def _cross_times(self, Xts, idx, sol):
@@ -105,12 +107,14 @@ class KRR_Nystrom:
         m = len(idx)
         Kt = KernelMatrix(Xts, kernel=self.kernel, bandwidth=self.bandwidth, device=dev, **self.kernel_kwargs)
         piv = K._dev_new_payload(m)
-        K._dev_gather(torch.as_tensor(np.asarray(idx, dtype=np.int64), device=dev), m, piv)
-        out = torch.empty((m, Kt.n_pad), dtype=torch.float64, device=dev)
-        Kt._dev_rows_into(None, m, piv, C.c_void_p(out.data_ptr()), Kt.n_pad)
+        with torch.cuda.device(dev):
+            K._dev_gather(torch.as_tensor(np.asarray(idx, dtype=np.int64), device=dev), m, piv)
         s = torch.from_numpy(np.ascontiguousarray(np.asarray(sol, dtype=np.float64))).to(dev)
-        preds = out[:, :Kt.shape[0]].T @ s
-        return preds.cpu().numpy()
+        s2 = s.reshape(m, -1)
+        preds = torch.empty((Kt.shape[0], s2.shape[1]), dtype=torch.float64, device=dev)
+        for c in range(s2.shape[1]):                          # preds[t] = sum_j sol[j] k(Xtr[S_j], Xts[t]), fused (no K block in memory)
+            preds[:, c] = ops.kernel_weighted_sum(Kt, piv.X, piv.norm, m, s2[:, c])[:Kt.shape[0]]
+        return preds.reshape((Kt.shape[0],) + tuple(s.shape[1:])).cpu().numpy()
 
     def predict_Nystrom(self, Xts):
         ts = time.time()

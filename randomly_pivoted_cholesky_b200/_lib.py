@@ -136,6 +136,11 @@ _SIGNATURES = {
                                       C.c_uint64]),
     "rpc_gather_pivots_peers": (_INT, [_P, _P, _P, _INT, _P, _P, _INT, _I64, _I64, _I64, _P, _I64, _INT, _I64, _I64, _I64, _I64,
                                        C.POINTER(Peers), C.c_uint64]),
+    "rpc_kernel_rows_wsum": (_INT, [_P, _P, C.POINTER(KernelSpec), _P, _P, _I64, _INT, _I64, _P, _P, _INT, _I64, _P, _P, _INT]),
+    "rpc_syrk_rows": (_INT, [_P, _P, _P, _I64, _INT, _I64, _P, _I64]),
+    "rpc_rows_dot": (_INT, [_P, _P, _P, _I64, _INT, _I64, _P, _P]),
+    "rpc_rows_tdot": (_INT, [_P, _P, _P, _I64, _INT, _I64, _P, _P]),
+    "rpc_chol_solve": (_INT, [_P, _P, _P, _I64, _INT, _P, _I64, _INT]),
     "rpc_probe_fp64_peak": (_INT, [_P, _P, _INT, C.POINTER(_DBL)]),
     "rpc_simple_run": (_INT, [_P, _P, _INT, C.POINTER(KernelSpec), _P, _P, _INT, _I64, _P, _I64, _I64, _P, _P, _P, _INT, _INT, _P,
                               _I64, _P, _I64, _P, _I64]),

@@ -338,15 +338,18 @@ constexpr int DK_TP = 64;    // pivots per CTA pass (16 thread rows x 4)
 constexpr int DK_TN = 64;    // points per CTA (16 thread cols x 4)
 constexpr int DK_FT = 32;    // features per smem chunk
 
-template <bool L1>
+// REDUCE (fused kernel-times-vector): out is a vector, out[col] = (accumulate ? out[col] : 0) + sum_row w[row] k(pivot row, X col)
+template <bool L1, bool REDUCE>
 __global__ void __launch_bounds__(256) direct_rows_kernel(KernParams kp, const double *__restrict__ X, int64_t ldx, int d,
                                                           const double *__restrict__ Xpiv, int64_t ldp, int s,
-                                                          double *__restrict__ out, int64_t ldo) {
+                                                          double *__restrict__ out, int64_t ldo, const double *__restrict__ w,
+                                                          int accumulate) {
     __shared__ double Ps[DK_FT][DK_TP + 4];
     __shared__ double Ys[DK_FT][DK_TN + 4];
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const int64_t col0 = (int64_t)blockIdx.x * DK_TN;
+    double cs[4] = {0.0, 0.0, 0.0, 0.0};
     for (int p0 = 0; p0 < s; p0 += DK_TP) {
         double acc[4][4];
 #pragma unroll
@@ -392,10 +395,30 @@ __global__ void __launch_bounds__(256) direct_rows_kernel(KernParams kp, const d
                 double v[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) v[j] = L1 ? kern_from_l1(kp, acc[i][j]) : kern_from_d2(kp, acc[i][j]);
-                double *dst = out + (int64_t)row * ldo + col0 + tx * 4;
-                *reinterpret_cast<double2 *>(dst) = make_double2(v[0], v[1]);
-                *reinterpret_cast<double2 *>(dst + 2) = make_double2(v[2], v[3]);
+                if (REDUCE) {
+                    const double wr = w[row];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) cs[j] = fma(wr, v[j], cs[j]);
+                } else {
+                    double *dst = out + (int64_t)row * ldo + col0 + tx * 4;
+                    *reinterpret_cast<double2 *>(dst) = make_double2(v[0], v[1]);
+                    *reinterpret_cast<double2 *>(dst + 2) = make_double2(v[2], v[3]);
+                }
             }
+        }
+    }
+    if (REDUCE) {
+        // sum over the 16 thread rows in a fixed order (Ps is free: every thread is past its last read of it)
+        __syncthreads();
+        double *red = &Ps[0][0];                                   // 16 x 64 doubles fit in the 32 x 68 panel buffer
+#pragma unroll
+        for (int j = 0; j < 4; ++j) red[ty * DK_TN + tx * 4 + j] = cs[j];
+        __syncthreads();
+        if (tid < DK_TN) {
+            double t = 0.0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) t += red[q * DK_TN + tid];
+            out[col0 + tid] = (accumulate ? out[col0 + tid] : 0.0) + t;
         }
     }
 }
@@ -431,9 +454,9 @@ extern "C" int rpc_kernel_rows(rpc_ctx *ctx, void *stream, const rpc_kernel_spec
         if (done) return 0;
         dim3 grid((unsigned)(n_pad / DK_TN));
         if (spec->kind == RPC_KERN_LAPLACE)
-            direct_rows_kernel<true><<<grid, 256, 0, st>>>(kp, X, ldx, d, Xpiv, ldp, s, out, ldo);
+            direct_rows_kernel<true, false><<<grid, 256, 0, st>>>(kp, X, ldx, d, Xpiv, ldp, s, out, ldo, nullptr, 0);
         else
-            direct_rows_kernel<false><<<grid, 256, 0, st>>>(kp, X, ldx, d, Xpiv, ldp, s, out, ldo);
+            direct_rows_kernel<false, false><<<grid, 256, 0, st>>>(kp, X, ldx, d, Xpiv, ldp, s, out, ldo, nullptr, 0);
         RPC_LAUNCHED(ctx);
         return 0;
     }
@@ -474,6 +497,68 @@ extern "C" int rpc_kernel_rows(rpc_ctx *ctx, void *stream, const rpc_kernel_spec
             rc = dispatch_gemm<MODE_EVAL>(ctx, st, p, m, n_pad);
         }
         if (rc) return rc;
+    }
+    return 0;
+}
+
+// Fused kernel-times-vector: out[col] = (accumulate ? out[col] : 0) + sum_{i < s} w[i] k(Xpiv_i, X_col) for all n_pad points, without
+// writing a kernel value to memory -- the blocked kernel mat-vec of Nystrom-PCG (block_experiments/pes_code.py:500-506) and the
+// prediction K(Xts, Xtr[S]) @ sol of KRR (KRR_Nystrom.py:60-66) are this operation with the roles of rows and columns chosen so
+// that the reduction runs over the (at most 256 at a time) resident pivots.  Row blocks are applied one after the other.
+extern "C" int rpc_kernel_rows_wsum(rpc_ctx *ctx, void *stream, const rpc_kernel_spec *spec, const double *X, const double *xnorm,
+                                    int64_t n_pad, int d, int64_t ldx, const double *Xpiv, const double *pnorm, int s, int64_t ldp,
+                                    const double *w, double *out, int accumulate) {
+    RPC_CHECK_ARG(ctx && spec && X && Xpiv && w && out, "null pointer");
+    RPC_CHECK_ARG(s >= 1, "s >= 1");
+    RPC_CHECK_ARG(n_pad > 0 && n_pad % RPC_COL_ALIGN == 0, "n_pad must be a positive multiple of RPC_COL_ALIGN");
+    RPC_CHECK_ARG(d >= 1 && d % RPC_FEAT_ALIGN == 0 && ldx >= d, "d must be a multiple of RPC_FEAT_ALIGN, ldx >= d");
+    RPC_CHECK_ARG(spec->kind >= 0 && spec->kind <= 2, "unknown kernel kind");
+    RPC_CHECK_ARG(spec->kind != RPC_KERN_MATERN || spec->nu2 == 1 || spec->nu2 == 3 || spec->nu2 == 5,
+                  "Matern nu must be 0.5, 1.5 or 2.5");
+    cudaStream_t st = (cudaStream_t)stream;
+    KernParams kp = make_kern_params(spec);
+    if (spec->kind == RPC_KERN_LAPLACE || spec->extra_stability) {
+        const bool l1 = spec->kind == RPC_KERN_LAPLACE;
+        bool done = true;
+        int acc_flag = accumulate;
+        for (int m0 = 0; m0 < s && done; m0 += 256) {
+            const int m = s - m0 < 256 ? s - m0 : 256;
+            const int ldpt = 16 * rpc_direct_pi_for(m, l1);
+            int rc = rpc_ws_reserve(ctx, (size_t)d * ldpt * sizeof(double));
+            if (rc) return rc;
+            rc = rpc_transpose_pad(ctx, st, Xpiv + (int64_t)m0 * ldp, ldp, m, d, ctx->ws, ldpt, d);
+            if (rc) return rc;
+            rc = rpc_direct_rows_tma(ctx, st, kp, l1, X, ldx, d, ctx->ws, ldpt, m, out, 0, n_pad, w + m0, acc_flag);
+            if (rc == -100) { done = false; break; }
+            if (rc) return rc;
+            acc_flag = 1;
+        }
+        if (done) return 0;
+        // the pivot panel does not fit in shared memory (large d): chunked kernel, all pivots in one launch.  A first row block
+        // may already have been applied above only if it fitted, and then every block fits: nothing was applied here.
+        dim3 grid((unsigned)(n_pad / DK_TN));
+        if (l1) direct_rows_kernel<true, true><<<grid, 256, 0, st>>>(kp, X, ldx, d, Xpiv, ldp, s, out, 0, w, accumulate);
+        else direct_rows_kernel<false, true><<<grid, 256, 0, st>>>(kp, X, ldx, d, Xpiv, ldp, s, out, 0, w, accumulate);
+        RPC_LAUNCHED(ctx);
+        return 0;
+    }
+    RPC_CHECK_ARG(xnorm && pnorm, "row norms required for the expanded Euclidean form");
+    RPC_CHECK_ARG(ldx % 2 == 0, "the DMMA evaluator needs an even point stride (16-byte rows)");
+    int acc_flag = accumulate;
+    for (int m0 = 0; m0 < s; m0 += 248) {
+        const int m = s - m0 < 248 ? s - m0 : 248;
+        const int ld_res = rpc_eval_panel_wsum_ld(m, d, ldx);
+        if (ld_res <= 0) {
+            rpc_set_error("rpc_kernel_rows_wsum: a %d x %d pivot panel does not fit in shared memory (d too large for the fused DMMA path)", d, m);
+            return -4;
+        }
+        int rc = rpc_ws_reserve(ctx, (size_t)d * ld_res * sizeof(double));
+        if (rc) return rc;
+        rc = rpc_transpose_pad(ctx, st, Xpiv + (int64_t)m0 * ldp, ldp, m, d, ctx->ws, ld_res, d);
+        if (rc) return rc;
+        rc = rpc_eval_panel_wsum(ctx, st, kp, X, xnorm, n_pad, d, ldx, ctx->ws, pnorm + m0, m, w + m0, out, acc_flag);
+        if (rc) return rc;
+        acc_flag = 1;
     }
     return 0;
 }

@@ -15,14 +15,17 @@ using namespace dg;
 constexpr int DE_TN = 64;          // points per tile
 constexpr int DE_THREADS = 256;    // 16 x 16
 
-template <bool L1, int PI>
+// REDUCE (fused kernel-times-vector): out is a vector, out[col] = (accumulate ? out[col] : 0) + sum_row w[row] k(pivot row, X col)
+template <bool L1, int PI, bool REDUCE>
 __global__ void __launch_bounds__(DE_THREADS, 1) direct_rows_tma(const KernParams kp, const double *__restrict__ X, int64_t ldx,
                                                                  int d, const double *__restrict__ Pt, int ldpt, int s,
-                                                                 double *__restrict__ out, int64_t ldo, int ntiles) {
+                                                                 double *__restrict__ out, int64_t ldo, int ntiles,
+                                                                 const double *__restrict__ w, int accumulate) {
     extern __shared__ __align__(16) double sm[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(sm);          // [0] panel, [1..2] X tiles
     double *Ps = sm + 4;                                        // [d][ldpt]
     double *Xs = Ps + (size_t)d * ldpt;                         // [2][DE_TN * ldx]
+    double *red = Xs + 2 * (size_t)DE_TN * ldx;                 // REDUCE: [16 thread rows][DE_TN] partial column sums
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int tile_doubles = DE_TN * (int)ldx;
 
@@ -78,6 +81,34 @@ __global__ void __launch_bounds__(DE_THREADS, 1) direct_rows_tma(const KernParam
                 }
         }
         const int64_t col0 = (int64_t)tile * DE_TN;
+        if (REDUCE) {
+            double cs[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int i = 0; i < PI; ++i) {
+                const int row = ty + 16 * i;
+                if (row < s) {
+                    const double wr = w[row];
+#pragma unroll
+                    for (int j = 0; j < 4; j += 2) {
+                        const double2 v = L1 ? kern_from_l1_pair(kp, acc[i][j], acc[i][j + 1])
+                                             : kern_from_d2_pair(kp, acc[i][j], acc[i][j + 1]);
+                        cs[j] = fma(wr, v.x, cs[j]);
+                        cs[j + 1] = fma(wr, v.y, cs[j + 1]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) red[ty * DE_TN + tx + 16 * j] = cs[j];
+            __syncthreads();
+            if (tid < DE_TN) {
+                double t = 0.0;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) t += red[q * DE_TN + tid];          // fixed order: deterministic
+                out[col0 + tid] = (accumulate ? out[col0 + tid] : 0.0) + t;
+            }
+            __syncthreads();
+            continue;
+        }
 #pragma unroll
         for (int i = 0; i < PI; ++i) {
             const int row = ty + 16 * i;
@@ -97,28 +128,31 @@ __global__ void __launch_bounds__(DE_THREADS, 1) direct_rows_tma(const KernParam
 
 template <bool L1, int PI>
 static int launch_direct(rpc_ctx *ctx, cudaStream_t st, const KernParams &kp, const double *X, int64_t ldx, int d, const double *Pt,
-                         int ldpt, int s, double *out, int64_t ldo, int64_t n_pad, size_t shm) {
+                         int ldpt, int s, double *out, int64_t ldo, int64_t n_pad, size_t shm, const double *w, int accumulate) {
     static unsigned long long configured = 0;   // one bit per device: function attributes are per device
     if (!rpc_dev_bit(configured, ctx)) {
-        RPC_CUDA(cudaFuncSetAttribute(direct_rows_tma<L1, PI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        RPC_CUDA(cudaFuncSetAttribute(direct_rows_tma<L1, PI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        RPC_CUDA(cudaFuncSetAttribute(direct_rows_tma<L1, PI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured |= 1ull << (ctx->device & 63);
     }
     const int ntiles = (int)(n_pad / DE_TN);
     const int ctas = rpc_persistent_ctas(ctx);
     const int grid = ntiles < ctas ? ntiles : ctas;
-    direct_rows_tma<L1, PI><<<grid, DE_THREADS, shm, st>>>(kp, X, ldx, d, Pt, ldpt, s, out, ldo, ntiles);
+    if (w) direct_rows_tma<L1, PI, true><<<grid, DE_THREADS, shm, st>>>(kp, X, ldx, d, Pt, ldpt, s, out, ldo, ntiles, w, accumulate);
+    else direct_rows_tma<L1, PI, false><<<grid, DE_THREADS, shm, st>>>(kp, X, ldx, d, Pt, ldpt, s, out, ldo, ntiles, nullptr, 0);
     RPC_LAUNCHED(ctx);
     return 0;
 }
 
 // s <= 256 pivots, panel Pt (d x ldpt, ldpt = 16 * PI) already built.  Returns -100 if the shape does not fit.
+// w != NULL: the fused kernel-times-vector variant (out = vector of n_pad weighted column sums).
 int rpc_direct_rows_tma(rpc_ctx *ctx, cudaStream_t st, const KernParams &kp, bool l1, const double *X, int64_t ldx, int d,
-                        const double *Pt, int ldpt, int s, double *out, int64_t ldo, int64_t n_pad) {
+                        const double *Pt, int ldpt, int s, double *out, int64_t ldo, int64_t n_pad, const double *w, int accumulate) {
     const int pi = ldpt / 16;
-    const size_t shm = (4 + (size_t)d * ldpt + 2 * (size_t)DE_TN * ldx) * sizeof(double);
+    const size_t shm = (4 + (size_t)d * ldpt + 2 * (size_t)DE_TN * ldx + 16 * DE_TN) * sizeof(double);
     if (shm > 227 * 1024 || (ldx * 8 * DE_TN) % 16 != 0) return -100;
 #define DE_CASE(L, P) \
-    case P: return launch_direct<L, P>(ctx, st, kp, X, ldx, d, Pt, ldpt, s, out, ldo, n_pad, shm);
+    case P: return launch_direct<L, P>(ctx, st, kp, X, ldx, d, Pt, ldpt, s, out, ldo, n_pad, shm, w, accumulate);
     if (l1) {
         switch (pi) {
             DE_CASE(true, 1) DE_CASE(true, 2) DE_CASE(true, 4) DE_CASE(true, 6) DE_CASE(true, 8) DE_CASE(true, 10)

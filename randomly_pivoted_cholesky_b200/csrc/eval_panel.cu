@@ -34,6 +34,10 @@ struct EvalParams {
     int64_t ldo;
     int ntiles;             // n_pad / N_TILE
     int xb;                 // X buffers in the ring (2 or 3)
+    // REDUCE variant (fused kernel-times-vector): out[col] = (accumulate ? out[col] : 0) + sum_row w[row] k(pivot row, X col);
+    // `out` is then a vector of n_pad entries and no kernel value is written to memory
+    const double *w;        // [m_valid]
+    int accumulate;
 };
 
 // 2^(j/32), correctly rounded
@@ -117,11 +121,26 @@ static __device__ __noinline__ void gauss_tab_store4(double *dst, int ok, double
     }
 }
 
+// REDUCE variant: eight scaled arguments (two fragment rows A, B of an NI = 2 tile, columns c0..c3 each) -> kernel values ->
+// the thread's four running weighted column sums, returned in registers
+static __device__ __noinline__ double4 gauss_tab_wsum8(double tab_lane, double wA, double wB, double4 cs, double x0, double x1, double x2,
+                                                       double x3, double x4, double x5, double x6, double x7) {
+    double x[8] = {x0, x1, x2, x3, x4, x5, x6, x7};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = x[i] < 0.0 ? x[i] : 0.0;
+    exp_tab_batch<8>(x, tab_lane);
+    cs.x = fma(wB, x[4], fma(wA, x[0], cs.x));
+    cs.y = fma(wB, x[5], fma(wA, x[1], cs.y));
+    cs.z = fma(wB, x[6], fma(wA, x[2], cs.z));
+    cs.w = fma(wB, x[7], fma(wA, x[3], cs.w));
+    return cs;
+}
+
 template <class C>
 struct Smem {
     // doubles: panel | pivot norms | X ring | norm ring | barriers
     static size_t doubles(int kp, int64_t ldx, int xb) {
-        return (size_t)kp * C::LDA + C::M_TILE + (size_t)xb * (C::N_TILE * ldx + C::N_TILE) + 16;
+        return (size_t)kp * C::LDA + 2 * C::M_TILE + C::WM * C::N_TILE + (size_t)xb * (C::N_TILE * ldx + C::N_TILE) + 16;
     }
 };
 
@@ -154,14 +173,17 @@ __device__ __forceinline__ void k_loop(double (&acc)[C::MI][C::NI][2], const dou
     if (nks & 1) mma(a0, b0);
 }
 
-template <class C, bool GAUSS>
+template <class C, bool GAUSS, bool REDUCE>
 __global__ void __launch_bounds__(C::THREADS, 1) eval_panel_kernel(const EvalParams p) {
+    static_assert(!REDUCE || C::NI == 2, "the fused kernel-times-vector variant is written for the NI = 2 tiles");
     extern __shared__ __align__(16) double smem[];
     const int ldx = (int)p.ldx;
     const int xtile = C::N_TILE * ldx;
     double *Pan = smem;
     double *pns = Pan + (size_t)p.kp * C::LDA;
-    double *Xs = pns + C::M_TILE;
+    double *wts = pns + C::M_TILE;                                              // REDUCE: weights of the rows (0 past m_valid)
+    double *red = wts + C::M_TILE;                                              // REDUCE: [WM][N_TILE] column sums of the warp rows
+    double *Xs = red + C::WM * C::N_TILE;
     double *xns = Xs + (size_t)p.xb * xtile;
     uint64_t *bars = reinterpret_cast<uint64_t *>(xns + p.xb * C::N_TILE);      // [0] panel, [1 + b] full, [1 + xb + b] empty
     uint64_t *xfull = bars + 1, *xempty = bars + 1 + p.xb;
@@ -177,7 +199,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) eval_panel_kernel(const EvalPar
         }
         fence_barrier_init();
     }
-    for (int r = tid; r < C::M_TILE; r += C::THREADS) pns[r] = r < p.m_valid ? g * p.pnorm[r] : 0.0;
+    for (int r = tid; r < C::M_TILE; r += C::THREADS) {
+        pns[r] = r < p.m_valid ? g * p.pnorm[r] : 0.0;
+        wts[r] = (REDUCE && r < p.m_valid) ? p.w[r] : 0.0;
+    }
     __syncthreads();
 
     if (warp >= C::CONSUMERS) {
@@ -249,6 +274,66 @@ __global__ void __launch_bounds__(C::THREADS, 1) eval_panel_kernel(const EvalPar
         __syncwarp();
         if (lane == 0) mbar_arrive(&xempty[b]);
 
+        if (REDUCE) {
+            // weighted column sums over the rows of the tile: in the thread, over the 8 row groups of the warp (shuffles), over
+            // the warp rows (shared memory), in a fixed order
+            double4 cs = make_double4(0.0, 0.0, 0.0, 0.0);          // columns n0 + {2lk, 2lk+1, 8+2lk, 8+2lk+1}
+            constexpr int J1 = C::NI > 1 ? 1 : 0;
+#pragma unroll
+            for (int i = 0; i < C::MI; i += 2) {
+                const int rA = m0 + i * C::RSTEP;
+                if (i < mi_cnt && rA < p.m_valid) {                         // warp uniform
+                    const int rowA = rA + lr;
+                    const int i1 = (i + 1 < C::MI) ? i + 1 : i;
+                    const bool pairB = i + 1 < C::MI && i + 1 < mi_cnt;
+                    const int rowB = pairB ? rowA + C::RSTEP : rowA;
+                    const double pnA = pns[rowA], pnB = pns[rowB];
+                    const double wA = wts[rowA], wB = pairB ? wts[rowB] : 0.0;
+                    if (GAUSS) {
+                        cs = gauss_tab_wsum8(tab_lane, wA, wB, cs, fma(acc[i][0][0], m2g, pnA + xn[0][0]), fma(acc[i][0][1], m2g, pnA + xn[0][1]),
+                                             fma(acc[i][J1][0], m2g, pnA + xn[J1][0]), fma(acc[i][J1][1], m2g, pnA + xn[J1][1]),
+                                             fma(acc[i1][0][0], m2g, pnB + xn[0][0]), fma(acc[i1][0][1], m2g, pnB + xn[0][1]),
+                                             fma(acc[i1][J1][0], m2g, pnB + xn[J1][0]), fma(acc[i1][J1][1], m2g, pnB + xn[J1][1]));
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int ih = h ? i1 : i;
+                            const double pn = h ? pnB : pnA, wv = h ? wB : wA;
+                            double d00 = (-2.0 * acc[ih][0][0] + pn) + xn[0][0], d01 = (-2.0 * acc[ih][0][1] + pn) + xn[0][1];
+                            double d10 = (-2.0 * acc[ih][J1][0] + pn) + xn[J1][0], d11 = (-2.0 * acc[ih][J1][1] + pn) + xn[J1][1];
+                            const double2 v0 = kern_from_d2_pair(p.kparm, d00 > 0.0 ? d00 : 0.0, d01 > 0.0 ? d01 : 0.0);
+                            const double2 v1 = kern_from_d2_pair(p.kparm, d10 > 0.0 ? d10 : 0.0, d11 > 0.0 ? d11 : 0.0);
+                            cs.x = fma(wv, v0.x, cs.x); cs.y = fma(wv, v0.y, cs.y);
+                            cs.z = fma(wv, v1.x, cs.z); cs.w = fma(wv, v1.y, cs.w);
+                        }
+                    }
+                }
+            }
+            double c4[4] = {cs.x, cs.y, cs.z, cs.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                double v = c4[q];
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                c4[q] = v;
+            }
+            consumer_bar_sync(C::CONSUMERS * 32);                  // the previous tile's readers of `red` are done
+            if (lr == 0) {
+                red[wm * C::N_TILE + n0 + 2 * lk] = c4[0];
+                red[wm * C::N_TILE + n0 + 2 * lk + 1] = c4[1];
+                red[wm * C::N_TILE + n0 + 8 * J1 + 2 * lk] = c4[2];
+                red[wm * C::N_TILE + n0 + 8 * J1 + 2 * lk + 1] = c4[3];
+            }
+            consumer_bar_sync(C::CONSUMERS * 32);
+            for (int n = tid; n < C::N_TILE; n += C::CONSUMERS * 32) {
+                double sres = 0.0;
+#pragma unroll
+                for (int wq = 0; wq < C::WM; ++wq) sres += red[wq * C::N_TILE + n];
+                p.out[col0 + n] = (p.accumulate ? p.out[col0 + n] : 0.0) + sres;
+            }
+            continue;
+        }
         double *out0 = p.out + col0 + n0 + 2 * lk;
         if (GAUSS && C::NI == 2) {
             // two fragment rows (8 values) per call
@@ -306,12 +391,12 @@ __global__ void __launch_bounds__(C::THREADS, 1) eval_panel_kernel(const EvalPar
 
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 
-template <class C>
+template <class C, bool REDUCE = false>
 static int launch(rpc_ctx *ctx, cudaStream_t st, EvalParams p, int64_t n_pad) {
     static unsigned long long configured = 0;   // one bit per device: function attributes are per device
     if (!rpc_dev_bit(configured, ctx)) {
-        RPC_CUDA(cudaFuncSetAttribute(eval_panel_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
-        RPC_CUDA(cudaFuncSetAttribute(eval_panel_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        RPC_CUDA(cudaFuncSetAttribute(eval_panel_kernel<C, true, REDUCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        RPC_CUDA(cudaFuncSetAttribute(eval_panel_kernel<C, false, REDUCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
         configured |= 1ull << (ctx->device & 63);
     }
     p.ntiles = (int)(n_pad / C::N_TILE);
@@ -319,8 +404,8 @@ static int launch(rpc_ctx *ctx, cudaStream_t st, EvalParams p, int64_t n_pad) {
     const size_t shm = Smem<C>::doubles(p.kp, p.ldx, p.xb) * 8;
     const int ctas = rpc_persistent_ctas(ctx);
     const unsigned grid = (unsigned)(p.ntiles < ctas ? p.ntiles : ctas);
-    if (p.kparm.kind == RPC_KERN_GAUSSIAN) eval_panel_kernel<C, true><<<grid, C::THREADS, shm, st>>>(p);
-    else eval_panel_kernel<C, false><<<grid, C::THREADS, shm, st>>>(p);
+    if (p.kparm.kind == RPC_KERN_GAUSSIAN) eval_panel_kernel<C, true, REDUCE><<<grid, C::THREADS, shm, st>>>(p);
+    else eval_panel_kernel<C, false, REDUCE><<<grid, C::THREADS, shm, st>>>(p);
     RPC_LAUNCHED(ctx);
     return 0;
 }
@@ -382,5 +467,48 @@ int rpc_eval_panel_rows(rpc_ctx *ctx, cudaStream_t st, const KernParams &kparm, 
         case 96: return launch<E96>(ctx, st, p, n_pad);
         case 128: return launch<E128>(ctx, st, p, n_pad);
         default: return launch<E256>(ctx, st, p, n_pad);
+    }
+}
+
+// ---- fused kernel-times-vector: out[col] (+)= sum_{i < m} w[i] k(Xpiv_i, X_col), no kernel value written to memory ----------
+// row tiles of the REDUCE variant (all NI = 2): 16, 32, 64, 128, 192, 248
+namespace ep {
+typedef Cfg<2, 4, 4, 2> R64;
+typedef Cfg<2, 4, 8, 2> R128;
+typedef Cfg<2, 4, 12, 2> R192;
+typedef Cfg<2, 4, 16, 2, true> R248;
+}  // namespace ep
+
+static int ep_wsum_tile_rows(int m) {
+    const int tiles[] = {16, 32, 64, 128, 192, 248};
+    for (int t : tiles) if (m <= t) return t;
+    return 248;
+}
+
+int rpc_eval_panel_wsum_ld(int m, int kp, int64_t ldx) {
+    using namespace ep;
+    switch (ep_wsum_tile_rows(m)) {
+        case 16: return fits<E16>(kp, ldx) ? E16::LDA : 0;
+        case 32: return fits<E32>(kp, ldx) ? E32::LDA : 0;
+        case 64: return fits<R64>(kp, ldx) ? R64::LDA : 0;
+        case 128: return fits<R128>(kp, ldx) ? R128::LDA : 0;
+        case 192: return fits<R192>(kp, ldx) ? R192::LDA : 0;
+        default: return fits<R248>(kp, ldx) ? R248::LDA : 0;
+    }
+}
+
+int rpc_eval_panel_wsum(rpc_ctx *ctx, cudaStream_t st, const KernParams &kparm, const double *X, const double *xnorm, int64_t n_pad,
+                        int kp, int64_t ldx, const double *Pan, const double *pnorm, int m, const double *w, double *out, int accumulate) {
+    using namespace ep;
+    EvalParams p{};
+    p.Pan = Pan; p.kp = kp; p.pnorm = pnorm; p.m_valid = m; p.X = X; p.ldx = ldx; p.xnorm = xnorm; p.kparm = kparm;
+    p.out = out; p.ldo = 0; p.w = w; p.accumulate = accumulate;
+    switch (ep_wsum_tile_rows(m)) {
+        case 16: return launch<E16, true>(ctx, st, p, n_pad);
+        case 32: return launch<E32, true>(ctx, st, p, n_pad);
+        case 64: return launch<R64, true>(ctx, st, p, n_pad);
+        case 128: return launch<R128, true>(ctx, st, p, n_pad);
+        case 192: return launch<R192, true>(ctx, st, p, n_pad);
+        default: return launch<R248, true>(ctx, st, p, n_pad);
     }
 }

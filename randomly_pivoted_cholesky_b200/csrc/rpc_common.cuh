@@ -165,10 +165,15 @@ struct rpc_ctx;
 // csrc/direct_eval.cu: persistent TMA-staged evaluator for the non-contraction kernels (returns -100 if the shape
 // does not fit in shared memory; the caller then uses the chunked kernel)
 int rpc_direct_rows_tma(rpc_ctx *ctx, cudaStream_t st, const KernParams &kp, bool l1, const double *X, int64_t ldx, int d,
-                        const double *Pt, int ldpt, int s, double *out, int64_t ldo, int64_t n_pad);
+                        const double *Pt, int ldpt, int s, double *out, int64_t ldo, int64_t n_pad, const double *w = nullptr,
+                        int accumulate = 0);
 int rpc_direct_pi_for(int s, bool l1);
 // csrc/eval_panel.cu: DMMA evaluator with the pivot panel resident in shared memory (short contractions).
 // rpc_eval_panel_ld: leading dimension to build the transposed panel with for m <= 256 rows, 0 if the shape does not fit.
 int rpc_eval_panel_ld(int m, int kp, int64_t ldx);
 int rpc_eval_panel_rows(rpc_ctx *ctx, cudaStream_t st, const KernParams &kparm, const double *X, const double *xnorm, int64_t n_pad,
                         int kp, int64_t ldx, const double *Pan, const double *pnorm, int m, double *out, int64_t ldo);
+// fused kernel-times-vector variant of the panel-resident evaluator (tiles of up to 248 rows)
+int rpc_eval_panel_wsum_ld(int m, int kp, int64_t ldx);
+int rpc_eval_panel_wsum(rpc_ctx *ctx, cudaStream_t st, const KernParams &kparm, const double *X, const double *xnorm, int64_t n_pad,
+                        int kp, int64_t ldx, const double *Pan, const double *pnorm, int m, const double *w, double *out, int accumulate);

@@ -157,3 +157,78 @@ def fp64_peak_tflops(device=None, iters=4000, reps=5):
             if r > 0:
                 best = min(best, e0.elapsed_time(e1))
     return fl.value / best / 1e9
+
+
+# ---- N-proportional linear algebra on the factor rows (KRR_Nystrom / Nystrom-PCG, the "next" rows of the scope table) --------
+def syrk_rows(R, n_cols=None):
+    """M = R[:, :n_cols] @ R[:, :n_cols].T for a (k, ld) CUDA tensor with unit column stride: rpc_syrk_rows (DMMA + tensor-map TMA)."""
+    if R.stride(1) != 1:
+        raise ValueError("syrk_rows needs a row-major tensor")
+    ctx = _ctx(R.device)
+    k = R.shape[0]
+    n_cols = R.shape[1] if n_cols is None else int(n_cols)
+    if R.stride(0) % 2 or R.data_ptr() % 16:                 # tensor-map TMA: 16-byte aligned rows
+        Rp = torch.zeros((k, n_cols + (n_cols & 1)), dtype=torch.float64, device=R.device)
+        Rp[:, :n_cols] = R[:, :n_cols]
+        R = Rp
+    M = torch.empty((k, k), dtype=torch.float64, device=R.device)
+    with torch.cuda.device(R.device):
+        check(ctx.lib.rpc_syrk_rows(ctx.handle, _stream(), _ptr(R), R.stride(0), k, n_cols, _ptr(M), k), "rpc_syrk_rows")
+    return M
+
+
+def rows_dot(R, y, n_cols=None):
+    """R[:, :n_cols] @ y for y of shape (n_cols,) or (n_cols, m): rpc_rows_dot, one pass over R per column of y."""
+    ctx = _ctx(R.device)
+    k = R.shape[0]
+    n_cols = R.shape[1] if n_cols is None else int(n_cols)
+    y2 = y.reshape(n_cols, -1)
+    out = torch.empty((k, y2.shape[1]), dtype=torch.float64, device=R.device)
+    with torch.cuda.device(R.device):
+        for c in range(y2.shape[1]):
+            yc = y2[:, c].contiguous()
+            oc = torch.empty((k,), dtype=torch.float64, device=R.device)
+            check(ctx.lib.rpc_rows_dot(ctx.handle, _stream(), _ptr(R), R.stride(0), k, n_cols, _ptr(yc), _ptr(oc)), "rpc_rows_dot")
+            out[:, c] = oc
+    return out.reshape((k,) + tuple(y.shape[1:]))
+
+
+def rows_tdot(R, w, n_cols=None):
+    """R[:, :n_cols].T @ w for w of shape (k,): rpc_rows_tdot (n_cols is rounded up to even inside the padded row)."""
+    ctx = _ctx(R.device)
+    k = R.shape[0]
+    n_cols = R.shape[1] if n_cols is None else int(n_cols)
+    n_even = n_cols + (n_cols & 1)
+    if n_even > R.shape[1] and n_even > R.stride(0):
+        raise ValueError("rows_tdot needs one column of padding for an odd column count")
+    out = torch.empty((n_even,), dtype=torch.float64, device=R.device)
+    wc = w.contiguous()
+    with torch.cuda.device(R.device):
+        check(ctx.lib.rpc_rows_tdot(ctx.handle, _stream(), _ptr(R), R.stride(0), k, n_even, _ptr(wc), _ptr(out)), "rpc_rows_tdot")
+    return out[:n_cols]
+
+
+def chol_solve(L, b):
+    """(L L^T)^{-1} b for a lower-triangular (k, k) CUDA tensor and b of shape (k,) or (k, m): rpc_chol_solve."""
+    ctx = _ctx(L.device)
+    k = L.shape[0]
+    x = b.reshape(k, -1).contiguous().clone()
+    Lc = L.contiguous()
+    with torch.cuda.device(L.device):
+        check(ctx.lib.rpc_chol_solve(ctx.handle, _stream(), _ptr(Lc), Lc.stride(0), k, _ptr(x), x.stride(0), x.shape[1]), "rpc_chol_solve")
+    return x.reshape(b.shape)
+
+
+def kernel_weighted_sum(A, piv_X, piv_norm, m, w, out=None, accumulate=False):
+    """out[col] (+)= sum_{i < m} w[i] k(piv_X[i], A's point col) over A's n_pad points: rpc_kernel_rows_wsum (no kernel value is
+    written to memory).  piv_X: (>= m, A.ldx) points in A's padded layout, piv_norm their squared norms."""
+    ctx = A._ctx
+    if out is None:
+        out = torch.empty((A.n_pad,), dtype=torch.float64, device=A.device)
+        accumulate = False
+    wc = w.contiguous()
+    with torch.cuda.device(A.device):
+        check(ctx.lib.rpc_kernel_rows_wsum(ctx.handle, _stream(), C.byref(A._spec), _ptr(A._Xd), _ptr(A._xnorm), A.n_pad, A.d_pad, A.ldx,
+                                           _ptr(piv_X), _ptr(piv_norm), int(m), piv_X.stride(0), _ptr(wc), _ptr(out),
+                                           1 if accumulate else 0), "rpc_kernel_rows_wsum")
+    return out

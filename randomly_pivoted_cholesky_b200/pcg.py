@@ -6,10 +6,12 @@ under the script's own names:
     precondition = NystromPreconditioner(lra, mu)     # :464-475  thin QR of G^T, SVD of R, P^{-1}v = U((S^2+mu)^{-1} - mu^{-1})U^T v + v/mu
     x, resid = pcg(A, y, mu, precondition, tol, max_iters)   # :479-511  solves (A + mu I) x = y
 
-`A` is a device-backed KernelMatrix / PSDMatrix: the mat-vec A @ p is evaluated block of rows by block of rows with the
-CUDA kernel-row evaluator (the script's `np.dot(A[blocks[i]:blocks[i+1], :], p)`, :502-505), the factor `lra.G` stays in
-HBM, QR / SVD / GEMV are library calls (cuSOLVER / cuBLAS through torch).  `CompactEigenvalueDecomposition.from_G(G).krr`
-(lra.py:51-55, 78-80) is the same operator in eigen form.
+`A` is a device-backed KernelMatrix / PSDMatrix.  Every N-proportional operation runs in the library's own kernels: the
+mat-vec A @ p is the fused kernel-times-vector kernel (`rpc_kernel_rows_wsum`: the script's blocked
+`np.dot(A[blocks[i]:blocks[i+1], :], p)`, :502-505, without ever writing a block of A), the preconditioner works on the factor
+`lra.G` in HBM through `rpc_syrk_rows` / `rpc_rows_dot` / `rpc_rows_tdot`; the only library call is one k x k `eigh`.
+`CompactEigenvalueDecomposition.from_G(G).krr` (lra.py:51-55, 78-80) is the same operator in eigen form.  The loop is pinned to
+the reference's own statements by tests/golden/pcg_loop_*.npz (tests/golden/make_golden_pcg.py executes them unchanged).
 """
 from __future__ import annotations
 
@@ -18,43 +20,52 @@ import ctypes as C
 import numpy as np
 import torch
 
+from . import ops
 from .matrix import AbstractPSDMatrix
 
 
 class NystromPreconditioner:
-    """pes_code.py:464-475 for a factor G (k x N, A ~ G^T G) and shift mu."""
+    """pes_code.py:464-475 for a factor G (k x N, A ~ G^T G) and shift mu:  P^{-1} v = U ((S^2 + mu)^{-1} - mu^{-1}) U^T v + v / mu
+    with G^T = U S W^T.  The reference forms U explicitly from a thin QR of G^T and an SVD of R; here U = G^T W S^{-1} stays
+    implicit: W, S^2 come from the k x k eigenproblem of G G^T (`rpc_syrk_rows`, then one small library eigh), and an application
+    is two passes over G in HBM (`rpc_rows_dot` for G v, `rpc_rows_tdot` for G^T w) -- no N x k matrix besides G is ever formed.
+    Directions with S^2 below eps * S_max^2 * k are dropped: their coefficient (S^2 + mu)^{-1} - mu^{-1} vanishes with S^2."""
 
     def __init__(self, lra, mu):
         G = lra.G_device if hasattr(lra, "G_device") else lra
         if not isinstance(G, torch.Tensor):
             raise RuntimeError("NystromPreconditioner needs a device-backed PSDLowRank (or a CUDA tensor G)")
-        Qm, R = torch.linalg.qr(G.T, mode="reduced")          # :467
-        Cm, Sigma, _ = torch.linalg.svd(R)                     # :468
-        self.U = Qm @ Cm                                       # :469
-        self.Sigma = Sigma
+        self.G = G
+        self.n = lra.shape[0] if hasattr(lra, "shape") and not isinstance(lra, torch.Tensor) else G.shape[1]
+        k = G.shape[0]
+        S2, W = torch.linalg.eigh(ops.syrk_rows(G, self.n))       # G G^T = W S^2 W^T (k x k)
+        keep = S2 > S2.max() * k * torch.finfo(torch.float64).eps
+        self.Sigma = torch.sqrt(S2.clamp_min(0.0))
+        inv = torch.where(keep, 1.0 / self.Sigma.clamp_min(1e-300), torch.zeros_like(S2))
+        self.WSinv = W * inv[None, :]                              # k x k: U = G^T (W S^{-1})
         self.mu = float(mu)
-        self.diag = 1.0 / (Sigma ** 2 + self.mu) - 1.0 / self.mu
+        self.diag = torch.where(keep, 1.0 / (S2 + self.mu) - 1.0 / self.mu, torch.zeros_like(S2))
 
     def __call__(self, v):
-        t = self.U.T @ v
-        t = self.diag * t if t.ndim == 1 else self.diag[:, None] * t
-        return self.U @ t + v / self.mu                        # :471-473
+        if v.ndim != 1:
+            return torch.stack([self(v[:, c]) for c in range(v.shape[1])], dim=1)
+        t = self.WSinv.T @ ops.rows_dot(self.G, v, self.n)         # U^T v       (k)
+        w = self.WSinv @ (self.diag * t)                           # k x k products: tiny
+        return ops.rows_tdot(self.G, w, self.n) + v / self.mu      # :471-473
 
 
 def kernel_matvec(A: AbstractPSDMatrix, p: torch.Tensor, block_rows: int = 256) -> torch.Tensor:
-    """A @ p with the rows of A evaluated block by block on the device (pes_code.py:502-505); counts N^2 queries."""
+    """A @ p (pes_code.py:500-506, `np.dot(A[blocks[i]:blocks[i+1], :], p)` block by block); counts N^2 queries.
+    KernelMatrix: the fused kernel-times-vector kernel `rpc_kernel_rows_wsum` -- out[i] = sum_j p[j] k(x_j, x_i) with blocks of
+    pivots j resident and all points i streamed, so no block of A is ever written to memory.  Dense PSDMatrix: `rpc_rows_dot`."""
     n = A.shape[0]
     dev = A.device
-    out = torch.empty((n,) + tuple(p.shape[1:]), dtype=torch.float64, device=dev)
-    buf = torch.empty((block_rows, A.n_pad), dtype=torch.float64, device=dev)
-    piv = A._dev_new_payload(block_rows) if hasattr(A, "_dev_new_payload") else None
-    for r0 in range(0, n, block_rows):
-        m = min(block_rows, n - r0)
-        idx = torch.arange(r0, r0 + m, dtype=torch.int64, device=dev)
-        if piv is not None:
-            A._dev_gather(idx, m, piv)
-        A._dev_rows_into(idx, m, piv, C.c_void_p(buf.data_ptr()), A.n_pad)
-        out[r0:r0 + m] = buf[:m, :n] @ p
+    if p.ndim != 1:
+        return torch.stack([kernel_matvec(A, p[:, c].contiguous(), block_rows) for c in range(p.shape[1])], dim=1)
+    if hasattr(A, "_spec"):
+        out = ops.kernel_weighted_sum(A, A._Xd, A._xnorm, n, p.contiguous())[:n]
+    else:
+        out = ops.rows_dot(A._Ad, p.contiguous(), n)
     A._count(n * n)
     return out
 

@@ -678,3 +678,82 @@ def test_nystrom_pcg_matches_oracle(rpc, kernel, kw, bw):
     assert relerr(x, exact) <= 1e-8 and relerr(xw, exact) <= 1e-8
     x0, resid0 = pcg(A, y, mu, None, tol=1e-10, max_iters=80)
     assert len(resid) < len(resid0) or resid[-1] < resid0[-1]              # the preconditioner pays
+
+
+@pytest.mark.parametrize("name", ["pcg_loop_gauss", "pcg_loop_laplace", "pcg_loop_noprecond"])
+def test_pcg_loop_matches_the_reference_statements(rpc, name):
+    """The whole Nystrom-PCG loop against the iterates of the reference's OWN statements (block_experiments/pes_code.py:463-524,
+    executed unchanged at fixture-generation time): same iteration count, same residual history, same solution."""
+    from make_golden_pcg import PCG_CASES, pcg_loop_inputs
+    from randomly_pivoted_cholesky_b200.pcg import NystromPreconditioner, pcg
+    spec, gold = PCG_CASES[name], load(name)
+    X, y = pcg_loop_inputs(spec)
+    A = rpc.KernelMatrix(X, kernel=spec["kernel"], bandwidth=spec["bw"], **spec["kw"])
+    pre = None
+    if spec["k"] > 0:
+        with replay(spec["seed"]):
+            lra = rpc.accelerated_rpcholesky(A, spec["k"], b=spec["b"])
+        pre = NystromPreconditioner(lra, spec["mu"])
+        probe = np.cos(np.arange(spec["N"]) * 0.37)
+        assert relerr(pre(torch.from_numpy(probe).to(A.device)).cpu().numpy(), gold["precond_probe"]) <= 1e-9
+    x, resid = pcg(A, y, spec["mu"], pre, tol=spec["tol"], max_iters=spec["max_iters"])
+    assert len(resid) == len(gold["resid"])
+    np.testing.assert_allclose(resid, gold["resid"], rtol=1e-5, atol=1e-14)
+    assert relerr(x, gold["x"]) <= 1e-7
+
+
+@pytest.mark.parametrize("k,n", [(1, 1000), (37, 5000), (128, 20000), (300, 33331), (1000, 100000)])
+def test_factor_row_products_match_numpy(rpc, k, n):
+    """rpc_syrk_rows (DMMA + tensor-map TMA), rpc_rows_dot, rpc_rows_tdot against numpy on a padded (k, n_pad) factor whose pad
+    columns hold garbage (they must not enter: the tensor map ends at n columns)."""
+    from randomly_pivoted_cholesky_b200 import ops
+    rng = np.random.default_rng(k + n)
+    n_pad = (n + 127) // 128 * 128
+    Rh = rng.standard_normal((k, n_pad))
+    R = torch.from_numpy(Rh).cuda()
+    y, w = rng.standard_normal(n), rng.standard_normal(k)
+    M = ops.syrk_rows(R, n).cpu().numpy()
+    want = Rh[:, :n] @ Rh[:, :n].T
+    assert relerr(M, want) <= 1e-13 and np.array_equal(M, M.T)
+    assert relerr(ops.rows_dot(R, torch.from_numpy(y).cuda(), n).cpu().numpy(), Rh[:, :n] @ y) <= 1e-13
+    assert relerr(ops.rows_tdot(R, torch.from_numpy(w).cuda(), n).cpu().numpy(), Rh[:, :n].T @ w) <= 1e-13
+    # deterministic: fixed-order reductions
+    assert np.array_equal(ops.syrk_rows(R, n).cpu().numpy(), M)
+
+
+@pytest.mark.parametrize("k,m", [(1, 1), (31, 2), (32, 1), (100, 3), (1000, 1)])
+def test_chol_solve_matches_scipy(rpc, k, m):
+    from randomly_pivoted_cholesky_b200 import ops
+    import scipy.linalg
+    rng = np.random.default_rng(k)
+    B = rng.standard_normal((k, k + 5))
+    S = B @ B.T + k * np.eye(k)
+    L = np.linalg.cholesky(S)
+    b = rng.standard_normal((k, m)) if m > 1 else rng.standard_normal(k)
+    got = ops.chol_solve(torch.from_numpy(L).cuda(), torch.from_numpy(b).cuda()).cpu().numpy()
+    np.testing.assert_allclose(got, scipy.linalg.solve(S, b, assume_a="pos"), rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("kernel,kw,d", [("gaussian", {}, 50), ("gaussian", {}, 3), ("matern", {"nu": 2.5}, 7), ("laplace", {}, 12),
+                                         ("laplace", {}, 750), ("gaussian", {"extra_stability": True}, 9)])
+@pytest.mark.parametrize("m", [1, 40, 248, 300, 611])
+def test_fused_kernel_times_vector(rpc, kernel, kw, d, m):
+    """rpc_kernel_rows_wsum (no kernel value written to memory) against the oracle's dense block: both evaluator families, one and
+    several row blocks, the chunked fallback for d = 750, accumulation into an existing vector."""
+    from randomly_pivoted_cholesky_b200 import ops
+    rng = np.random.default_rng(d * 1000 + m)
+    n = 3000 if d < 100 else 900
+    X = rng.standard_normal((n, d))
+    bw = float(d) if kernel == "laplace" else float(np.sqrt(d))
+    A = rpc.KernelMatrix(X, kernel=kernel, bandwidth=bw, **kw)
+    idx = rng.integers(0, n, m)
+    w = rng.standard_normal(m)
+    Kb = orc.OracleKernelMatrix(X, kernel=kernel, bandwidth=bw, **kw).rows(idx)          # (m, n)
+    piv = A._dev_new_payload(m)
+    A._dev_gather(torch.as_tensor(idx, device=A.device), m, piv)
+    wd = torch.from_numpy(w).to(A.device)
+    got = ops.kernel_weighted_sum(A, piv.X, piv.norm, m, wd)
+    assert relerr(got[:n].cpu().numpy(), w @ Kb) <= 1e-12
+    base = torch.from_numpy(rng.standard_normal(A.n_pad)).to(A.device)
+    acc = ops.kernel_weighted_sum(A, piv.X, piv.norm, m, wd, out=base.clone(), accumulate=True)
+    assert relerr(acc[:n].cpu().numpy(), base[:n].cpu().numpy() + w @ Kb) <= 1e-12

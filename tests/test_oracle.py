@@ -205,3 +205,35 @@ def test_pcg_oracle_solves_the_system():
     np.testing.assert_allclose(x, np.linalg.solve(K + mu * np.eye(200), y), rtol=1e-6, atol=1e-8)
     x0, resid0 = pcg_oracle.pcg(K, y, mu, None, tol=1e-10, max_iters=200)
     assert len(resid) < len(resid0)            # the preconditioner pays
+
+
+def pcg_case_operands(spec):
+    """Dense kernel matrix and Nystrom factor of a PCG fixture case, from the oracle (pinned to the reference elsewhere in this file)."""
+    from make_golden_pcg import pcg_loop_inputs
+    X, y = pcg_loop_inputs(spec)
+    A = orc.OracleKernelMatrix(X, kernel=spec["kernel"], bandwidth=spec["bw"], **spec["kw"])
+    K = A.rows(np.arange(spec["N"]))
+    G = None
+    if spec["k"] > 0:
+        rs, lg = orc.make_streams(spec["seed"])
+        G = orc.accelerated_rpcholesky(orc.OracleKernelMatrix(X, kernel=spec["kernel"], bandwidth=spec["bw"], **spec["kw"]),
+                                       spec["k"], spec["b"], rs, lg).G
+    return X, y, K, G
+
+
+@pytest.mark.parametrize("name", ["pcg_loop_gauss", "pcg_loop_laplace", "pcg_loop_noprecond"])
+def test_pcg_oracle_matches_the_reference_loop(name):
+    """The CG loop is pinned: the fixtures hold the iterates of the reference's own statements (pes_code.py:463-524, executed
+    unchanged by tests/golden/make_golden_pcg.py); the numpy restatement reproduces the iteration count, every residual and x."""
+    from make_golden_pcg import PCG_CASES
+    from oracle import pcg_oracle
+    spec, gold = PCG_CASES[name], load(name)
+    X, y, K, G = pcg_case_operands(spec)
+    pre = pcg_oracle.nystrom_preconditioner(G, spec["mu"]) if G is not None else None
+    x, resid = pcg_oracle.pcg(K, y, spec["mu"], pre, tol=spec["tol"], max_iters=spec["max_iters"])
+    assert len(resid) == len(gold["resid"])
+    np.testing.assert_allclose(resid, gold["resid"], rtol=1e-5, atol=1e-14)
+    assert relerr(x, gold["x"]) <= 1e-7
+    if pre is not None:
+        probe = np.cos(np.arange(spec["N"]) * 0.37)
+        assert relerr(pre(probe), gold["precond_probe"]) <= 1e-9
