@@ -23,7 +23,7 @@ PCG_CASES = {
     # name: kernel, kw, bandwidth, N, d, k, b, mu, tol, max_iters, seed
     "pcg_loop_gauss": dict(kernel="gaussian", kw={}, bw=2.0, N=700, d=5, k=160, b=32, mu=1e-1, tol=1e-9, max_iters=60, seed=11),
     "pcg_loop_laplace": dict(kernel="laplace", kw={}, bw=6.0, N=520, d=6, k=60, b=12, mu=5e-2, tol=1e-8, max_iters=80, seed=12),
-    "pcg_loop_noprecond": dict(kernel="matern", kw={"nu": 1.5}, bw=2.5, N=400, d=3, k=0, b=0, mu=1e-1, tol=1e-7, max_iters=120, seed=13),
+    "pcg_loop_noprecond": dict(kernel="matern", kw={"nu": 1.5}, bw=1.0, N=400, d=3, k=0, b=0, mu=2.0, tol=1e-8, max_iters=120, seed=13),
 }
 
 
