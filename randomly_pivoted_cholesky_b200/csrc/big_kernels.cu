@@ -41,10 +41,16 @@ typedef Cfg<4, 2, 5, 4> C160;   // 160 x 64
 // above 128 rows: 2 x 4 warps of (MI x 2) fragments, N tile 64; ODD tiles give 8-row steps (Schur update only)
 #define RPC_FINE_TILES(X) X(136, 9, true) X(144, 9, false) X(152, 10, true) X(160, 10, false) X(168, 11, true) \
     X(176, 11, false) X(184, 12, true) X(192, 12, false) X(200, 13, true) X(208, 13, false) X(216, 14, true) \
-    X(224, 14, false) X(232, 15, true) X(240, 15, false) X(248, 16, true)
+    X(224, 14, false) X(232, 15, true) X(240, 15, false) X(248, 16, true)                                       \
+    X(72, 5, true) X(80, 5, false) X(88, 6, true) X(104, 7, true) X(112, 7, false) X(120, 8, true)
 #define RPC_DECL_TILE(M, MI, ODD) typedef Cfg<2, 4, MI, 2, ODD> F##M;
 RPC_FINE_TILES(RPC_DECL_TILE)
 #undef RPC_DECL_TILE
+// short updates (the truncated last round of a factorisation, small blocks): 1 x 8 warps of (MI x 2) fragments, N tile 128
+#define RPC_SHORT_TILES(X) X(24, 3) X(40, 5) X(48, 6) X(56, 7)
+#define RPC_DECL_SHORT(M, MI) typedef Cfg<1, 8, MI, 2> F##M;
+RPC_SHORT_TILES(RPC_DECL_SHORT)
+#undef RPC_DECL_SHORT
 typedef Cfg<2, 4, 8, 4> C128;   // 128 x 128
 typedef Cfg<2, 4, 6, 4> C96;    //  96 x 128
 typedef Cfg<2, 4, 4, 4> C64;    //  64 x 128
@@ -52,7 +58,7 @@ typedef Cfg<1, 8, 4, 2> C32;    //  32 x 128
 typedef Cfg<1, 8, 2, 2> C16;    //  16 x 128
 
 static int tile_rows_for(int m, bool fine = false) {
-    if (fine && m > 128) return m <= 256 ? (m + 7) / 8 * 8 : 256;         // 136, 144, ..., 256
+    if (fine && m > 16) return m <= 256 ? (m + 7) / 8 * 8 : 256;          // 24, 32, ..., 256 (Schur update: 8-row steps)
     const int tiles[] = {16, 32, 64, 96, 128, 160, 192, 224, 256};
     for (int t : tiles) if (m <= t) return t;
     return 256;
@@ -65,6 +71,9 @@ static int dispatch_gemm(rpc_ctx *ctx, cudaStream_t st, const Params &p, int m, 
 #define RPC_CASE_TILE(M, MI, ODD) case M: return launch_gemm<F##M, MODE_SCHUR>(ctx, st, p, n_pad);
             RPC_FINE_TILES(RPC_CASE_TILE)
 #undef RPC_CASE_TILE
+#define RPC_CASE_SHORT(M, MI) case M: return launch_gemm<F##M, MODE_SCHUR>(ctx, st, p, n_pad);
+            RPC_SHORT_TILES(RPC_CASE_SHORT)
+#undef RPC_CASE_SHORT
             default: break;
         }
     }
@@ -88,6 +97,9 @@ static int panel_ld_for(int m, bool fine = false) {
 #define RPC_LD_TILE(M, MI, ODD) case M: return F##M::LDA;
             RPC_FINE_TILES(RPC_LD_TILE)
 #undef RPC_LD_TILE
+#define RPC_LD_SHORT(M, MI) case M: return F##M::LDA;
+            RPC_SHORT_TILES(RPC_LD_SHORT)
+#undef RPC_LD_SHORT
             default: break;
         }
     }

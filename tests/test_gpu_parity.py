@@ -264,7 +264,8 @@ def test_shifted_cholesky_and_failure_flag(rpc):
     assert info == 8
 
 
-@pytest.mark.parametrize("c,s", [(0, 1), (0, 40), (5, 3), (37, 16), (100, 64), (130, 130), (64, 200), (300, 256), (50, 300)])
+@pytest.mark.parametrize("c,s", [(0, 1), (0, 40), (5, 3), (37, 16), (100, 64), (130, 130), (64, 200), (300, 256), (50, 300),
+                                 (20, 23), (10, 50), (33, 72), (70, 88), (12, 104), (99, 118), (7, 56), (0, 248), (3, 136)])
 def test_schur_update_matches_numpy(rpc, c, s):
     """G_new = L^{-1}(rows - P^T G[:c]) and the fused diagonal update, against numpy (fp64)."""
     from randomly_pivoted_cholesky_b200 import ops
