@@ -316,8 +316,9 @@ def gpu_arm(args, w):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+    # stdout carries the ONE JSON line: whatever NCCL is asked to log (it writes to stdout by default, "NCCL version ..." included)
+    # goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     rpc.load()

@@ -117,7 +117,7 @@ class _State:
         self.rows = torch.empty((k, self.n_pad), **f64)
         self.diag = torch.empty((self.n_pad,), **f64)
         self.m_max = m_max
-        self.u_dev = torch.empty((2 * m_max,), **f64)
+        self.u_dev = torch.empty((4 * m_max,), **f64)            # two slots of [proposal | rejection] uniforms (prefetch)
         self.idx_dev = torch.empty((m_max,), dtype=torch.int64, device=self.dev)
         self.sel_dev = torch.empty((m_max,), dtype=torch.int64, device=self.dev)
         self.stats = torch.zeros((4,), **f64)
@@ -153,12 +153,12 @@ class _State:
         self.k_pad_max = _round_up(k + m_max, KT)
         self.At = torch.empty((self.k_pad_max * (_round_up(m_max, AT_LD_ALIGN) + 16),), **f64)   # panel, per-round ld
         # pinned staging
-        self.u_host = torch.empty((2 * m_max,), dtype=torch.float64).pin_memory()
+        self.u_host = torch.empty((4 * m_max,), dtype=torch.float64).pin_memory()
         self.sel_host = torch.empty((m_max,), dtype=torch.int64).pin_memory()
         self.rb_host = None
         self.spec = False
         self.draw_stream = None                # sharded: side stream of the uniform upload + broadcast
-        self.ev_u_free = None
+        self.ev_draw = [None, None]            # per slot: the upload (+ broadcast) of the slot's uniforms has completed
         A._dev_diag_into(self.diag)
         A._count(self.n)                                       # A.diag() counts N queries (matrix.py:33-39)
 
@@ -202,30 +202,37 @@ class _State:
         return out[0:4], out[4:8].astype(np.int64), out[8:8 + m].astype(np.int64), out[8 + m:8 + 2 * m].astype(np.int64)
 
     # ---- thin wrappers over the C ABI ------------------------------------------------------------
-    def upload_uniforms(self, up, ur=None):
-        """u_dev <- [proposal uniforms | rejection uniforms].  Row-sharded runs use RANK 0's draws on every rank (the
-        reference's generators are unseeded, so nothing else makes the ranks' streams agree): upload + broadcast run on a
-        side stream, beside the previous round's Schur update, and the sampler waits for them."""
+    def upload_uniforms(self, up, ur=None, slot=0):
+        """u_dev[slot] <- [proposal uniforms | rejection uniforms]; returns the slot's offset into u_dev.  Row-sharded runs use
+        RANK 0's draws on every rank (the reference's generators are unseeded, so nothing else makes the ranks' streams agree):
+        upload + broadcast run on a side stream and `wait_uniforms(slot)` makes the consumer wait for them.  With two slots the
+        accelerated driver issues round t+1's upload at the start of round t, so the broadcast never sits between the Schur
+        update (whose persistent CTAs leave no room for the NCCL kernel) and the next sampler."""
         m = len(up)
-        self.u_host[:m] = torch.from_numpy(up)
+        off = slot * 2 * self.m_max
+        self.u_host[off:off + m] = torch.from_numpy(up)
         tot = m
         if ur is not None:
-            self.u_host[m:m + len(ur)] = torch.from_numpy(ur)
+            self.u_host[off + m:off + m + len(ur)] = torch.from_numpy(ur)
             tot = m + len(ur)
         if self.info.world == 1 or self.dev.type != "cuda":
-            self.u_dev[:tot].copy_(self.u_host[:tot], non_blocking=True)
-            rdist.broadcast_draws(self.info, self.u_dev[:tot])
-            return
+            self.u_dev[off:off + tot].copy_(self.u_host[off:off + tot], non_blocking=True)
+            rdist.broadcast_draws(self.info, self.u_dev[off:off + tot])
+            self.ev_draw[slot] = None
+            return off
         if self.draw_stream is None:
             self.draw_stream = torch.cuda.Stream(device=self.dev)
-            self.ev_draw = torch.cuda.Event()
-        if self.ev_u_free is not None:
-            self.draw_stream.wait_event(self.ev_u_free)        # the last kernel that read the previous round's uniforms
         with torch.cuda.stream(self.draw_stream):
-            self.u_dev[:tot].copy_(self.u_host[:tot], non_blocking=True)
-            rdist.broadcast_draws(self.info, self.u_dev[:tot])
-            self.ev_draw.record(self.draw_stream)
-        torch.cuda.current_stream().wait_event(self.ev_draw)
+            self.u_dev[off:off + tot].copy_(self.u_host[off:off + tot], non_blocking=True)
+            rdist.broadcast_draws(self.info, self.u_dev[off:off + tot])
+            self.ev_draw[slot] = torch.cuda.Event()
+            self.ev_draw[slot].record(self.draw_stream)
+        return off
+
+    def wait_uniforms(self, slot=0):
+        if self.ev_draw[slot] is not None:
+            torch.cuda.current_stream().wait_event(self.ev_draw[slot])
+            self.ev_draw[slot] = None
 
     def sample(self, m, u_off=0):
         """Every rank samples on the FULL residual diagonal (all-gathered when sharded): identical pivots everywhere."""
@@ -286,9 +293,6 @@ class _State:
         check(self.lib.rpc_rejection_cholesky(self.ctx.handle, _stream(), _ptr(self.H), m, self.m_max, u, max_accept, mode,
                                               float(shift), _ptr(self.L), self.m_max, _ptr(self.acc), _ptr(self.info_dev)),
               "rpc_rejection_cholesky")
-        if self.draw_stream is not None:
-            self.ev_u_free = torch.cuda.Event()
-            self.ev_u_free.record()
 
     # ---- speculative evaluation of all proposals beside the rejection Cholesky (accelerated, sharded) ---------------------
     def enable_speculation(self):
@@ -319,9 +323,10 @@ class _State:
             self.ev_eval.record(self.side)
 
     def launch_row_gather(self, c, m):
-        """rows[c:c+s] = rows_all[acc[:s]] on the side stream (s read on the device), beside the panel solve / Schur update."""
+        """rows[c:c+s] = rows_all[acc[:s]] on the side stream (s read on the device), once this round's Schur update has drained:
+        the copy overlaps the next round's sampler; the next rejection kernel (which overwrites acc) waits for it."""
         main = torch.cuda.current_stream()
-        self.ev_rej.record(main)
+        self.ev_rej.record(main)                              # recorded behind the Schur update (which only reads rows_all / acc)
         self.side.wait_event(self.ev_rej)
         with torch.cuda.stream(self.side):
             check(self.lib.rpc_gather_rows(self.ctx2.handle, _stream(), _ptr(self.rows_all), self.n_pad, _ptr(self.acc),
@@ -569,6 +574,7 @@ def block_cholesky_helper(A, k, b, alg, stoptol=1e-14, strategy="regularize", rb
         if alg == "rp":
             up = rng.random(2 * block_size)                    # rng.choice(..., size=2*block_size) (:91)
             st.upload_uniforms(up)
+            st.wait_uniforms()
             st.sample(2 * block_size)
         else:
             # np.argpartition(diags, -block_size)[-block_size:] (:94-95): the set of the block_size largest residuals
@@ -656,14 +662,30 @@ def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
     orig_trace = None
     count = k
     rounds = []
+    # Row-sharded runs with a fixed b draw (and upload + broadcast) round t+1's uniforms at the start of round t.  The two numpy
+    # streams are state independent, so the values are the ones the reference would draw; if round t+1 never happens the legacy
+    # stream is put back where the reference leaves it.
+    prefetch = st.info.world > 1 and not auto_b
+    ahead = None                                               # (slot offset, legacy state before the draw) of the next round
+
+    def draw_round(slot):
+        up = rng.random(b)                                     # :184
+        state = np.random.get_state()
+        ur = np.random.random_sample(b)                        # the b np.random.rand() calls of :151
+        return st.upload_uniforms(up, ur, slot), state
+
+    slot = 0
     while counter < k:
         t0 = time.perf_counter()
-        up = rng.random(b)                                     # :184
-        legacy_state = np.random.get_state()
-        ur = np.random.random_sample(b)                        # the b np.random.rand() calls of :151
-        st.upload_uniforms(up, ur)
+        if ahead is None:
+            u_off, legacy_state = draw_round(slot)
+        else:
+            u_off, legacy_state = ahead
+        st.wait_uniforms(slot)
+        if prefetch:
+            ahead = draw_round(slot ^ 1)
         with _timed("sample", 0.0, 16.0 * st.n):
-            st.sample(b)
+            st.sample(b, u_off)
         with _timed("gram", 2.0 * b * b * counter, 8.0 * counter * b):
             st.gather(st.idx_dev, b, counter)
             st.residual_block(st.idx_dev, b, counter)              # :189
@@ -673,10 +695,8 @@ def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
             st.launch_eval_all(b)
         st.wait_row_gather()                                       # the previous round's row compaction still reads acc
         with _timed("reject", b ** 3 / 3.0, 8.0 * b * b):
-            st.cholesky(b, 0, k - counter, 0.0, b)                 # :190 + truncation :193-196
+            st.cholesky(b, 0, k - counter, 0.0, u_off + b)         # :190 + truncation :193-196
         st.publish(b)
-        if st.spec:
-            st.launch_row_gather(counter, b)
         with _timed("panel", 1.0 * b * b * counter, 8.0 * counter * b):
             st.prelaunch_panel(counter, b)                         # runs while the host wakes up
         stats_host, info, acc_host, idx_host = st.collect(b)                        # the round's only sync
@@ -685,6 +705,7 @@ def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
             orig_trace = float(stats_host[0])
         elif stoptol > 0 and float(stats_host[0]) <= stoptol * orig_trace:          # :224-227
             np.random.set_state(legacy_state)                  # this round never happens in the reference
+            ahead = None
             A.queries -= b * b
             count = counter
             break
@@ -697,7 +718,12 @@ def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
         t1 = time.perf_counter()
         if num_sel > 0:
             st.update(counter, num_sel, st.acc, st.idx_dev, panel_done=True, spec_rows=st.spec)
+        if st.spec:
+            # rows[c:c+s] <- the accepted rows of rows_all, on the side stream once the Schur update has drained: the copy then
+            # runs beside the NEXT round's sampler (idle SMs) instead of beside this round's panel solve
+            st.launch_row_gather(counter, b)
         counter += num_sel
+        slot ^= 1
         rounds.append(num_sel)
         if auto_b:                                             # :211-220, on device-synchronised wall time
             torch.cuda.synchronize(st.dev)
@@ -715,6 +741,8 @@ def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
             sh = st.stats.cpu().numpy()
             if float(sh[0]) <= stoptol * orig_trace:
                 count = counter
+    if ahead is not None:
+        np.random.set_state(ahead[1])                          # the prefetched round does not exist in the reference
     res = st.result(min(count, counter), arr_idx)
     res.rounds = rounds
     return res
