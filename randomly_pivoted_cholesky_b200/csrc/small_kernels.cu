@@ -1028,21 +1028,34 @@ extern "C" int rpc_pivoted_cholesky(rpc_ctx *ctx, void *stream, const double *H,
 __global__ void __launch_bounds__(256) gather_rows_kernel(const double *__restrict__ src, int64_t lds, const int32_t *__restrict__ rowmap,
                                                           const int32_t *__restrict__ count, double *__restrict__ dst, int64_t ldd,
                                                           int64_t n_pad) {
-    const int i = blockIdx.y;
-    if (i >= *count) return;
-    const double2 *s2 = reinterpret_cast<const double2 *>(src + (int64_t)rowmap[i] * lds);
-    double2 *d2 = reinterpret_cast<double2 *>(dst + (int64_t)i * ldd);
-    for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < n_pad / 2; q += (int64_t)gridDim.x * 256) d2[q] = s2[q];
+    // A FEW persistent CTAs (the launch leaves most SM slots free: the copy runs beside the next round's sampler, whose many small
+    // launches must not queue behind it), eight 16-byte loads in flight per thread.
+    const int rows = *count;
+    const int64_t per_row = n_pad / 2;                                   // double2 elements per row
+    const int64_t step = (int64_t)gridDim.x * 256;
+    for (int i = 0; i < rows; ++i) {
+        const double2 *s2 = reinterpret_cast<const double2 *>(src + (int64_t)rowmap[i] * lds);
+        double2 *d2 = reinterpret_cast<double2 *>(dst + (int64_t)i * ldd);
+        int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x;
+        for (; q + 7 * step < per_row; q += 8 * step) {
+            double2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = s2[q + u * step];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) d2[q + u * step] = v[u];
+        }
+        for (; q < per_row; q += step) d2[q] = s2[q];
+    }
 }
 
 extern "C" int rpc_gather_rows(rpc_ctx *ctx, void *stream, const double *src, int64_t lds, const int32_t *rowmap,
                                const int32_t *count_dev, int max_rows, double *dst, int64_t ldd, int64_t n_pad) {
     RPC_CHECK_ARG(ctx && src && rowmap && count_dev && dst, "null pointer");
     RPC_CHECK_ARG(max_rows >= 1 && n_pad > 0 && n_pad % 2 == 0 && lds % 2 == 0 && ldd % 2 == 0, "bad sizes");
-    int gx = (int)((n_pad / 2 + 256 * 8 - 1) / (256 * 8));
+    int gx = (int)((n_pad / 2 + 256 * 4 - 1) / (256 * 4));
     if (gx < 1) gx = 1;
-    if (gx > 64) gx = 64;
-    gather_rows_kernel<<<dim3(gx, max_rows), 256, 0, (cudaStream_t)stream>>>(src, lds, rowmap, count_dev, dst, ldd, n_pad);
+    if (gx > ctx->sm_count / 2) gx = ctx->sm_count / 2;                 // one CTA on every other SM at most
+    gather_rows_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>(src, lds, rowmap, count_dev, dst, ldd, n_pad);
     RPC_LAUNCHED(ctx);
     return 0;
 }
