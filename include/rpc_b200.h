@@ -270,6 +270,15 @@ int rpc_kernel_rows_wsum(rpc_ctx *ctx, void *stream, const rpc_kernel_spec *spec
  * flops_per_launch; the caller times it with CUDA events on `stream`.  Replaces no reference call site. */
 int rpc_probe_fp64_peak(rpc_ctx *ctx, void *stream, int iters, double *flops_per_launch_host);
 
+/* rpc_schur_update_ex that ALSO writes the new rows it consumes to rows_out[i, :] = rows_src[rowmap[i], :], i < s: with
+ * speculatively evaluated proposal rows (rows_src = the rows of all b proposals, rowmap = the accepted positions) this is
+ * `rows[c:c+s] = A[S,:]` of rpcholesky.py:205 at no extra pass over memory -- the kernel copies each B stage of new rows out of
+ * shared memory while it multiplies it. */
+int rpc_schur_update_rows(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At, int64_t ldat,
+                          int k_pad, const double *rows_src, int64_t ldr, const int32_t *rowmap, double *rows_out,
+                          int64_t ld_rows_out, double *diag, int64_t n_pad, const struct rpc_peers *peers,
+                          unsigned long long epoch, int panel_lower);
+
 /* ---- peer-memory exchange for row-sharded runs (one process per GPU of one NVSwitch box) --------------------------
  * The two per-round exchanges of the sharded factorisation (the residual-diagonal all-gather and
  * the pivot-payload exchange) are done by the producing kernels themselves: they store their results straight into every

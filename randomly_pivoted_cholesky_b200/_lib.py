@@ -127,6 +127,8 @@ _SIGNATURES = {
     "rpc_gather_rows": (_INT, [_P, _P, _P, _I64, _P, _P, _INT, _P, _I64, _I64]),
     "rpc_schur_update_ex": (_INT, [_P, _P, _P, _I64, _INT, _INT, _P, _I64, _INT, _P, _I64, _P, _P, _I64, C.POINTER(Peers),
                                    C.c_uint64, _INT]),
+    "rpc_schur_update_rows": (_INT, [_P, _P, _P, _I64, _INT, _INT, _P, _I64, _INT, _P, _I64, _P, _P, _I64, _P, _I64, C.POINTER(Peers),
+                                     C.c_uint64, _INT]),
     "rpc_peer_alloc": (_INT, [_P, _I64, C.POINTER(_P), _P]),
     "rpc_peer_free": (_INT, [_P, _P]),
     "rpc_peer_open": (_INT, [_P, _P, C.POINTER(_P)]),

@@ -185,8 +185,10 @@ static bool g_no_tri = getenv("RPC_B200_NO_TRI") != nullptr;         // diagnost
 
 static int schur_update_impl(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At, int64_t ldat,
                              int k_pad, const double *rows_new, int64_t ldr, const int32_t *rowmap, double *diag, int64_t n_pad,
-                             const rpc_peers *peers, unsigned long long epoch, int panel_lower) {
+                             const rpc_peers *peers, unsigned long long epoch, int panel_lower, double *rows_out = nullptr,
+                             int64_t ld_rows_out = 0) {
     RPC_CHECK_ARG(ctx && G && At && rows_new && diag, "null pointer");
+    RPC_CHECK_ARG(!rows_out || (ld_rows_out >= n_pad && ld_rows_out % 2 == 0), "rows_out needs an even leading dimension >= n_pad");
     const int tri = (panel_lower && !g_no_tri) ? 1 : 0;
     RPC_CHECK_ARG(s >= 1 && c >= 0, "s >= 1, c >= 0");
     RPC_CHECK_ARG(n_pad > 0 && n_pad % RPC_COL_ALIGN == 0, "n_pad must be a positive multiple of RPC_COL_ALIGN");
@@ -223,6 +225,7 @@ static int schur_update_impl(rpc_ctx *ctx, void *stream, double *G, int64_t ldg,
             p.G = G; p.ldg = ldg; p.c = c; p.R = rows_new; p.ldr = ldr; p.K = c + s; p.rowmap = rowmap;
             p.Cout = G + (int64_t)c * ldg; p.ldc = ldg; p.diag = diag;
             p.tri = tri; p.row_base = 0;
+            p.rows_out = rows_out; p.ld_rows_out = ld_rows_out;
             if (peers) {
                 p.npeers = peers->world;
                 for (int r = 0; r < peers->world; ++r) {
@@ -271,6 +274,7 @@ static int schur_update_impl(rpc_ctx *ctx, void *stream, double *G, int64_t ldg,
         p.G = G; p.ldg = ldg; p.c = c; p.R = rows_new; p.ldr = ldr; p.K = c + s; p.rowmap = rowmap;
         p.Cout = G + (int64_t)(c + m0) * ldg; p.ldc = ldg; p.diag = diag;
         p.tri = tri; p.row_base = m0;
+        if (m0 == 0) { p.rows_out = rows_out; p.ld_rows_out = ld_rows_out; }      // every row chunk streams all K rows: one copies
         if (peers && m0 + 256 >= s) {
             // the last row chunk leaves the final diagonal: it stores it into every rank's copy and publishes the epoch
             p.npeers = peers->world;
@@ -301,6 +305,15 @@ extern "C" int rpc_schur_update_ex(rpc_ctx *ctx, void *stream, double *G, int64_
                                    int panel_lower) {
     return schur_update_impl(ctx, stream, G, ldg, c, s, At, ldat, k_pad, rows_src, ldr, rowmap, diag, n_pad, peers, epoch,
                              panel_lower);
+}
+
+extern "C" int rpc_schur_update_rows(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At,
+                                     int64_t ldat, int k_pad, const double *rows_src, int64_t ldr, const int32_t *rowmap,
+                                     double *rows_out, int64_t ld_rows_out, double *diag, int64_t n_pad, const rpc_peers *peers,
+                                     unsigned long long epoch, int panel_lower) {
+    RPC_CHECK_ARG(rows_out != nullptr, "rows_out required (use rpc_schur_update_ex otherwise)");
+    return schur_update_impl(ctx, stream, G, ldg, c, s, At, ldat, k_pad, rows_src, ldr, rowmap, diag, n_pad, peers, epoch,
+                             panel_lower, rows_out, ld_rows_out);
 }
 
 extern "C" int rpc_schur_update_peers(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At,

@@ -83,6 +83,12 @@ struct Params {
     // j < i, so output row j only needs the k range kk <= c + j and the DMMAs of the structurally-zero half are skipped.
     // row_base = panel column (= row of the whole update) of this launch's row 0 (row chunks of updates with s > 256).
     int tri, row_base;
+    // rows_out != NULL (speculative row evaluation: R holds the rows of ALL proposals, the new rows are picked through rowmap):
+    // the kernel also writes new row i to rows_out[i, :] -- the B stages it fetches for kk >= c ARE those rows, so the
+    // compaction rows[c:c+s] = rows_all[acc] costs no extra pass over memory (it used to be a separate copy kernel that
+    // collided with the panel solve or the next sampler)
+    double *rows_out;
+    int64_t ld_rows_out;
     double *Cout;
     int64_t ldc;
     double *diag;
@@ -311,6 +317,19 @@ __device__ __forceinline__ void consume_stage_tri(double (&acc)[C::MI][C::NI][2]
     else consume_stage_tri_n<C, C::MI>(acc, As, Bs, lk, first);
 }
 
+// The warps of warp row 0 copy the new rows held by a k-major B stage (panel rows kk in [c, K)) out to rows_out: lane -> stage
+// row lane >> 1 and one half of the warp's NI * 8 columns, 16-byte accesses.
+template <class C>
+__device__ __forceinline__ void store_new_rows(const Params &p, const double *Bs_stage, int k0, int64_t col0, int n0, int lane) {
+    const int r = lane >> 1, h = lane & 1;
+    const int kk = k0 + r;
+    if (kk < p.c || kk >= p.K) return;
+    const double *src = Bs_stage + r * C::LDB + n0 + h * (C::NI * 4);
+    double *dst = p.rows_out + (int64_t)(kk - p.c) * p.ld_rows_out + col0 + n0 + h * (C::NI * 4);
+#pragma unroll
+    for (int q = 0; q < C::NI * 2; ++q) *reinterpret_cast<double2 *>(dst + 2 * q) = *reinterpret_cast<const double2 *>(src + 2 * q);
+}
+
 // kernel values from the x.y accumulators -> Cout (MODE_EVAL and phase 1 of MODE_FUSED)
 template <class C>
 __device__ __forceinline__ void eval_epilogue(const Params &p, double (&acc)[C::MI][C::NI][2], double *out, int64_t ldo,
@@ -525,6 +544,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
                 else
                     consume_stage<C, 0>(acc, As_base + s * C::A_STAGE + m0 + lr, Bs_base + s * C::B_STAGE + n0 + lr, 0, lk,
                                         live_ksteps(kt, k_real), mi_cnt);
+                if (MODE == MODE_SCHUR && p.rows_out && wm == 0 && chunk == 0 && kt * KT + KT > p.c)
+                    store_new_rows<C>(p, Bs_base + s * C::B_STAGE, kt * KT, col0, n0, lane);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);         // this warp is done reading the stage

@@ -306,7 +306,6 @@ class _State:
             self.ctx._side = (_lib.Context.extra(self.dev.index), torch.cuda.Stream(device=self.dev))   # stream must not
         self.ctx2, self.side = self.ctx._side                 # share the main workspace) and the side stream
         self.ev_fork, self.ev_eval = torch.cuda.Event(), torch.cuda.Event()
-        self.ev_rej, self.ev_copy = torch.cuda.Event(), None
 
     def launch_eval_all(self, m):
         """rows_all[:m] = A[idx, :] on the side stream, one SM left free for the rejection kernel."""
@@ -321,24 +320,6 @@ class _State:
                                                self.n_pad, A.d_pad, A.ldx, _ptr(self.piv.X), _ptr(self.piv.norm), m, A.ldx,
                                                _ptr(self.rows_all), self.n_pad), "rpc_kernel_rows")
             self.ev_eval.record(self.side)
-
-    def launch_row_gather(self, c, m):
-        """rows[c:c+s] = rows_all[acc[:s]] on the side stream (s read on the device), once this round's Schur update has drained:
-        the copy overlaps the next round's sampler; the next rejection kernel (which overwrites acc) waits for it."""
-        main = torch.cuda.current_stream()
-        self.ev_rej.record(main)                              # recorded behind the Schur update (which only reads rows_all / acc)
-        self.side.wait_event(self.ev_rej)
-        with torch.cuda.stream(self.side):
-            check(self.lib.rpc_gather_rows(self.ctx2.handle, _stream(), _ptr(self.rows_all), self.n_pad, _ptr(self.acc),
-                                           _ptr(self.info_dev), m, C.c_void_p(self.rows.data_ptr() + 8 * c * self.n_pad),
-                                           self.n_pad, self.n_pad), "rpc_gather_rows")
-            self.ev_copy = torch.cuda.Event()
-            self.ev_copy.record(self.side)
-
-    def wait_row_gather(self):
-        if self.spec and self.ev_copy is not None:
-            torch.cuda.current_stream().wait_event(self.ev_copy)
-            self.ev_copy = None
 
     def prelaunch_panel(self, c, s_max):
         """Panel solve + compaction of the accepted pivots with the accepted count read on the device (info_dev[0]):
@@ -383,7 +364,8 @@ class _State:
             # the rows of all proposals were evaluated on the side stream; the accepted ones are read through acc
             torch.cuda.current_stream().wait_event(self.ev_eval)
             A._count(s * self.n)
-            self._schur(c, s, ldat, k_pad, _ptr(self.rows_all), _ptr(self.acc), panel_mode == 0)
+            self._schur(c, s, ldat, k_pad, _ptr(self.rows_all), _ptr(self.acc), panel_mode == 0,
+                        rows_out=C.c_void_p(self.rows.data_ptr() + 8 * c * self.n_pad))
             return
         spec = getattr(A, "_spec", None)
         if USE_FUSED and spec is not None and self.lib.rpc_fused_update_supported(C.byref(spec), s, A.ldx):
@@ -400,7 +382,7 @@ class _State:
         A._count(s * self.n)
         self._schur(c, s, ldat, k_pad, rows_ptr, None, panel_mode == 0)
 
-    def _schur(self, c, s, ldat, k_pad, rows_src, rowmap, panel_lower=True):
+    def _schur(self, c, s, ldat, k_pad, rows_src, rowmap, panel_lower=True, rows_out=None):
         """G[c:c+s] = At^T [G[:c]; rows_new], diag update; new row i is rows_src[rowmap[i]] (rowmap None: rows_src[i]).
         Sharded with peer windows: the kernel also stores the new diagonal into every rank's copy and publishes the epoch.
         Algorithmic work: s (2c + s) N flops; reads G[:c] and rows_new, writes G_new."""
@@ -413,16 +395,21 @@ class _State:
         # the s x s block is a full product
         flops = (1.0 * s * (2 * c + s) if panel_lower else 2.0 * s * (c + s)) * n
         with _timed("schur", flops, 8.0 * n * (c + 2 * s + 2), (c, s, self.n_pad) if panel_lower else None):
-            check(self.lib.rpc_schur_update_ex(self.ctx.handle, _stream(), _ptr(self.G), self.n_pad, c, s, _ptr(self.At), ldat,
-                                               k_pad, rows_src, self.n_pad, rowmap, _ptr(self.diag), self.n_pad, peers, epoch,
-                                               1 if panel_lower else 0),
-                  "rpc_schur_update_ex")
+            if rows_out is not None:
+                # speculative rows: the kernel also writes rows[c:c+s] = rows_all[acc] from the stages it multiplies
+                check(self.lib.rpc_schur_update_rows(self.ctx.handle, _stream(), _ptr(self.G), self.n_pad, c, s, _ptr(self.At), ldat,
+                                                     k_pad, rows_src, self.n_pad, rowmap, rows_out, self.n_pad, _ptr(self.diag),
+                                                     self.n_pad, peers, epoch, 1 if panel_lower else 0), "rpc_schur_update_rows")
+            else:
+                check(self.lib.rpc_schur_update_ex(self.ctx.handle, _stream(), _ptr(self.G), self.n_pad, c, s, _ptr(self.At), ldat,
+                                                   k_pad, rows_src, self.n_pad, rowmap, _ptr(self.diag), self.n_pad, peers, epoch,
+                                                   1 if panel_lower else 0),
+                      "rpc_schur_update_ex")
         self.diag_pending = self.peer is not None
 
     def result(self, count, arr_idx):
         # sharded: keep the whole padded shard (equal widths on all ranks, so `.G` can all-gather); else cut to N
         nl = self.n_pad if self.info.world > 1 else self.n_loc
-        self.wait_row_gather()
         if self.peer is not None and int(self.info_dev[3].item()) != 0:
             raise RuntimeError("peer-memory exchange timed out waiting for another rank's epoch")
         return PSDLowRank(self.G[:count, :nl], n=self.n, idx=arr_idx, rows=self.rows[:count, :nl], shard_info=self.info)
@@ -693,7 +680,6 @@ def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
             # side stream, forked behind the (many-CTA) Gram kernels: the 147-CTA evaluation then runs beside the
             # single-CTA rejection kernel only
             st.launch_eval_all(b)
-        st.wait_row_gather()                                       # the previous round's row compaction still reads acc
         with _timed("reject", b ** 3 / 3.0, 8.0 * b * b):
             st.cholesky(b, 0, k - counter, 0.0, u_off + b)         # :190 + truncation :193-196
         st.publish(b)
@@ -718,10 +704,6 @@ def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
         t1 = time.perf_counter()
         if num_sel > 0:
             st.update(counter, num_sel, st.acc, st.idx_dev, panel_done=True, spec_rows=st.spec)
-        if st.spec:
-            # rows[c:c+s] <- the accepted rows of rows_all, on the side stream once the Schur update has drained: the copy then
-            # runs beside the NEXT round's sampler (idle SMs) instead of beside this round's panel solve
-            st.launch_row_gather(counter, b)
         counter += num_sel
         slot ^= 1
         rounds.append(num_sel)

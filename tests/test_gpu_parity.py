@@ -319,14 +319,16 @@ def test_schur_update_tail_of_the_tile_waves(rpc, c, s, left):
     assert np.array_equal(G[:c].cpu().numpy(), Gh[:c])
 
 
-def test_speculative_rows_and_tail_launch_against_oracle(rpc, monkeypatch):
+@pytest.mark.parametrize("shape", ["tail", "row_chunks"])
+def test_speculative_rows_and_tail_launch_against_oracle(rpc, monkeypatch, shape):
     """The >= 4-GPU code path forced on one GPU: all proposals evaluated on the side stream, accepted rows read through the
-    row map, on a shape whose Schur update also takes the row-chunked tail launch."""
+    row map and written to rows[c:c+s] by the Schur kernel itself, on a shape whose Schur update also takes the row-chunked tail
+    launch, and on one with more than 256 accepted pivots per round (row chunks: only the first chunk writes the rows)."""
     import importlib
     drivers = importlib.import_module("randomly_pivoted_cholesky_b200.rpcholesky")     # the module, not the function
     monkeypatch.setattr(drivers, "USE_SPEC", "1")
     sms = torch.cuda.get_device_properties(0).multi_processor_count
-    n, d, k, b = (4 * sms + 30) * 64 - 5, 9, 500, 200
+    n, d, k, b = ((4 * sms + 30) * 64 - 5, 9, 500, 200) if shape == "tail" else (24000, 6, 1400, 640)
     X = np.random.default_rng(17).standard_normal((n, d))
     bw = float(np.sqrt(d))
     A = rpc.KernelMatrix(X, kernel="gaussian", bandwidth=bw)
