@@ -164,6 +164,14 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// shared -> global bulk copy (TMA store), tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
@@ -317,19 +325,6 @@ __device__ __forceinline__ void consume_stage_tri(double (&acc)[C::MI][C::NI][2]
     else consume_stage_tri_n<C, C::MI>(acc, As, Bs, lk, first);
 }
 
-// The warps of warp row 0 copy the new rows held by a k-major B stage (panel rows kk in [c, K)) out to rows_out: lane -> stage
-// row lane >> 1 and one half of the warp's NI * 8 columns, 16-byte accesses.
-template <class C>
-__device__ __forceinline__ void store_new_rows(const Params &p, const double *Bs_stage, int k0, int64_t col0, int n0, int lane) {
-    const int r = lane >> 1, h = lane & 1;
-    const int kk = k0 + r;
-    if (kk < p.c || kk >= p.K) return;
-    const double *src = Bs_stage + r * C::LDB + n0 + h * (C::NI * 4);
-    double *dst = p.rows_out + (int64_t)(kk - p.c) * p.ld_rows_out + col0 + n0 + h * (C::NI * 4);
-#pragma unroll
-    for (int q = 0; q < C::NI * 2; ++q) *reinterpret_cast<double2 *>(dst + 2 * q) = *reinterpret_cast<const double2 *>(src + 2 * q);
-}
-
 // kernel values from the x.y accumulators -> Cout (MODE_EVAL and phase 1 of MODE_FUSED)
 template <class C>
 __device__ __forceinline__ void eval_epilogue(const Params &p, double (&acc)[C::MI][C::NI][2], double *out, int64_t ldo,
@@ -402,7 +397,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], C::CONSUMERS);
+            mbar_init(&empty[s], C::CONSUMERS + ((MODE == MODE_SCHUR && p.rows_out) ? 1 : 0));     // + the row-store warp
         }
         mbar_init(xfull, 1);
         mbar_init(xempty, C::CONSUMERS);
@@ -424,6 +419,37 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
     if (warp >= C::CONSUMERS) {
         // the producer warpgroup hands its registers to the consumers (the kernel launches with 168/thread)
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+        if (MODE == MODE_SCHUR && p.rows_out && warp == C::CONSUMERS + 1) {
+            // ------------------------- row-store warp (speculative rows only) ------------------------------------------
+            // The B stages fetched for panel rows kk >= c ARE the accepted rows A[S, tile]: this warp waits for each stage like
+            // a consumer and sends those rows on to rows_out with TMA bulk stores (lane r = stage row r), so the compaction
+            // rows[c:c+s] = rows_all[acc] costs neither a pass over memory nor an instruction of the DMMA warps.
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                int ct = tile, chunk = 0;
+                if (p.chunk_rows) {
+                    chunk = tile / p.ncol_tiles;
+                    ct = tile - chunk * p.ncol_tiles;
+                }
+                const int64_t col0 = p.tile_col0 + (int64_t)ct * C::N_TILE;
+                for (int kt = 0; kt < nk; ++kt, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&full[s], (it / STAGES) & 1);
+                    if (chunk == 0 && kt * KT + KT > p.c) {            // every row chunk of a tail tile streams the same rows: one stores
+                        const int kk = kt * KT + lane;
+                        if (lane < KT && kk >= p.c && kk < p.K)
+                            bulk_s2g(p.rows_out + (int64_t)(kk - p.c) * p.ld_rows_out + col0, Bs_base + s * C::B_STAGE + lane * C::LDB,
+                                     C::N_TILE * 8);
+                        bulk_commit();
+                        bulk_wait_read0();                               // the stage may be refilled once the reads are done
+                        __syncwarp();
+                    }
+                    if (lane == 0) mbar_arrive(&empty[s]);
+                }
+            }
+            bulk_wait0();
+            return;
+        }
         if (warp != C::CONSUMERS) return;
         // ------------------------------- producer warp: runs ahead over the tiles -------------------
         int it = 0;
@@ -544,8 +570,6 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
                 else
                     consume_stage<C, 0>(acc, As_base + s * C::A_STAGE + m0 + lr, Bs_base + s * C::B_STAGE + n0 + lr, 0, lk,
                                         live_ksteps(kt, k_real), mi_cnt);
-                if (MODE == MODE_SCHUR && p.rows_out && wm == 0 && chunk == 0 && kt * KT + KT > p.c)
-                    store_new_rows<C>(p, Bs_base + s * C::B_STAGE, kt * KT, col0, n0, lane);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);         // this warp is done reading the stage
