@@ -316,9 +316,12 @@ def gpu_arm(args, w):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    # stdout carries the ONE JSON line: whatever NCCL is asked to log (it writes to stdout by default, "NCCL version ..." included)
-    # goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries the ONE JSON line: anything a library prints there (NCCL's "NCCL version ..." banner when NCCL_DEBUG is set in
+    # the environment, compiler chatter) goes to stderr -- file descriptor 1 is pointed at stderr for the run and the line is
+    # written to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     rpc.load()
@@ -523,7 +526,8 @@ def gpu_arm(args, w):
             "wall_time_s": ms * 1e-3 / args.steps, "phase_ms_per_step": phase_ms, "dominant_kernel_launches_ms_tflops": detail,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
         }
-        print(json.dumps(out), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
