@@ -430,7 +430,7 @@ def gpu_arm(args, w):
     traffic = None
     if args.workload == "tstar" and world == 1:
         try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of this command
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))["schur"]["avg_dram_bytes_per_launch"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r02.json")))["schur"]["avg_dram_bytes_per_launch"]
         except Exception:
             traffic = None
     if "schur" in phases:
@@ -441,7 +441,7 @@ def gpu_arm(args, w):
         executed = sum(schur_executed_flops(t[5][0], t[5][1], t[5][2]) for t in timers if t[2] == "schur" and len(t) > 5 and t[5])
         roofline = {"bound": "tensor", "kernel": "dg::gemm_kernel<MODE_SCHUR> (FP64 DMMA: Schur product + triangular solve + diag update fused)",
                     "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
-                    "traffic_source": "profiles/traffic_r01.json (ncu, same command)" if traffic else None,
+                    "traffic_source": "profiles/traffic_r02.json (ncu dram__bytes_read+write over the 12 Schur launches of this command)" if traffic else None,
                     "peak_source": peak_src, "peak_tracked_r01": tracked_tf,
                     "launches": cnt, "avg_launch_ms": 1e3 * sec / cnt, "share_of_step": sec / (ms * 1e-3),
                     "algorithmic_flops_per_launch": flops / cnt, "algorithmic_bytes_per_launch": nbytes / cnt,
