@@ -41,6 +41,8 @@ USE_PEER = _os.environ.get("RPC_B200_PEER", "1") != "0"
 # through a row map.  Worth it once the evaluation is short compared with the serial chain, i.e. when sharded:
 # RPC_B200_SPEC = "auto" (sharded only) | "1" (always) | "0" (never)
 USE_SPEC = _os.environ.get("RPC_B200_SPEC", "auto")
+# sharded accelerated runs draw + broadcast the NEXT round's uniforms at the start of a round (RPC_B200_PREFETCH=0: per round)
+USE_PREFETCH = _os.environ.get("RPC_B200_PREFETCH", "1") != "0"
 # how long a rank waits for another rank's epoch before the factorisation is aborted (0 = the library default, 20 s)
 PEER_TIMEOUT_MS = int(_os.environ.get("RPC_B200_PEER_TIMEOUT_MS", "0"))
 
@@ -204,10 +206,8 @@ class _State:
     # ---- thin wrappers over the C ABI ------------------------------------------------------------
     def upload_uniforms(self, up, ur=None, slot=0):
         """u_dev[slot] <- [proposal uniforms | rejection uniforms]; returns the slot's offset into u_dev.  Row-sharded runs use
-        RANK 0's draws on every rank (the reference's generators are unseeded, so nothing else makes the ranks' streams agree):
-        upload + broadcast run on a side stream and `wait_uniforms(slot)` makes the consumer wait for them.  With two slots the
-        accelerated driver issues round t+1's upload at the start of round t, so the broadcast never sits between the Schur
-        update (whose persistent CTAs leave no room for the NCCL kernel) and the next sampler."""
+        RANK 0's draws on every rank (the reference's generators are unseeded, so nothing else makes the ranks' streams agree).
+        With two slots the accelerated driver uploads round t+1's draws at the start of round t."""
         m = len(up)
         off = slot * 2 * self.m_max
         self.u_host[off:off + m] = torch.from_numpy(up)
@@ -215,18 +215,15 @@ class _State:
         if ur is not None:
             self.u_host[off + m:off + m + len(ur)] = torch.from_numpy(ur)
             tot = m + len(ur)
-        if self.info.world == 1 or self.dev.type != "cuda":
-            self.u_dev[off:off + tot].copy_(self.u_host[off:off + tot], non_blocking=True)
-            rdist.broadcast_draws(self.info, self.u_dev[off:off + tot])
-            self.ev_draw[slot] = None
-            return off
-        if self.draw_stream is None:
-            self.draw_stream = torch.cuda.Stream(device=self.dev)
-        with torch.cuda.stream(self.draw_stream):
-            self.u_dev[off:off + tot].copy_(self.u_host[off:off + tot], non_blocking=True)
-            rdist.broadcast_draws(self.info, self.u_dev[off:off + tot])
-            self.ev_draw[slot] = torch.cuda.Event()
-            self.ev_draw[slot].record(self.draw_stream)
+        # On the MAIN stream, on purpose.  The broadcast is an NCCL kernel that spins until every rank has joined; launched from
+        # a side stream it lands beside the persistent Schur / evaluator kernels (the host runs one update ahead of the device),
+        # takes an SM as soon as one of their CTAs exits and keeps it while the slowest rank arrives -- and the NEXT persistent
+        # launch, whose 148 CTAs each need a whole SM and own a fixed share of the tiles, then finishes a whole tile-share late
+        # (measured: +9 ms per factorisation on 4 GPUs, +10 ms on 8 without speculation).  In stream order it runs between two
+        # updates, when the device has nothing else to do.
+        self.u_dev[off:off + tot].copy_(self.u_host[off:off + tot], non_blocking=True)
+        rdist.broadcast_draws(self.info, self.u_dev[off:off + tot])
+        self.ev_draw[slot] = None
         return off
 
     def wait_uniforms(self, slot=0):
@@ -297,8 +294,9 @@ class _State:
     # ---- speculative evaluation of all proposals beside the rejection Cholesky (accelerated, sharded) ---------------------
     def enable_speculation(self):
         A = self.A
-        # break-even is where evaluating b rows takes about as long as the rejection kernel: N/world <~ 3e5 points at d = 50
-        if not (hasattr(A, "_spec") and self.ldx) or USE_SPEC == "0" or (USE_SPEC == "auto" and self.info.world < 4) or USE_FUSED:
+        # break-even is where evaluating b rows takes about as long as the rejection kernel: N/world <~ 1.5e5 points at d = 50
+        # (round 2, faster evaluator: on 4 GPUs the plain order measured 41.6 ms against 43 with speculation)
+        if not (hasattr(A, "_spec") and self.ldx) or USE_SPEC == "0" or (USE_SPEC == "auto" and self.info.world < 8) or USE_FUSED:
             return
         self.spec = True
         self.rows_all = torch.empty((self.m_max, self.n_pad), dtype=torch.float64, device=self.dev)
@@ -652,7 +650,7 @@ def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
     # Row-sharded runs with a fixed b draw (and upload + broadcast) round t+1's uniforms at the start of round t.  The two numpy
     # streams are state independent, so the values are the ones the reference would draw; if round t+1 never happens the legacy
     # stream is put back where the reference leaves it.
-    prefetch = st.info.world > 1 and not auto_b
+    prefetch = st.info.world > 1 and not auto_b and USE_PREFETCH
     ahead = None                                               # (slot offset, legacy state before the draw) of the next round
 
     def draw_round(slot):
