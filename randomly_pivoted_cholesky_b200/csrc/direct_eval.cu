@@ -15,6 +15,28 @@ using namespace dg;
 constexpr int DE_TN = 64;          // points per tile
 constexpr int DE_THREADS = 256;    // 16 x 16
 
+// Laplace epilogue: exp(-l1 / bw) as exp_tab_batch(l1 * (-1 / bw)) -- 13 FP64-pipe instructions per entry instead of a division
+// and libm's exp (~40), eight interleaved chains per out-of-line call (two pivot rows of the thread).  The L1 distance itself
+// stays bit-equal to scipy's cdist; the kernel value is within ~2.5 ulp of the reference's (argument: one rounding of the
+// reciprocal multiply; exponential: <= 1.2 ulp).  Stores go to the thread's four points tx + 16 j of each row.
+static __device__ __noinline__ void l1_tab_store8(double *dstA, int okA, double *dstB, int okB, double tab_lane, double x0, double x1,
+                                                  double x2, double x3, double x4, double x5, double x6, double x7) {
+    double x[8] = {x0, x1, x2, x3, x4, x5, x6, x7};
+    exp_tab_batch<8>(x, tab_lane);
+    if (okA) { dstA[0] = x[0]; dstA[16] = x[1]; dstA[32] = x[2]; dstA[48] = x[3]; }
+    if (okB) { dstB[0] = x[4]; dstB[16] = x[5]; dstB[32] = x[6]; dstB[48] = x[7]; }
+}
+static __device__ __noinline__ double4 l1_tab_wsum8(double tab_lane, double wA, double wB, double4 cs, double x0, double x1, double x2,
+                                                    double x3, double x4, double x5, double x6, double x7) {
+    double x[8] = {x0, x1, x2, x3, x4, x5, x6, x7};
+    exp_tab_batch<8>(x, tab_lane);
+    cs.x = fma(wB, x[4], fma(wA, x[0], cs.x));
+    cs.y = fma(wB, x[5], fma(wA, x[1], cs.y));
+    cs.z = fma(wB, x[6], fma(wA, x[2], cs.z));
+    cs.w = fma(wB, x[7], fma(wA, x[3], cs.w));
+    return cs;
+}
+
 // REDUCE (fused kernel-times-vector): out is a vector, out[col] = (accumulate ? out[col] : 0) + sum_row w[row] k(pivot row, X col)
 template <bool L1, int PI, bool REDUCE>
 __global__ void __launch_bounds__(DE_THREADS, 1) direct_rows_tma(const KernParams kp, const double *__restrict__ X, int64_t ldx,
@@ -28,6 +50,8 @@ __global__ void __launch_bounds__(DE_THREADS, 1) direct_rows_tma(const KernParam
     double *red = Xs + 2 * (size_t)DE_TN * ldx;                 // REDUCE: [16 thread rows][DE_TN] partial column sums
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int tile_doubles = DE_TN * (int)ldx;
+    const double tab_lane = c_exp2_tab[tid & 31];
+    const double nib = -1.0 / kp.bw;                            // Laplace: exp(-l1 / bw) = exp(l1 * nib)
 
     if (tid == 0) {
         mbar_init(&bars[0], 1);
@@ -81,6 +105,39 @@ __global__ void __launch_bounds__(DE_THREADS, 1) direct_rows_tma(const KernParam
                 }
         }
         const int64_t col0 = (int64_t)tile * DE_TN;
+        if (L1) {
+            // every lane takes part (the table lives in the lanes' registers): rows past s are computed and not stored
+            double4 cs4 = make_double4(0.0, 0.0, 0.0, 0.0);
+#pragma unroll
+            for (int i = 0; i < PI; i += 2) {
+                constexpr int LAST = PI - 1;
+                const int i1 = i + 1 < PI ? i + 1 : LAST;
+                const int rowA = ty + 16 * i, rowB = ty + 16 * i1;
+                const bool pair = i + 1 < PI;
+                if (REDUCE) {
+                    const double wA = rowA < s ? w[rowA] : 0.0, wB = (pair && rowB < s) ? w[rowB] : 0.0;
+                    cs4 = l1_tab_wsum8(tab_lane, wA, wB, cs4, acc[i][0] * nib, acc[i][1] * nib, acc[i][2] * nib, acc[i][3] * nib,
+                                       acc[i1][0] * nib, acc[i1][1] * nib, acc[i1][2] * nib, acc[i1][3] * nib);
+                } else {
+                    l1_tab_store8(out + (int64_t)rowA * ldo + col0 + tx, rowA < s, out + (int64_t)rowB * ldo + col0 + tx,
+                                  pair && rowB < s, tab_lane, acc[i][0] * nib, acc[i][1] * nib, acc[i][2] * nib, acc[i][3] * nib,
+                                  acc[i1][0] * nib, acc[i1][1] * nib, acc[i1][2] * nib, acc[i1][3] * nib);
+                }
+            }
+            if (REDUCE) {
+                red[ty * DE_TN + tx] = cs4.x; red[ty * DE_TN + tx + 16] = cs4.y;
+                red[ty * DE_TN + tx + 32] = cs4.z; red[ty * DE_TN + tx + 48] = cs4.w;
+                __syncthreads();
+                if (tid < DE_TN) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) t += red[q * DE_TN + tid];          // fixed order: deterministic
+                    out[col0 + tid] = (accumulate ? out[col0 + tid] : 0.0) + t;
+                }
+            }
+            __syncthreads();      // every thread is done with xs (and red) before they are refilled
+            continue;
+        }
         if (REDUCE) {
             double cs[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll

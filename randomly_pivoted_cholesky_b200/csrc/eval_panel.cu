@@ -40,57 +40,6 @@ struct EvalParams {
     int accumulate;
 };
 
-// 2^(j/32), correctly rounded
-__constant__ double c_exp2_tab[32] = {
-    0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, 0x1.11301d0125b51p+0,
-    0x1.172b83c7d517bp+0, 0x1.1d4873168b9aap+0, 0x1.2387a6e756238p+0, 0x1.29e9df51fdee1p+0,
-    0x1.306fe0a31b715p+0, 0x1.371a7373aa9cbp+0, 0x1.3dea64c123422p+0, 0x1.44e086061892dp+0,
-    0x1.4bfdad5362a27p+0, 0x1.5342b569d4f82p+0, 0x1.5ab07dd485429p+0, 0x1.6247eb03a5585p+0,
-    0x1.6a09e667f3bcdp+0, 0x1.71f75e8ec5f74p+0, 0x1.7a11473eb0187p+0, 0x1.82589994cce13p+0,
-    0x1.8ace5422aa0dbp+0, 0x1.93737b0cdc5e5p+0, 0x1.9c49182a3f090p+0, 0x1.a5503b23e255dp+0,
-    0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0,
-    0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0, 0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
-
-// exp(x) for x <= 0, N values at a time (interleaved chains), all 32 lanes of the warp converged.
-//   k = round(32 x / ln2),  x = k ln2/32 + r,  |r| <= ln2/64  (two-term Cody-Waite: k * HI is exact, HI has 36 significant bits)
-//   exp(x) = 2^(k >> 5) * T[k & 31] * (1 + p(r)),  p = expm1 to degree 6 (remainder < 2^-57)
-// T[j] sits in lane j's register and is fetched with a warp shuffle (no shared-memory table, no bank conflicts); the power of
-// two is added to the exponent field on the integer pipe.  Results below 2^-1020 are flushed to zero.  <= 1.2 ulp from the
-// correctly rounded value (4e7 random arguments in [-700, 0], checked on the host: tools/exp_check.c).
-template <int N>
-__device__ __forceinline__ void exp_tab_batch(double (&x)[N], double tab_lane) {
-    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52: the rounded integer lands in the low mantissa bits
-    const double INV = 0x1.71547652b82fep+5;                  // 32 / ln2
-    const double HI = 0x1.62e42fefa0000p-6, LO = 0x1.cf79abc9e3b3ap-45;   // ln2 / 32
-    double r[N], t[N], q[N];
-    int k[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        const double tm = fma(x[i], INV, MAGIC);
-        k[i] = __double2loint(tm);
-        const double kf = tm - MAGIC;
-        r[i] = fma(kf, -HI, x[i]);
-        r[i] = fma(kf, -LO, r[i]);
-        q[i] = 0x1.6c16c16c16c17p-10;                        // 1/720
-    }
-#pragma unroll
-    for (int i = 0; i < N; ++i) t[i] = __shfl_sync(0xffffffffu, tab_lane, k[i] & 31);
-    const double cf[4] = {0x1.1111111111111p-7, 0x1.5555555555555p-5, 0x1.5555555555555p-3, 0.5};   // 1/120, 1/24, 1/6, 1/2
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int i = 0; i < N; ++i) q[i] = fma(q[i], r[i], cf[c]);
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        const double r2 = r[i] * r[i];
-        const double p = fma(q[i], r2, r[i]);
-        const double v = fma(t[i], p, t[i]);
-        const int m = k[i] >> 5;
-        const double sc = __hiloint2double(__double2hiint(v) + (m << 20), __double2loint(v));
-        x[i] = m < -1020 ? 0.0 : sc;
-    }
-}
-
 // Eight scaled arguments g * D2 (not yet clamped) -> kernel values -> two groups of two double2 stores: either two fragment
 // rows of an NI = 2 tile (dstA, dstB) or the two halves of one row of an NI = 4 tile (dstB = dstA + 16).  Eight interleaved
 // chains per call: with four the dependent FP64 chain (about 12 instructions of ~8 cycles) was latency bound (ncu: 440 cycles

@@ -111,14 +111,16 @@ def test_kernel_values_match_reference(rpc, name):
 
 
 def test_laplace_l1_distance_is_bit_exact(rpc):
-    """Sequential feature order == scipy cdist 'cityblock'; only exp() ulps may differ."""
+    """Sequential feature order == scipy cdist 'cityblock'; only the exponential's last bits may differ: the device evaluates
+    exp(l1 * (-1/bw)) with its table exponential (<= 1.2 ulp) instead of exp(-l1/bw) with libm (one more rounding in the
+    argument): a few ulp, i.e. 1e-15 relative.  A summation order other than cdist's would show up at 1e-14 and above."""
     rng = np.random.default_rng(5)
     X = rng.standard_normal((700, 50))
     A = rpc.KernelMatrix(X, kernel="laplace", bandwidth=50.0)
     idx = np.arange(0, 700, 53)
     got = A[idx, :]
     want = orc.laplace_mtx(X[idx], X, bandwidth=50.0)
-    np.testing.assert_allclose(got, want, rtol=4e-16, atol=0)
+    np.testing.assert_allclose(got, want, rtol=1e-15, atol=0)
 
 
 @pytest.mark.parametrize("d", [3, 20, 50, 130])
