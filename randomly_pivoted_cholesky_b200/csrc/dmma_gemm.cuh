@@ -20,16 +20,12 @@
 #pragma once
 #include "rpc_common.cuh"
 
-#ifndef RPC_DENSE_RUN
-#define RPC_DENSE_RUN 1          // 0: every stage starts with its own fragment loads (diagnostic builds only)
-#endif
 #ifndef RPC_ROW_INTERLEAVE
 #define RPC_ROW_INTERLEAVE 1     // 0: contiguous row blocks per warp row (diagnostic builds only)
 #endif
 
 namespace dg {
 
-constexpr bool DENSE_RUN = RPC_DENSE_RUN != 0;
 constexpr int KT = RPC_KT;      // k-depth per stage
 constexpr int STAGES = 4;
 constexpr int LDBK = KT + 4;    // point-major B stage: [n][LDBK]
@@ -266,56 +262,6 @@ __device__ __forceinline__ void consume_stage_n(double (&acc)[C::MI][C::NI][2], 
                     for (int j = 0; j < C::NI; ++j) dmma884(acc[i][j], a[cur][i], b[cur][j]);
                 }
         }
-    }
-}
-
-// A RUN of consecutive full, dense k-major stages (the c-part of the Schur product: ~90% of the stages of a T* update) with the
-// fragment double buffer carried ACROSS stage boundaries: during the last k4-step of a stage the warp waits for the next stage
-// (the producer runs up to four stages ahead, so the wait returns at once) and loads its first fragments, instead of starting
-// every stage with an exposed shared-memory load.  `it` counts the stages this CTA has consumed (ring position and parity).
-template <class C, int CMI>
-__device__ __forceinline__ void consume_dense_run(double (&acc)[C::MI][C::NI][2], const double *As_w, const double *Bs_w, uint64_t *full,
-                                                  uint64_t *empty, int &it, int nstages, int lk, int lane) {
-    if (nstages <= 0) return;
-    double a[2][C::MI], b[2][C::NI];
-    int s = it % STAGES;
-    mbar_wait(&full[s], (it / STAGES) & 1);
-    {
-        const double *As = As_w + s * C::A_STAGE, *Bs = Bs_w + s * C::B_STAGE;
-#pragma unroll
-        for (int i = 0; i < CMI; ++i) a[0][i] = As[lk * C::LDA + i * C::RSTEP];
-#pragma unroll
-        for (int j = 0; j < C::NI; ++j) b[0][j] = Bs[lk * C::LDB + j * 8];
-    }
-    for (int n = 0; n < nstages; ++n) {
-        const double *As = As_w + s * C::A_STAGE, *Bs = Bs_w + s * C::B_STAGE;
-        const int sn = (it + 1) % STAGES;
-#pragma unroll
-        for (int ks = 0; ks < KT / 4; ++ks) {
-            const int cur = ks & 1, nxt = cur ^ 1;
-            if (ks + 1 < KT / 4) {
-                const int kk = (ks + 1) * 4 + lk;
-#pragma unroll
-                for (int i = 0; i < CMI; ++i) a[nxt][i] = As[kk * C::LDA + i * C::RSTEP];
-#pragma unroll
-                for (int j = 0; j < C::NI; ++j) b[nxt][j] = Bs[kk * C::LDB + j * 8];
-            } else if (n + 1 < nstages) {
-                mbar_wait(&full[sn], ((it + 1) / STAGES) & 1);
-                const double *An = As_w + sn * C::A_STAGE, *Bn = Bs_w + sn * C::B_STAGE;
-#pragma unroll
-                for (int i = 0; i < CMI; ++i) a[nxt][i] = An[lk * C::LDA + i * C::RSTEP];
-#pragma unroll
-                for (int j = 0; j < C::NI; ++j) b[nxt][j] = Bn[lk * C::LDB + j * 8];
-            }
-#pragma unroll
-            for (int i = 0; i < CMI; ++i)
-#pragma unroll
-                for (int j = 0; j < C::NI; ++j) dmma884(acc[i][j], a[cur][i], b[cur][j]);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);             // this warp is done reading the stage
-        ++it;
-        s = sn;
     }
 }
 
@@ -608,22 +554,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
 #pragma unroll
                 for (int j = 0; j < C::NI; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
         }
-        int kt_first = 0;
-        if (MODE == MODE_SCHUR && DENSE_RUN) {
-            // leading stages that are full (all 16 panel rows real) and dense for this warp (no fragment skipped yet)
-            int nd = k_real / KT;
-            if (p.tri) {
-                const int lim = (p.c + p.row_base + rstart + m0 + 7) / KT + 1;     // stages with kt * KT - c - ... - 7 <= 0
-                nd = nd < lim ? nd : lim;
-            }
-            nd = nd < nk2 ? nd : nk2;
-            if (C::ODD && mi_cnt != C::MI)
-                consume_dense_run<C, (C::ODD ? C::MI - 1 : C::MI)>(acc, As_base + m0 + lr, Bs_base + n0 + lr, full, empty, it, nd, lk, lane);
-            else
-                consume_dense_run<C, C::MI>(acc, As_base + m0 + lr, Bs_base + n0 + lr, full, empty, it, nd, lk, lane);
-            kt_first = nd > 0 ? nd : 0;
-        }
-        for (int kt = kt_first; kt < nk2; ++kt, ++it) {
+        for (int kt = 0; kt < nk2; ++kt, ++it) {
             const int s = it % STAGES;
             mbar_wait(&full[s], (it / STAGES) & 1);
             if (MODE == MODE_EVAL)
