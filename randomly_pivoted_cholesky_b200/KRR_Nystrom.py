@@ -19,7 +19,7 @@ import torch
 
 from . import dist as rdist
 from . import ops
-from .matrix import COL_ALIGN, KernelMatrix, _round_up
+from .matrix import COL_ALIGN, KernelMatrix, _normalise_indices, _round_up
 
 
 class KRR_Nystrom:
@@ -107,8 +107,9 @@ class KRR_Nystrom:
         m = len(idx)
         Kt = KernelMatrix(Xts, kernel=self.kernel, bandwidth=self.bandwidth, device=dev, **self.kernel_kwargs)
         piv = K._dev_new_payload(m)
+        idx = _normalise_indices(idx, K.shape[0])             # numpy semantics: negative indices wrap, out-of-range raise
         with torch.cuda.device(dev):
-            K._dev_gather(torch.as_tensor(np.asarray(idx, dtype=np.int64), device=dev), m, piv)
+            K._dev_gather(torch.as_tensor(idx, device=dev), m, piv)
         s = torch.from_numpy(np.ascontiguousarray(np.asarray(sol, dtype=np.float64))).to(dev)
         s2 = s.reshape(m, -1)
         preds = torch.empty((Kt.shape[0], s2.shape[1]), dtype=torch.float64, device=dev)
