@@ -503,7 +503,8 @@ def gpu_arm(args, w):
     e2e = {"value": q2 / (ms2 * 1e-3), "unit": "entries/s",
            "h2d_bytes_per_step": int(X.nbytes + (y.nbytes + Xts.numel() * 8 if is_krr else 0)),
            "d2h_bytes_per_step": int(d2h), "ms_per_step": ms2 / args.steps, "trace_norm_error": float(err),
-           "note": "factors G, rows stay in HBM (PSDLowRank is device backed); result read back = pivots + trace error"}
+           "note": "factors G, rows stay in HBM (PSDLowRank is device backed); result read back = pivots + trace error "
+                   "(trace(A) - sum of the residual diagonal, the driver's exact account: no pass over G)"}
 
     if rank == 0:
         cpu = None

@@ -119,6 +119,7 @@ class PSDLowRank(AbstractPSDLowRank):
         super().__init__(**kwargs)
         self._G = G
         self._G_host = None
+        self._trace_hint = None
         ncols = G.shape[1] if n is None else n
         self.shape = (ncols, ncols)
 
@@ -135,6 +136,7 @@ class PSDLowRank(AbstractPSDLowRank):
     def G(self, value):
         self._G = value
         self._G_host = None
+        self._trace_hint = None
 
     @property
     def G_device(self):
@@ -144,6 +146,11 @@ class PSDLowRank(AbstractPSDLowRank):
         return isinstance(self._G, torch.Tensor) and self._G.is_cuda
 
     def trace(self):
+        if self._trace_hint is not None:
+            # the driver's own account of the factor's trace: trace(A) - sum(residual diagonal), both exact sequential sums
+            # of the device sampler.  ||G||_F^2 (lra.py:94-95) is the same number up to the rounding of the diagonal updates
+            # (~1e-15 relative), without a pass over the k x N factor (16 GB at the headline size).
+            return self._trace_hint
         if self._on_device():
             if self._sharded():                                # local columns only (the shard is padded), then sum
                 import torch.distributed as tdist

@@ -553,6 +553,7 @@ def block_cholesky_helper(A, k, b, alg, stoptol=1e-14, strategy="regularize", rb
     arr_idx = []
     counter = 0
     orig_trace = None
+    final_sum = None
     count = k
     while counter < k:
         block_size = min(k - counter, b)
@@ -575,6 +576,7 @@ def block_cholesky_helper(A, k, b, alg, stoptol=1e-14, strategy="regularize", rb
             orig_trace = float(stats_host[0])
         elif stoptol > 0 and float(stats_host[0]) <= stoptol * orig_trace:     # :133-136, checked after the previous block
             count = counter
+            final_sum = float(stats_host[0])
             break
         idx = np.unique(drawn)[:block_size] if alg == "rp" else drawn          # :92
         block_size = len(idx)
@@ -619,9 +621,13 @@ def block_cholesky_helper(A, k, b, alg, stoptol=1e-14, strategy="regularize", rb
         if stoptol > 0:
             st.sample(0)
             sh = st.stats.cpu().numpy()
+            final_sum = float(sh[0])
             if float(sh[0]) <= stoptol * orig_trace:
                 count = counter
-    return st.result(min(count, counter), arr_idx)
+    res = st.result(min(count, counter), arr_idx)
+    if final_sum is not None and min(count, counter) == counter:
+        res._trace_hint = orig_trace - final_sum               # trace(A) - sum(residual diagonal) = ||G||_F^2
+    return res
 
 
 # --------------------------------------------------------------------------------------------------
@@ -647,6 +653,7 @@ def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
     orig_trace = None
     count = k
     rounds = []
+    final_sum = None
     # Row-sharded runs with a fixed b draw (and upload + broadcast) round t+1's uniforms at the start of round t.  The two numpy
     # streams are state independent, so the values are the ones the reference would draw; if round t+1 never happens the legacy
     # stream is put back where the reference leaves it.
@@ -692,6 +699,7 @@ def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
             ahead = None
             A.queries -= b * b
             count = counter
+            final_sum = float(stats_host[0])
             break
         if info[2] != 0:
             raise RuntimeError("rejection_cholesky requires a strictly positive trace")      # :145
@@ -719,11 +727,14 @@ def accelerated_rpcholesky(A, k, b="auto", stoptol=1e-13, verbose=False):
         if stoptol > 0:
             st.sample(0)
             sh = st.stats.cpu().numpy()
+            final_sum = float(sh[0])
             if float(sh[0]) <= stoptol * orig_trace:
                 count = counter
     if ahead is not None:
         np.random.set_state(ahead[1])                          # the prefetched round does not exist in the reference
     res = st.result(min(count, counter), arr_idx)
+    if final_sum is not None and min(count, counter) == counter:
+        res._trace_hint = orig_trace - final_sum               # trace(A) - sum(residual diagonal) = ||G||_F^2
     res.rounds = rounds
     return res
 

@@ -367,6 +367,10 @@ def test_configs_c1_c2_against_oracle(rpc):
     assert np.array_equal(np.asarray(lra.idx), ref.idx)
     assert lra.rounds == ref.rounds
     assert relerr(lra.G, ref.G) <= F_TOL and relerr(lra.rows, ref.rows) <= F_TOL
+    # trace(): the driver's account trace(A) - sum(residual diagonal) (no pass over G) against ||G||_F^2 and the oracle
+    assert lra._trace_hint is not None
+    assert abs(lra.trace() - np.linalg.norm(lra.G, "fro") ** 2) <= 1e-12 * lra.trace()
+    assert abs(lra.trace() - ref.trace()) <= 1e-11 * ref.trace()
 
 
 def test_block_laplace_against_oracle(rpc):
@@ -378,6 +382,9 @@ def test_block_laplace_against_oracle(rpc):
     ref = orc.block_rpcholesky(orc.OracleKernelMatrix(X, kernel="laplace", bandwidth=50.0), 600, 200, rng)
     assert [int(i) for i in lra.idx] == [int(i) for i in ref.idx]
     assert relerr(lra.G, ref.G) <= F_TOL and relerr(lra.rows, ref.rows) <= F_TOL
+    assert lra._trace_hint is not None
+    assert abs(lra.trace() - np.linalg.norm(lra.G, "fro") ** 2) <= 1e-12 * lra.trace()
+    assert abs(lra.trace() - ref.trace()) <= 1e-11 * ref.trace()
 
 
 def test_dispatch_and_errors(rpc):
