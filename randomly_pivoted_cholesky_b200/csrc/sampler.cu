@@ -210,8 +210,13 @@ __device__ __forceinline__ double walk_dirty_tile(const double *__restrict__ d, 
                     }
                 }
                 if (f < 32) {
+                    // the real sequential adds: every lane adds ITS eight elements to the (identical) carry in its own registers and
+                    // lane f's result is broadcast -- the same eight fp64 additions in the same order as a chain of eight
+                    // shuffle + add pairs, with one shuffle latency on the serial path instead of eight
+                    double cf = carry;
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) carry += __shfl_sync(full, x[t], f);   // the real sequential adds
+                    for (int t = 0; t < 8; ++t) cf += x[t];
+                    carry = __shfl_sync(full, cf, f);
                     lpos = f + 1;
                 } else {
                     lpos = 32;
