@@ -193,60 +193,67 @@ class PSDLowRank(AbstractPSDLowRank):
 class NystromExtension(AbstractPSDLowRank):
     """A ~= rows^T core^{-1} rows, held as the k x k core and the k x N rows (lra.py:118-171).  Host numpy, off the
     hot path: the other samplers of the reference (uniform, leverage scores, DPP) return this type through
-    utils.lra_from_sample.  The factor G = L^{-1} rows (L = Cholesky factor of the symmetrised core shifted by
-    trace(core) * eps, lra.py:131-133) is formed lazily on first use."""
+    utils.lra_from_sample.  Everything derived from the core is lazy: the Cholesky factor L of the symmetrised core shifted
+    by trace(core) * eps (lra.py:131-133), the factor G = L^{-1} rows, and the interpolation matrix."""
 
     def __init__(self, core, factor=None, interpolation=None, **kwargs):
-        super().__init__(**kwargs)
         if "rows" not in kwargs:
             raise RuntimeError("Need to specify rows for Nystrom extension")
+        super().__init__(**kwargs)
         core = np.asarray(core)
-        self.C = (core + core.T) / 2
-        self.shape = (self.rows.shape[1], self.rows.shape[1])
-        self.L = None
-        self.G = factor
-        self.W = interpolation
+        self.C = 0.5 * (core + core.T)
+        n = self.rows.shape[1]
+        self.shape = (n, n)
+        self.L, self.G, self.W = None, factor, interpolation
 
+    # -- lazily built pieces ------------------------------------------------------------------------------------------
     def get_core_factor(self):
         if self.L is None:
-            k = self.C.shape[0]
-            shift = np.trace(self.C) * np.finfo(float).eps
-            self.L = np.linalg.cholesky(self.C + shift * np.identity(k))
+            shifted = self.C.copy()
+            shifted[np.diag_indices_from(shifted)] += np.trace(self.C) * np.finfo(float).eps
+            self.L = np.linalg.cholesky(shifted)
         return self.L
 
     def get_factor(self):
         if self.G is None:
-            self.G = np.linalg.solve(self.get_core_factor(), self.rows)
+            from scipy.linalg import solve_triangular
+            self.G = solve_triangular(self.get_core_factor(), self.rows, lower=True)
         return self.G
 
     def get_interpolation(self):
         if self.W is None:
-            # as the reference writes it (lra.py:140-143): L^T against the LEFT factor
-            self.W = np.linalg.solve(self.get_core_factor().T, self.get_left_factor())
+            from scipy.linalg import solve_triangular
+            # the reference solves L^T against the LEFT (N x k) factor here (lra.py:140-143), which only has matching shapes
+            # for N == k; the operand is kept as the reference has it
+            self.W = solve_triangular(self.get_core_factor().T, self.get_left_factor(), lower=False)
         return self.W
-
-    def get_left_factor(self):
-        return self.get_factor().T
 
     def get_right_factor(self):
         return self.get_factor()
+
+    def get_left_factor(self):
+        return self.get_right_factor().T
+
+    # -- the low-rank operator ----------------------------------------------------------------------------------------------
+    def rank(self):
+        return self.C.shape[0]
 
     def trace(self):
         return np.linalg.norm(self.get_factor()) ** 2
 
     def __matmul__(self, other):
-        return self.get_left_factor() @ (self.get_right_factor() @ other)
-
-    def rank(self):
-        return self.C.shape[0]
+        G = self.get_factor()
+        return G.T @ (G @ other)
 
     def matrix(self):
-        return self.get_left_factor() @ self.get_right_factor()
+        G = self.get_factor()
+        return G.T @ G
 
     def eigenvalue_decomposition(self):
         return CompactEigenvalueDecomposition.from_G(self.get_factor(), idx=self.idx, rows=self.rows)
 
     def scale(self, scaling):
         scaling = np.asarray(scaling)
-        G = None if self.G is None else self.G * np.sqrt(scaling[np.newaxis, :])
-        return NystromExtension(self.C, idx=self.idx, rows=self.rows * scaling[np.newaxis, :], factor=G, interpolation=self.W)
+        scaled_factor = None if self.G is None else self.G * np.sqrt(scaling)[np.newaxis, :]
+        return NystromExtension(self.C, idx=self.idx, rows=self.rows * scaling[np.newaxis, :], factor=scaled_factor,
+                                interpolation=self.W)
