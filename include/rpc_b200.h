@@ -162,7 +162,7 @@ int rpc_select_largest(rpc_ctx *ctx, void *stream, const double *diag, int64_t n
 int rpc_build_panel(rpc_ctx *ctx, void *stream, const double *P, int64_t ldP, int c, const int32_t *acc, int s,
                     const double *L, int64_t ldl, int mode, double *At, int64_t ldat, int k_pad);
 
-/* Leading dimension to build the panel At with so that rpc_schur_update / rpc_fused_update fetch each k-stage of it
+/* Leading dimension to build the panel At with so that rpc_schur_update fetches each k-stage of it
  * with ONE TMA bulk copy (the shared-memory stride of the row tile chosen for s rows).  Any even ldat >= the tile
  * height works; this one is the fast one. */
 int rpc_panel_ld(int s);
@@ -180,17 +180,6 @@ int rpc_publish_round(rpc_ctx *ctx, void *stream, const double *stats, const int
  * G rows [c, c+s) are written; rows_new is s x n_pad (normally rows + c*ldr). */
 int rpc_schur_update(rpc_ctx *ctx, void *stream, double *G, int64_t ldg, int c, int s, const double *At, int64_t ldat,
                      int k_pad, const double *rows_new, int64_t ldr, double *diag, int64_t n_pad);
-
-/* rows_new = A[S,:] evaluated AND consumed in one kernel (Gaussian / Matern without extra_stability, s <= 256,
- * point stride small enough for the X tile to stay in shared memory): phase 1 computes the kernel-row tile
- * k(Xsel, X[tile]) on DMMA and writes it to rows_new, phase 2 is rpc_schur_update reading those rows back through
- * L2 (rpcholesky.py:205-209 / 101-107,128-129 in one pass over G).  rpc_fused_update_supported() tells whether
- * the shape qualifies; otherwise call rpc_kernel_rows + rpc_schur_update. */
-int rpc_fused_update_supported(const rpc_kernel_spec *spec, int s, int64_t ldx);
-int rpc_fused_update(rpc_ctx *ctx, void *stream, const rpc_kernel_spec *spec, const double *X, const double *xnorm,
-                     int64_t n_pad, int d, int64_t ldx, const double *Xsel, const double *pnorm, int64_t ldp, double *G,
-                     int64_t ldg, int c, int s, const double *At, int64_t ldat, int k_pad, double *rows_new, int64_t ldr,
-                     double *diag);
 
 /* One step of simple RPCholesky (rpcholesky.py:40-43), fused: row = A[idx,:]; g = (row - G[:i,idx]^T
  * G[:i,:]) / sqrt(diag[idx]); rows[i,:] = row; G[i,:] = g; diag = max(diag - g^2, 0).

@@ -120,9 +120,6 @@ _SIGNATURES = {
     "rpc_build_panel_dev": (_INT, [_P, _P, _P, _I64, _INT, _P, _P, _INT, _P, _I64, _P, _P, _P, _P, _I64, _P, _P, _P]),
     "rpc_panel_ld": (_INT, [_INT]),
     "rpc_schur_update": (_INT, [_P, _P, _P, _I64, _INT, _INT, _P, _I64, _INT, _P, _I64, _P, _I64]),
-    "rpc_fused_update_supported": (_INT, [C.POINTER(KernelSpec), _INT, _I64]),
-    "rpc_fused_update": (_INT, [_P, _P, C.POINTER(KernelSpec), _P, _P, _I64, _INT, _I64, _P, _P, _I64, _P, _I64, _INT, _INT, _P,
-                                _I64, _INT, _P, _I64, _P]),
     "rpc_ctx_reserve_sms": (_INT, [_P, _INT]),
     "rpc_gather_rows": (_INT, [_P, _P, _P, _I64, _P, _P, _INT, _P, _I64, _I64]),
     "rpc_schur_update_ex": (_INT, [_P, _P, _P, _I64, _INT, _INT, _P, _I64, _INT, _P, _I64, _P, _P, _I64, C.POINTER(Peers),

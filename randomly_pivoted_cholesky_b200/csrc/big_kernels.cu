@@ -12,14 +12,14 @@ constexpr size_t SMEM_LIMIT = 227 * 1024;
 template <class C, int MODE>
 static int launch_gemm(rpc_ctx *ctx, cudaStream_t st, const Params &p, int64_t n_pad) {
     static unsigned long long configured = 0;   // one bit per device: function attributes are per device
-    size_t shm = (MODE == MODE_FUSED || MODE == MODE_EVALX) ? C::fused_smem_bytes((int)p.ldx) : C::SMEM_BYTES;
+    size_t shm = (MODE == MODE_EVALX) ? C::fused_smem_bytes((int)p.ldx) : C::SMEM_BYTES;
     if (shm > SMEM_LIMIT) {
         rpc_set_error("launch_gemm: %zu bytes of shared memory needed, %zu available", shm, SMEM_LIMIT);
         return -4;
     }
     if (!rpc_dev_bit(configured, ctx)) {
         RPC_CUDA(cudaFuncSetAttribute(gemm_kernel<C, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (MODE == MODE_FUSED || MODE == MODE_EVALX) ? (int)SMEM_LIMIT : (int)C::SMEM_BYTES));
+                                      (MODE == MODE_EVALX) ? (int)SMEM_LIMIT : (int)C::SMEM_BYTES));
         configured |= 1ull << (ctx->device & 63);
     }
     // persistent: one CTA per SM walks the column tiles; the producer warp prefetches across tile boundaries
@@ -117,7 +117,7 @@ static int panel_ld_for(int m, bool fine = false) {
 }
 extern "C" int rpc_panel_ld(int s) { return s <= 256 ? panel_ld_for(s, true) : (s + 255) / 256 * 256; }
 
-// shared-memory need of the fused kernel for a given row count / point stride (0 if no tile fits)
+// does the X-resident evaluator (MODE_EVALX) fit in shared memory for this row count / point stride?
 static bool fused_fits(int m, int64_t ldx) {
     int t = tile_rows_for(m);
     size_t need;
@@ -321,38 +321,6 @@ extern "C" int rpc_schur_update_peers(rpc_ctx *ctx, void *stream, double *G, int
                                       const rpc_peers *peers, unsigned long long epoch) {
     RPC_CHECK_ARG(peers != nullptr, "peer table required");
     return schur_update_impl(ctx, stream, G, ldg, c, s, At, ldat, k_pad, rows_new, ldr, nullptr, diag, n_pad, peers, epoch, 0);
-}
-
-extern "C" int rpc_fused_update_supported(const rpc_kernel_spec *spec, int s, int64_t ldx) {
-    if (!spec || spec->kind == RPC_KERN_LAPLACE || spec->extra_stability) return 0;
-    if (s < 1 || s > 256) return 0;
-    return fused_fits(s, ldx) ? 1 : 0;
-}
-
-extern "C" int rpc_fused_update(rpc_ctx *ctx, void *stream, const rpc_kernel_spec *spec, const double *X, const double *xnorm,
-                                int64_t n_pad, int d, int64_t ldx, const double *Xsel, const double *pnorm, int64_t ldp,
-                                double *G, int64_t ldg, int c, int s, const double *At, int64_t ldat, int k_pad,
-                                double *rows_new, int64_t ldr, double *diag) {
-    RPC_CHECK_ARG(ctx && spec && X && xnorm && Xsel && pnorm && G && At && rows_new && diag, "null pointer");
-    RPC_CHECK_ARG(rpc_fused_update_supported(spec, s, ldx), "kernel/shape not supported by the fused update");
-    RPC_CHECK_ARG(c >= 0 && n_pad > 0 && n_pad % RPC_COL_ALIGN == 0, "bad sizes");
-    RPC_CHECK_ARG(k_pad % RPC_KT == 0 && k_pad >= c + s, "k_pad must be a multiple of RPC_KT and >= c+s");
-    RPC_CHECK_ARG(d >= 1 && d % RPC_FEAT_ALIGN == 0 && ldx % RPC_FEAT_ALIGN == 0 && ldx >= d, "d, ldx must be multiples of 4");
-    RPC_CHECK_ARG(ldg % 2 == 0 && ldr % 2 == 0 && ldat % 2 == 0 && ldat >= tile_rows_for(s), "bad leading dimensions");
-    cudaStream_t st = (cudaStream_t)stream;
-    const int ke_pad = (d + RPC_KT - 1) / RPC_KT * RPC_KT;
-    const int ld_e = panel_ld_for(s);
-    int rc = rpc_ws_reserve(ctx, (size_t)ke_pad * ld_e * sizeof(double));
-    if (rc) return rc;
-    rc = rpc_transpose_pad(ctx, st, Xsel, ldp, s, d, ctx->ws, ld_e, ke_pad);
-    if (rc) return rc;
-    Params p{};
-    p.At = At; p.ldat = ldat; p.k_pad = k_pad; p.m_valid = s;
-    p.G = G; p.ldg = ldg; p.c = c; p.R = rows_new; p.ldr = ldr; p.K = c + s;
-    p.Cout = G + (int64_t)c * ldg; p.ldc = ldg; p.diag = diag;
-    p.X = X; p.ldx = ldx; p.d = d; p.xnorm = xnorm; p.pnorm = pnorm; p.kp = make_kern_params(spec);
-    p.At_e = ctx->ws; p.ldat_e = ld_e; p.ke_pad = ke_pad;
-    return dispatch_gemm<MODE_FUSED>(ctx, st, p, s, n_pad);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -30,7 +30,7 @@ constexpr int KT = RPC_KT;      // k-depth per stage
 constexpr int STAGES = 4;
 constexpr int LDBK = KT + 4;    // point-major B stage: [n][LDBK]
 
-enum { MODE_SCHUR = 0, MODE_EVAL = 1, MODE_FUSED = 2, MODE_EVALX = 3 };   // EVALX: EVAL with the X tile resident (phase 1 of FUSED only)
+enum { MODE_SCHUR = 0, MODE_EVAL = 1, MODE_EVALX = 3 };   // EVALX: EVAL with the X tile resident in shared memory
 
 // ODD (only with WM == 2): the second warp row owns MI-1 fragments, so tiles come in 8-row steps.  The two warps an
 // SM sub-partition hosts (w and w+4) are then given different warp rows, which keeps the four DMMA pipes balanced.
@@ -57,10 +57,10 @@ struct Cfg {
     static constexpr int B_STAGE_PT = N_TILE * LDBK;                          // point-major B stage
     static constexpr int B_STAGE = B_STAGE_ROW > B_STAGE_PT ? B_STAGE_ROW : B_STAGE_PT;
     static constexpr int STAGE_DOUBLES = STAGES * (A_STAGE + B_STAGE);
-    static constexpr int NBAR = 2 * STAGES + 4;                               // full[], empty[], xfull, xempty, rows_ready, pad
+    static constexpr int NBAR = 2 * STAGES + 4;                               // full[], empty[], xfull, xempty, 2 spare
     static constexpr int RED_DOUBLES = WM * N_TILE;                           // column-sum scratch of the epilogue
     static constexpr size_t SMEM_BYTES = (size_t)(STAGE_DOUBLES + NBAR + RED_DOUBLES) * sizeof(double);
-    // MODE_FUSED keeps the whole X tile resident: N_TILE x ldx doubles (+16 zero doubles of slack)
+    // MODE_EVALX keeps the whole X tile resident: N_TILE x ldx doubles (+16 zero doubles of slack)
     static constexpr size_t fused_smem_bytes(int ldx) { return SMEM_BYTES + ((size_t)N_TILE * ldx + 16) * sizeof(double); }
     static_assert(M_TILE % 8 == 0 && N_TILE % 16 == 0, "tile shape");
     static_assert(LDA % 16 == 4 && LDB % 16 == 4, "bank-conflict-free leading dimensions");
@@ -99,8 +99,7 @@ struct Params {
     const double *xnorm;   // per point
     const double *pnorm;   // per pivot (row of C)
     KernParams kp;
-    // MODE_FUSED: phase 1 evaluates rows_new = k(Xsel, X) (panel At_e = Xsel^T, ke_pad x ldat_e) into R,
-    // phase 2 is MODE_SCHUR reading those rows back through L2
+    // MODE_EVALX: rows = k(Xsel, X) with the panel At_e = Xsel^T (ke_pad x ldat_e) streamed and the X tile resident; output R
     const double *At_e;
     int64_t ldat_e;
     int ke_pad;
@@ -325,7 +324,7 @@ __device__ __forceinline__ void consume_stage_tri(double (&acc)[C::MI][C::NI][2]
     else consume_stage_tri_n<C, C::MI>(acc, As, Bs, lk, first);
 }
 
-// kernel values from the x.y accumulators -> Cout (MODE_EVAL and phase 1 of MODE_FUSED)
+// kernel values from the x.y accumulators -> Cout (MODE_EVAL, MODE_EVALX)
 template <class C>
 __device__ __forceinline__ void eval_epilogue(const Params &p, double (&acc)[C::MI][C::NI][2], double *out, int64_t ldo,
                                               int64_t col0, int m0, int n0, int lr, int lk, int mi_cnt) {
@@ -381,14 +380,13 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
     uint64_t *empty = full + STAGES;
     uint64_t *xfull = empty + STAGES;
     uint64_t *xempty = xfull + 1;
-    uint64_t *rows_ready = xempty + 1;
     double *red = smem + C::STAGE_DOUBLES + C::NBAR;         // [WM][N_TILE]
-    double *Xs = red + C::RED_DOUBLES;                       // MODE_FUSED only: [N_TILE][ldx] + 16 zeros
+    double *Xs = red + C::RED_DOUBLES;                       // MODE_EVALX only: [N_TILE][ldx] + 16 zeros
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int nk = p.k_pad / KT;
-    constexpr bool XRES = (MODE == MODE_FUSED || MODE == MODE_EVALX);   // phase 1 with the X tile resident
+    constexpr bool XRES = (MODE == MODE_EVALX);              // evaluation with the X tile resident
     const int nke = XRES ? p.ke_pad / KT : 0;
     const int nk2 = (MODE == MODE_EVALX) ? 0 : nk;
     const int ldx = (int)p.ldx;
@@ -401,7 +399,6 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
         }
         mbar_init(xfull, 1);
         mbar_init(xempty, C::CONSUMERS);
-        mbar_init(rows_ready, C::CONSUMERS);
         fence_barrier_init();
     }
     if (MODE == MODE_EVAL) {
@@ -479,16 +476,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
                     produce_panel<C>(As_base + s * C::A_STAGE, p.At_e, p.ldat_e, kt * KT, &full[s], lane);
                 }
             }
-            bool rows_waited = (MODE != MODE_FUSED);
             for (int kt = 0; kt < nk2; ++kt, ++it) {
                 const int s = it % STAGES;
-                if (!rows_waited && kt * KT + KT > p.c) {    // this stage reads rows_new written by phase 1
-                    mbar_wait(rows_ready, tpar);
-                    rows_waited = true;
-                }
                 mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);   // first lap: returns immediately
-                produce_stage<C, MODE == MODE_FUSED ? MODE_SCHUR : MODE>(p, At_tile, As_base + s * C::A_STAGE,
-                                                                          Bs_base + s * C::B_STAGE, &full[s], kt * KT, col0, lane);
+                produce_stage<C, MODE>(p, At_tile, As_base + s * C::A_STAGE, Bs_base + s * C::B_STAGE, &full[s], kt * KT, col0, lane);
             }
         }
         return;
@@ -533,7 +524,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
             for (int j = 0; j < C::NI; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
         if (XRES) {
-            // ---- phase 1: rows_new tile = k(Xsel, X tile), written to R and read back by phase 2 through L2
+            // ---- rows tile = k(Xsel, X tile) with the X tile resident, written to R
             mbar_wait(xfull, tpar);
             for (int kt = 0; kt < nke; ++kt, ++it) {
                 const int s = it % STAGES;
@@ -545,14 +536,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) gemm_kernel(const Params p) {
             }
             if (lane == 0) mbar_arrive(xempty);            // the X tile may be overwritten by the next one
             eval_epilogue<C>(p, acc, const_cast<double *>(p.R), p.ldr, col0, m0, n0, lr, lk, mi_cnt);
-            if (MODE == MODE_EVALX) continue;
-            fence_proxy_async_all();                       // generic-proxy global writes -> visible to the TMA reads
-            __syncwarp();
-            if (lane == 0) mbar_arrive(rows_ready);
-#pragma unroll
-            for (int i = 0; i < C::MI; ++i)
-#pragma unroll
-                for (int j = 0; j < C::NI; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+            continue;
         }
         for (int kt = 0; kt < nk2; ++kt, ++it) {
             const int s = it % STAGES;

@@ -29,10 +29,7 @@ from .matrix import AbstractPSDMatrix, PSDMatrix, _ptr, _round_up, _stream
 EPS = float(np.finfo(float).eps)
 AT_LD_ALIGN = 256          # panel leading dimension granularity (widest row tile of the DMMA kernel)
 
-# rpc_fused_update (kernel rows evaluated inside the Schur kernel) measured ~10% slower per round than
-# rpc_kernel_rows + rpc_schur_update on B200 (profiles/): opt-in only
 import os as _os
-USE_FUSED = _os.environ.get("RPC_B200_FUSED", "0") == "1"
 # Row-sharded runs exchange the residual diagonal and the pivot payload through NVLink peer memory, stored by the
 # producing kernels themselves (dist.PeerWindow); RPC_B200_PEER=0 falls back to the two NCCL collectives per round
 USE_PEER = _os.environ.get("RPC_B200_PEER", "1") != "0"
@@ -129,7 +126,7 @@ class _State:
         payload_len = nx + (m_max if self.ldx else 0) + max(k, 1) * m_max
         self.peer = None
         self.diag_pending = False              # True: the last Schur update published the new diagonal into diag_full
-        if (self.info.world > 1 and self.info.world <= _lib.MAX_PEERS and USE_PEER and not USE_FUSED and self.dev.type == "cuda"
+        if (self.info.world > 1 and self.info.world <= _lib.MAX_PEERS and USE_PEER and self.dev.type == "cuda"
                 and self.ldx):
             self.peer = rdist.PeerWindow.get(self.info, self.ctx, self.dev, payload_len)     # None: no peer access here
         global LAST_DATA_PLANE
@@ -296,7 +293,7 @@ class _State:
         A = self.A
         # break-even is where evaluating b rows takes about as long as the rejection kernel: N/world <~ 1.5e5 points at d = 50
         # (round 2, faster evaluator: on 4 GPUs the plain order measured 41.6 ms against 43 with speculation)
-        if not (hasattr(A, "_spec") and self.ldx) or USE_SPEC == "0" or (USE_SPEC == "auto" and self.info.world < 8) or USE_FUSED:
+        if not (hasattr(A, "_spec") and self.ldx) or USE_SPEC == "0" or (USE_SPEC == "auto" and self.info.world < 8):
             return
         self.spec = True
         self.rows_all = torch.empty((self.m_max, self.n_pad), dtype=torch.float64, device=self.dev)
@@ -364,16 +361,6 @@ class _State:
             A._count(s * self.n)
             self._schur(c, s, ldat, k_pad, _ptr(self.rows_all), _ptr(self.acc), panel_mode == 0,
                         rows_out=C.c_void_p(self.rows.data_ptr() + 8 * c * self.n_pad))
-            return
-        spec = getattr(A, "_spec", None)
-        if USE_FUSED and spec is not None and self.lib.rpc_fused_update_supported(C.byref(spec), s, A.ldx):
-            # kernel rows evaluated and consumed in ONE pass over the column tile (fused update)
-            with _timed("schur", 2.0 * s * (c + s + d) * n, 8.0 * n * (c + 2 * s + d + 2)):
-                check(self.lib.rpc_fused_update(self.ctx.handle, _stream(), C.byref(spec), _ptr(A._Xd), _ptr(A._xnorm),
-                                                self.n_pad, A.d_pad, A.ldx, _ptr(sel_piv.X), _ptr(sel_piv.norm), A.ldx,
-                                                _ptr(self.G), self.n_pad, c, s, _ptr(self.At), ldat, k_pad, rows_ptr,
-                                                self.n_pad, _ptr(self.diag)), "rpc_fused_update")
-            A._count(s * self.n)
             return
         with _timed("eval", 2.0 * s * n * d, 8.0 * n * (s + d)):
             A._dev_rows_into(sel_idx, s, sel_piv, rows_ptr, self.n_pad)
