@@ -209,3 +209,24 @@ def test_nystrom_extension_and_krr_vec():
     np.testing.assert_allclose(ced.krr_vec(B, 0.1), np.linalg.solve(A + 0.1 * np.eye(N), B), atol=1e-8)
     np.testing.assert_allclose(ced.krr(B[:, 0], 0.1), np.linalg.solve(A + 0.1 * np.eye(N), B[:, 0]), atol=1e-8)
     assert PSDLowRank(G).eigenvalue_decomposition().rank() == r
+
+
+def test_bench_flop_accounting():
+    """bench.py's roofline bookkeeping: algorithmic flops are SURVEY 8(d)'s s (2c + s) N; the executed count replays the
+    kernel's fragment skip and must lie between the algorithmic and the dense count."""
+    sys.path.insert(0, ROOT)
+    import bench
+    rounds = [88, 161, 184, 187, 189, 197, 193, 196, 197, 193, 192, 23]          # T*, seed 1234
+    c = 0
+    alg = ex = dense = 0.0
+    for s_ in rounds:
+        alg += s_ * (2 * c + s_)
+        dense += 2 * s_ * (c + s_)
+        ex += bench.schur_executed_flops(c, s_, 1.0)
+        assert bench.schur_executed_flops(c, s_, 1.0, tri=False) >= 2 * s_ * (c + s_)      # row / k padding only adds
+        c += s_
+    assert c == 2000 and alg == 2000 ** 2                                          # N k^2 per unit column
+    assert alg < ex < dense
+    assert ex / alg < 1.05                                                         # staircase + padding: a few per cent
+    # s > 256 runs in row chunks; the skip applies inside each chunk
+    assert bench.schur_executed_flops(100, 300, 1.0) < bench.schur_executed_flops(100, 300, 1.0, tri=False)
