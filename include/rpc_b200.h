@@ -254,6 +254,13 @@ int rpc_kernel_rows_wsum(rpc_ctx *ctx, void *stream, const rpc_kernel_spec *spec
                          int d, int64_t ldx, const double *Xpiv, const double *pnorm, int s, int64_t ldp, const double *w,
                          double *out, int accumulate);
 
+/* Debug aid for bindings: counts the violations of the padding contract stated at the top of this file -- non-zero (or NaN)
+ * entries among the pad features [d, ldx) of the n real points, the pad points [n, n_pad) and, when diag != NULL, the pad
+ * entries of the residual diagonal -- and returns the count through the HOST pointer.  SYNCHRONISES the stream.  The Python host
+ * runs it on every operator it builds when RPC_B200_VALIDATE=1 is set. */
+int rpc_check_padding(rpc_ctx *ctx, void *stream, const double *X, int64_t n, int64_t n_pad, int d, int64_t ldx, const double *diag,
+                      int32_t *violations_host);
+
 /* Measurement aid (bench.py's roofline denominator): enqueues one launch of a pure DMMA.8x8x4 stream (one 256-thread CTA
  * per SM, 16 independent accumulator pairs per warp, `iters` rounds) and returns its flop count through the HOST pointer
  * flops_per_launch; the caller times it with CUDA events on `stream`.  Replaces no reference call site. */

@@ -140,6 +140,7 @@ _SIGNATURES = {
     "rpc_rows_dot": (_INT, [_P, _P, _P, _I64, _INT, _I64, _P, _P]),
     "rpc_rows_tdot": (_INT, [_P, _P, _P, _I64, _INT, _I64, _P, _P]),
     "rpc_chol_solve": (_INT, [_P, _P, _P, _I64, _INT, _P, _I64, _INT]),
+    "rpc_check_padding": (_INT, [_P, _P, _P, _I64, _I64, _INT, _I64, _P, C.POINTER(C.c_int32)]),
     "rpc_probe_fp64_peak": (_INT, [_P, _P, _INT, C.POINTER(_DBL)]),
     "rpc_simple_run": (_INT, [_P, _P, _INT, C.POINTER(KernelSpec), _P, _P, _INT, _I64, _P, _I64, _I64, _P, _P, _P, _INT, _INT, _P,
                               _I64, _P, _I64, _P, _I64]),

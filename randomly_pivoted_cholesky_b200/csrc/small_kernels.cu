@@ -36,6 +36,43 @@ extern "C" int rpc_kernel_diag(rpc_ctx *ctx, void *stream, double *diag, int64_t
     return 0;
 }
 
+// The padding contract of include/rpc_b200.h (pad points all-zero, pad features zero, pad diagonal entries 0) is what lets the
+// N-proportional kernels run over n_pad columns without edge checks.  This counts its violations (NaN counts as one).
+__global__ void __launch_bounds__(256) check_padding_kernel(const double *__restrict__ X, int64_t n, int64_t n_pad, int d, int64_t ldx,
+                                                            const double *__restrict__ diag, int32_t *__restrict__ bad) {
+    int local = 0;
+    const int64_t fp = ldx - d;                                       // pad features per point
+    const int64_t nfeat = n * fp, nrow = (n_pad - n) * ldx, ndiag = diag ? n_pad - n : 0;
+    for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < nfeat + nrow + ndiag; q += (int64_t)gridDim.x * 256) {
+        double v;
+        if (q < nfeat) v = X[(q / fp) * ldx + d + q % fp];           // feature pad of a real point
+        else if (q < nfeat + nrow) v = X[n * ldx + (q - nfeat)];     // a pad point
+        else v = diag[n + (q - nfeat - nrow)];                       // pad entries of the residual diagonal
+        local += !(v == 0.0);
+    }
+    if (local) atomicAdd(bad, local);
+}
+
+extern "C" int rpc_check_padding(rpc_ctx *ctx, void *stream, const double *X, int64_t n, int64_t n_pad, int d, int64_t ldx,
+                                 const double *diag, int32_t *violations_host) {
+    RPC_CHECK_ARG(ctx && X && violations_host, "null pointer");
+    RPC_CHECK_ARG(n >= 0 && n_pad >= n && d >= 1 && ldx >= d, "bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = rpc_flags_reserve(ctx, sizeof(int32_t));
+    if (rc) return rc;
+    RPC_CUDA(cudaMemsetAsync(ctx->flags, 0, sizeof(int32_t), st));
+    const int64_t total = n * (ldx - d) + (n_pad - n) * ldx + (diag ? n_pad - n : 0);
+    if (total > 0) {
+        int grid = (int)((total + 255) / 256);
+        if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+        check_padding_kernel<<<grid, 256, 0, st>>>(X, n, n_pad, d, ldx, diag, ctx->flags);
+        RPC_LAUNCHED(ctx);
+    }
+    RPC_CUDA(cudaMemcpyAsync(violations_host, ctx->flags, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    RPC_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
 // out (k_pad x ldo) = zero-padded transpose of in (m x d): out[f][j] = in[j][f]
 __global__ void transpose_pad_kernel(const double *__restrict__ in, int64_t ldi, int m, int d, double *__restrict__ out,
                                      int64_t ldo, int k_pad) {

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import numbers
+import os
 
 import numpy as np
 import torch
@@ -278,12 +279,24 @@ class KernelMatrix(AbstractPSDMatrix):
             check(self._ctx.lib.rpc_row_norms(self._ctx.handle, _stream(), _ptr(Xp), self.n_pad, self.d_pad, self.ldx,
                                               _ptr(self._xnorm)), "rpc_row_norms")
 
+        if os.environ.get("RPC_B200_VALIDATE", "0") == "1" and self.padding_violations() != 0:
+            raise RuntimeError("internal error: the padded point buffer violates the padding contract of include/rpc_b200.h")
+
         if isinstance(bandwidth, str):
             if info.world > 1:
                 raise NotImplementedError("'median' bandwidths need all pairwise distances: pass a float when sharded")
             bandwidth = self._median_bandwidth(bandwidth, kind)
         self.bandwidth = bandwidth
         self._spec = KernelSpec(kind, nu2, 1 if stab else 0, 0, float(bandwidth))
+
+    def padding_violations(self, diag=None):
+        """Number of entries that break the padding contract of include/rpc_b200.h (pad features / pad points / pad diagonal
+        entries must be zero: the N-proportional kernels run over n_pad columns without edge checks).  Synchronises."""
+        bad = C.c_int32(-1)
+        with torch.cuda.device(self.device):
+            check(self._ctx.lib.rpc_check_padding(self._ctx.handle, _stream(), _ptr(self._Xd), self.shard_info.n_loc, self.n_pad, self.d,
+                                                  self.ldx, _ptr(diag) if diag is not None else None, C.byref(bad)), "rpc_check_padding")
+        return int(bad.value)
 
     # matrix.py:168-176: median of ALL pairwise distances (zeros on the diagonal included)
     def _median_bandwidth(self, mode, kind):

@@ -776,3 +776,24 @@ def test_fused_kernel_times_vector(rpc, kernel, kw, d, m):
     base = torch.from_numpy(rng.standard_normal(A.n_pad)).to(A.device)
     acc = ops.kernel_weighted_sum(A, piv.X, piv.norm, m, wd, out=base.clone(), accumulate=True)
     assert relerr(acc[:n].cpu().numpy(), base[:n].cpu().numpy() + w @ Kb) <= 1e-12
+
+
+@pytest.mark.parametrize("kernel,n,d", [("gaussian", 1000, 5), ("laplace", 129, 12), ("matern", 256, 3)])
+def test_padding_contract_is_checkable(rpc, kernel, n, d):
+    """rpc_check_padding: the operators the host builds satisfy the padding contract of include/rpc_b200.h, and a binding that
+    breaks it (non-zero pad feature, pad point, pad diagonal entry, NaN) is caught."""
+    X = np.random.default_rng(n).standard_normal((n, d))
+    A = rpc.KernelMatrix(X, kernel=kernel, bandwidth=1.5, **({"nu": 1.5} if kernel == "matern" else {}))
+    diag = torch.zeros((A.n_pad,), dtype=torch.float64, device=A.device)
+    A._dev_diag_into(diag)
+    assert A.padding_violations(diag) == 0
+    if A.ldx > d:
+        A._Xd[3, d] = 1e-300
+        assert A.padding_violations() == 1
+        A._Xd[3, d] = 0.0
+    if A.n_pad > n:
+        A._Xd[n, 0] = float("nan")
+        diag[A.n_pad - 1] = 2.0
+        assert A.padding_violations(diag) == 2
+        A._Xd[n, 0] = 0.0
+        assert A.padding_violations() == 0
